@@ -1,0 +1,84 @@
+// sdumc_b200 — extern "C" entry points (include/sdumc_b200.h).
+#include "../../include/sdumc_b200.h"
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+namespace sdumc {
+const char* last_error();
+
+__global__ void frame_mask_kernel(DropKey key, uint32_t site, long rows, int cols, float* out) {
+  const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, 32-col chunk)
+  const int chunks = (cols + 31) / 32;
+  if (idx >= rows * chunks) return;
+  const long r = idx / chunks;
+  const int c = (int)(idx - r * chunks);
+  const int n0 = c * 32;
+  const U4 w = frame_mask_words(key, site, (uint32_t)r, (uint32_t)(n0 >> 7));
+  const int wsel = (n0 >> 5) & 3;
+  const uint32_t bits = wsel == 0 ? w.x : (wsel == 1 ? w.y : (wsel == 2 ? w.z : w.w));
+  for (int j = 0; j < 32 && n0 + j < cols; ++j) out[r * cols + n0 + j] = ((bits >> j) & 1u) ? 2.f : 0.f;
+}
+
+__global__ void elem_mask_kernel(DropKey key, uint32_t site, long n, uint32_t thr, float scale, float* out) {
+  const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  out[e] = elem_rand(key, site, (uint32_t)e) >= thr ? scale : 0.f;
+}
+}  // namespace sdumc
+
+using namespace sdumc;
+
+extern "C" {
+
+int sdumc_version(void) { return SDUMC_ABI_VERSION; }
+const char* sdumc_last_error(void) { return sdumc::last_error(); }
+
+int sdumc_gemm(const sdumc_gemm_desc* d, void* stream) {
+  SDUMC_CHECK_ARG(d != nullptr, "sdumc_gemm: null descriptor");
+  GemmShape sh{};
+  sh.M = d->M; sh.N = d->N; sh.K = d->K;
+  sh.a_mn = d->a_mn; sh.b_mn = d->b_mn;
+  sh.k_splits = d->k_splits;
+  sh.dbg_lbo = d->dbg_lbo; sh.dbg_sbo = d->dbg_sbo;
+  GemmEpi ep{};
+  ep.kind = d->epi_kind;
+  ep.bias = d->bias;
+  ep.act = d->act;
+  ep.gate = d->gate; ep.ld_gate = d->ld_gate; ep.gate_scale = d->gate_scale;
+  ep.drop_p = d->drop_p; ep.drop_site = d->drop_site;
+  ep.fmask_site = d->fmask_site;
+  ep.out_f32 = d->out_f32; ep.ld_f32 = d->ld_f32; ep.f32_mode = d->f32_mode;
+  ep.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16); ep.ld_bf16 = d->ld_bf16; ep.bf16_mode = d->bf16_mode;
+  ep.n_tgt = d->n_tgt;
+  for (int i = 0; i < 4; ++i) {
+    ep.tgt[i] = static_cast<__nv_bfloat16*>(d->tgt[i]);
+    ep.tgt_site[i] = d->tgt_site[i];
+  }
+  ep.qv = d->qv; ep.q_stride = d->q_stride; ep.nq = d->nq; ep.L = d->L; ep.scores = d->scores;
+  ep.key = DropKey{(uint32_t)(d->seed & 0xffffffffu), (uint32_t)(d->seed >> 32), d->step};
+  GemmOperand A{d->A, d->lda}, B{d->B, d->ldb};
+  return launch_gemm(A, B, sh, ep, d->tf32 != 0, d->block_n, d->max_ctas, static_cast<cudaStream_t>(stream));
+}
+
+int sdumc_frame_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t rows, int32_t cols, float* out,
+                     void* stream) {
+  SDUMC_CHECK_ARG(out && rows > 0 && cols > 0, "sdumc_frame_mask: bad arguments");
+  DropKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), step};
+  const long n = rows * ((cols + 31) / 32);
+  frame_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(key, site, rows, cols,
+                                                                                                 out);
+  SDUMC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int sdumc_elem_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t n, float p, float* out, void* stream) {
+  SDUMC_CHECK_ARG(out && n > 0 && p >= 0.f && p < 1.f, "sdumc_elem_mask: bad arguments");
+  DropKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), step};
+  elem_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      key, site, n, drop_threshold(p), 1.f / (1.f - p), out);
+  SDUMC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,438 @@
+// sdumc_b200 — the one tcgen05 GEMM of the library (sm_100a).
+//
+//   C[M,N] (+)= op(A)[M,K] * op(B)[K,N]      fp32 accumulation in TMEM
+//
+// * operands bf16 (kind::f16) or fp32 read as tf32 (kind::tf32), staged in shared memory by TMA
+//   (SWIZZLE_128B boxes) through a kStages-deep mbarrier ring;
+// * either operand may be K-major (reduction index contiguous: the nn.Linear forward case) or
+//   MN-major (reduction index strided: the dX = dY*W and dW = dY^T*X cases) — only the TMA box
+//   and the UMMA descriptor differ;
+// * persistent CTAs, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
+//   warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> HBM), accumulators
+//   double-buffered in TMEM (2 x kBlockN columns) so the epilogue of tile i overlaps the MMAs
+//   of tile i+1;
+// * split-K over the reduction for the weight-gradient shapes (fp32 atomics into the grad buffer).
+//
+// Epilogues (fused, selected at run time):
+//   generic : bias, ReLU/tanh, ReLU+dropout backward gate, element dropout, frame-mask multiply,
+//             fp32 store / += / atomicAdd, bf16 store / +=
+//   in-proj : bias, plain bf16 H plus up to 4 independently dropped copies (the X' of
+//             FRA2UTT_new / Cross_Attention of both passes; reference
+//             toolkit/models/wengnet_mosei_mult_views_text_missing.py:57,81)
+//   key-proj: bias + tanh + per-sample query dot products -> attention scores
+//             (reference :60-61 and :82-88), optional bf16 K for the backward pass
+#pragma once
+
+#include "common.cuh"
+
+namespace sdumc {
+
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
+enum : int { OUT_STORE = 0, OUT_ADD = 1, OUT_ATOMIC = 2 };
+enum : int { EPI_GENERIC = 0, EPI_INPROJ = 1, EPI_KEYPROJ = 2 };
+
+struct GemmEpi {
+  int kind;  // EPI_*
+  const float* bias;
+  int act;
+  const float* gate;  // fp32 [M, N] (ld_gate): v *= gate_scale * (gate > 0)
+  long ld_gate;
+  float gate_scale;
+  float drop_p;  // element dropout after activation, index e = r * N + n
+  uint32_t drop_site;
+  uint32_t fmask_site;  // != 0: v *= 2 * framebit(site, r, n)
+  float* out_f32;
+  long ld_f32;
+  int f32_mode;
+  __nv_bfloat16* out_bf16;
+  long ld_bf16;
+  int bf16_mode;
+  // EPI_INPROJ
+  int n_tgt;
+  __nv_bfloat16* tgt[4];
+  uint32_t tgt_site[4];
+  // EPI_KEYPROJ
+  const float* qv;  // [n_samples, nq, N] (q_stride = nq * N) or one shared [nq, N] (q_stride = 0)
+  long q_stride;
+  int nq;
+  int L;          // frames per sample: sample = row / L
+  float* scores;  // [M, nq]
+  DropKey key;
+};
+
+struct GemmShape {
+  int M, N, K;
+  int a_mn, b_mn;  // 0 = K-major, 1 = MN-major
+  int k_splits;
+  // debug overrides of the MN-major descriptor fields (0 = computed); see tests/test_gemm_gpu.py
+  uint32_t dbg_lbo, dbg_sbo;
+};
+
+template <int kBlockN>
+struct GemmCfg {
+  static constexpr int kBlockM = 128;
+  static constexpr int kRowBytes = 128;                      // one swizzle row
+  static constexpr int kABytes = kBlockM * kRowBytes;        // 16 KB
+  static constexpr int kBBytes = kBlockN * kRowBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kBlockN == 256) ? 4 : (kBlockN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * kBlockN < 32) ? 32 : 2 * kBlockN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kThreads = 256;
+};
+
+template <int kBlockN, bool kTF32>
+__global__ void __launch_bounds__(256, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const GemmShape sh, const GemmEpi ep) {
+  using Cfg = GemmCfg<kBlockN>;
+  constexpr int kElem = kTF32 ? 4 : 2;
+  constexpr int kBlockK = 128 / kElem;   // elements (K-major) == k rows (MN-major) per stage
+  constexpr int kUmmaK = 32 / kElem;     // 16 (bf16) / 8 (tf32)
+  constexpr int kPanel = 128 / kElem;    // MN elements per 128-byte swizzle row
+  constexpr uint32_t kFmt = kTF32 ? 2u : 1u;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
+  uint8_t* stage_base = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages]
+  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m_tiles = (sh.M + 127) / 128;
+  const int n_tiles = (sh.N + kBlockN - 1) / kBlockN;
+  const int nkb = (sh.K + kBlockK - 1) / kBlockK;
+  const int num_tiles = m_tiles * n_tiles * sh.k_splits;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int ks = t / (m_tiles * n_tiles);
+        const int mn = t - ks * (m_tiles * n_tiles);
+        const int m_blk = mn / n_tiles, n_blk = mn - m_blk * n_tiles;
+        const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
+        const int kb1 = (int)(((long)(ks + 1) * nkb) / sh.k_splits);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + Cfg::kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (!sh.a_mn) {
+            tma_load_2d(sa, &tmA, kb * kBlockK, m_blk * 128, &full_bar[stage]);
+          } else {
+#pragma unroll
+            for (int p = 0; p < 128 / kPanel; ++p)
+              tma_load_2d(sa + p * (kBlockK * 128), &tmA, m_blk * 128 + p * kPanel, kb * kBlockK,
+                          &full_bar[stage]);
+          }
+          if (!sh.b_mn) {
+            tma_load_2d(sb, &tmB, kb * kBlockK, n_blk * kBlockN, &full_bar[stage]);
+          } else {
+#pragma unroll
+            for (int p = 0; p < kBlockN / kPanel; ++p)
+              tma_load_2d(sb + p * (kBlockK * 128), &tmB, n_blk * kBlockN + p * kPanel, kb * kBlockK,
+                          &full_bar[stage]);
+          }
+          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    const uint32_t idesc = make_idesc(kFmt, (uint32_t)sh.a_mn, (uint32_t)sh.b_mn, (uint32_t)kBlockN);
+    const uint32_t mn_lbo = sh.dbg_lbo ? sh.dbg_lbo : (uint32_t)(kBlockK * 128);
+    const uint32_t mn_sbo = sh.dbg_sbo ? sh.dbg_sbo : 1024u;
+    const uint32_t a_lbo = sh.a_mn ? mn_lbo : 16u, a_sbo = sh.a_mn ? mn_sbo : 1024u;
+    const uint32_t b_lbo = sh.b_mn ? mn_lbo : 16u, b_sbo = sh.b_mn ? mn_sbo : 1024u;
+    // descriptor start-address advance per UMMA_K step, in 16-byte units
+    const uint32_t a_kstep = sh.a_mn ? (uint32_t)(kUmmaK * 128) >> 4 : 32u >> 4;
+    const uint32_t b_kstep = sh.b_mn ? (uint32_t)(kUmmaK * 128) >> 4 : 32u >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int ks = t / (m_tiles * n_tiles);
+      const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
+      const int kb1 = (int)(((long)(ks + 1) * nkb) / sh.k_splits);
+      mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBlockN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t da = make_smem_desc(sa, a_lbo, a_sbo);
+          const uint64_t db = make_smem_desc(sb, b_lbo, b_sbo);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            umma_ss<kTF32>(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc,
+                           (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
+          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue =====================
+    const int ew = warp & 3;  // TMEM lane quarter this warp may touch
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t drop_thr = drop_threshold(ep.drop_p);
+    const float drop_scale = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int ks = t / (m_tiles * n_tiles);
+      const int mn = t - ks * (m_tiles * n_tiles);
+      const int m_blk = mn / n_tiles, n_blk = mn - m_blk * n_tiles;
+      (void)ks;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const int r = m_blk * 128 + ew * 32 + lane;
+      const bool row_ok = r < sh.M;
+      const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN);
+
+      float sc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      const float* qrow = nullptr;
+      if (ep.kind == EPI_KEYPROJ && row_ok) qrow = ep.qv + (long)(r / ep.L) * ep.q_stride;
+      U4 tw[4];
+
+#pragma unroll 1
+      for (int c = 0; c < kBlockN / 32; ++c) {
+        uint32_t acc_r[32];
+        tmem_ld32(taddr + (uint32_t)(c * 32), acc_r);
+        tmem_ld_wait();
+        const int n0 = n_blk * kBlockN + c * 32;
+        if (!row_ok || n0 >= sh.N) continue;
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc_r[j]);
+        const bool full = (n0 + 32 <= sh.N);
+        if (ep.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < sh.N) v[j] += __ldg(ep.bias + n0 + j);
+        }
+        if (ep.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        } else if (ep.act == ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
+        }
+
+        if (ep.kind == EPI_INPROJ) {
+          // plain H
+          if (ep.out_bf16) {
+            __nv_bfloat16* dst = ep.out_bf16 + (long)r * ep.ld_bf16 + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&b0);
+              pk.y = *reinterpret_cast<uint32_t*>(&b1);
+              pk.z = *reinterpret_cast<uint32_t*>(&b2);
+              pk.w = *reinterpret_cast<uint32_t*>(&b3);
+              *reinterpret_cast<uint4*>(dst + j) = pk;
+            }
+          }
+          // dropped copies: word (n0 >> 5) & 3 of Philox(row, n0 >> 7, site, step)
+          if ((c & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              if (i < ep.n_tgt) tw[i] = frame_mask_words(ep.key, ep.tgt_site[i], (uint32_t)r, (uint32_t)(n0 >> 7));
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (i >= ep.n_tgt) break;
+            const int wsel = (n0 >> 5) & 3;
+            const uint32_t bits = wsel == 0 ? tw[i].x : (wsel == 1 ? tw[i].y : (wsel == 2 ? tw[i].z : tw[i].w));
+            __nv_bfloat16* dst = ep.tgt[i] + (long)r * ep.ld_bf16 + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float w[8];
+#pragma unroll
+              for (int u = 0; u < 8; ++u) w[u] = ((bits >> (j + u)) & 1u) ? 2.f * v[j + u] : 0.f;
+              uint4 pk;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(w[0], w[1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(w[2], w[3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(w[4], w[5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(w[6], w[7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&b0);
+              pk.y = *reinterpret_cast<uint32_t*>(&b1);
+              pk.z = *reinterpret_cast<uint32_t*>(&b2);
+              pk.w = *reinterpret_cast<uint32_t*>(&b3);
+              *reinterpret_cast<uint4*>(dst + j) = pk;
+            }
+          }
+          continue;
+        }
+
+        if (ep.kind == EPI_KEYPROJ) {
+          if (ep.out_bf16) {
+            __nv_bfloat16* dst = ep.out_bf16 + (long)r * ep.ld_bf16 + n0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 pk;
+              __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
+              __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
+              __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+              pk.x = *reinterpret_cast<uint32_t*>(&b0);
+              pk.y = *reinterpret_cast<uint32_t*>(&b1);
+              pk.z = *reinterpret_cast<uint32_t*>(&b2);
+              pk.w = *reinterpret_cast<uint32_t*>(&b3);
+              *reinterpret_cast<uint4*>(dst + j) = pk;
+            }
+            // the backward pass reads the bf16 K; score with the same rounded values
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+          }
+#pragma unroll
+          for (int q = 0; q < 7; ++q) {
+            if (q >= ep.nq) break;
+            const float4* qp = reinterpret_cast<const float4*>(qrow + (long)q * sh.N + n0);
+            float s = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 w4 = __ldg(qp + j);
+              s = fmaf(v[4 * j], w4.x, s);
+              s = fmaf(v[4 * j + 1], w4.y, s);
+              s = fmaf(v[4 * j + 2], w4.z, s);
+              s = fmaf(v[4 * j + 3], w4.w, s);
+            }
+            sc[q] += s;
+          }
+          continue;
+        }
+
+        // ---- generic ----
+        if (ep.gate) {
+          const float* g = ep.gate + (long)r * ep.ld_gate + n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (full || n0 + j < sh.N) v[j] = (__ldg(g + j) > 0.f) ? v[j] * ep.gate_scale : 0.f;
+        }
+        if (ep.drop_p > 0.f) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            // e = r * N + n0 + j is a multiple of 4 whenever N % 4 == 0 (checked on the host)
+            const uint32_t e = (uint32_t)r * (uint32_t)sh.N + (uint32_t)(n0 + j);
+            const U4 rw = philox4x32_10(e >> 2, 0x5D0Cu, ep.drop_site, ep.key.step, ep.key.seed_lo, ep.key.seed_hi);
+            v[j] = rw.x >= drop_thr ? v[j] * drop_scale : 0.f;
+            v[j + 1] = rw.y >= drop_thr ? v[j + 1] * drop_scale : 0.f;
+            v[j + 2] = rw.z >= drop_thr ? v[j + 2] * drop_scale : 0.f;
+            v[j + 3] = rw.w >= drop_thr ? v[j + 3] * drop_scale : 0.f;
+          }
+        }
+        if (ep.fmask_site) {
+          const U4 w4 = frame_mask_words(ep.key, ep.fmask_site, (uint32_t)r, (uint32_t)(n0 >> 7));
+          const int wsel = (n0 >> 5) & 3;
+          const uint32_t bits = wsel == 0 ? w4.x : (wsel == 1 ? w4.y : (wsel == 2 ? w4.z : w4.w));
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? 2.f * v[j] : 0.f;
+        }
+        if (ep.out_f32) {
+          float* dst = ep.out_f32 + (long)r * ep.ld_f32 + n0;
+          if (ep.f32_mode == OUT_ATOMIC) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (full || n0 + j < sh.N) atomicAdd(dst + j, v[j]);
+          } else if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (ep.f32_mode == OUT_ADD) {
+                const float4 old = *reinterpret_cast<const float4*>(dst + j);
+                o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+              }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < sh.N) dst[j] = (ep.f32_mode == OUT_ADD) ? dst[j] + v[j] : v[j];
+          }
+        }
+        if (ep.out_bf16) {
+          __nv_bfloat16* dst = ep.out_bf16 + (long)r * ep.ld_bf16 + n0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (full || n0 + j < sh.N) {
+              float o = v[j];
+              if (ep.bf16_mode == OUT_ADD) o += __bfloat162float(dst[j]);
+              dst[j] = __float2bfloat16_rn(o);
+            }
+          }
+        }
+      }
+      if (ep.kind == EPI_KEYPROJ && row_ok) {
+        float* srow = ep.scores + (long)r * ep.nq;
+#pragma unroll
+        for (int q = 0; q < 7; ++q)
+          if (q < ep.nq) srow[q] = sc[q];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// host side (gemm.cu)
+struct GemmOperand {
+  const void* ptr;
+  long ld;  // leading dimension in elements of the stored (row-major) matrix
+};
+// Launch C = op(A) op(B). `tf32` selects fp32 operands (else bf16). Returns 0 or an error code.
+int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& shape, const GemmEpi& epi, bool tf32,
+                int block_n /*0 = auto*/, int max_ctas /*0 = all SMs*/, cudaStream_t stream);
+
+}  // namespace sdumc
