@@ -175,6 +175,12 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
     SDUMC_CHECK_ARG(epi.ld_f32 % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.out_f32) & 15u) == 0,
                     "gemm: fp32 output must be 16-byte aligned with ld %% 4 == 0");
   if (epi.drop_p > 0.f) SDUMC_CHECK_ARG(sh.N % 4 == 0, "gemm: element dropout needs N %% 4 == 0");
+  if (epi.out_bf16)
+    SDUMC_CHECK_ARG(sh.N % 32 == 0 && epi.ld_bf16 % 8 == 0 && (reinterpret_cast<uintptr_t>(epi.out_bf16) & 15u) == 0,
+                    "gemm: bf16 output needs N %% 32 == 0, ld %% 8 == 0 and a 16-byte aligned base");
+  if (epi.bias) SDUMC_CHECK_ARG((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
+  if (epi.gate) SDUMC_CHECK_ARG(epi.ld_gate % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.gate) & 15u) == 0,
+                                "gemm: gate must be 16-byte aligned with ld %% 4 == 0");
   if (sh.k_splits > 1)
     SDUMC_CHECK_ARG(epi.kind == EPI_GENERIC && epi.f32_mode == OUT_ATOMIC && !epi.out_bf16 && !epi.bias &&
                         epi.act == ACT_NONE,

@@ -8,9 +8,9 @@
 //   MN-major (reduction index strided: the dX = dY*W and dW = dY^T*X cases) — only the TMA box
 //   and the UMMA descriptor differ;
 // * persistent CTAs, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-//   warp 2 = TMEM allocator, warps 4..7 = epilogue (TMEM -> registers -> HBM), accumulators
-//   double-buffered in TMEM (2 x kBlockN columns) so the epilogue of tile i overlaps the MMAs
-//   of tile i+1;
+//   warp 2 = TMEM allocator, warps 4..7 / 8..11 = two epilogue groups (TMEM -> registers -> smem
+//   staging -> coalesced 16-byte stores) that alternate tiles; accumulators double-buffered in
+//   TMEM (2 x kBlockN columns) so the epilogue of tile i overlaps the MMAs of tiles i+1, i+2;
 // * split-K over the reduction for the weight-gradient shapes (fp32 atomics into the grad buffer).
 //
 // Epilogues (fused, selected at run time):
@@ -68,6 +68,48 @@ struct GemmShape {
   uint32_t dbg_lbo, dbg_sbo;
 };
 
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+  const float lo = __uint_as_float(a << 16) + __uint_as_float(b << 16);
+  const float hi = __uint_as_float(a & 0xffff0000u) + __uint_as_float(b & 0xffff0000u);
+  return pack_bf16x2(lo, hi);
+}
+
+// Coalesced store of a 32-row x 32-column bf16 block owned row-per-lane (w = this lane's 32 values,
+// packed) through the warp's padded staging buffer: 4 conflict-free 128-bit smem writes per lane,
+// then each instruction stores eight full 64-byte row segments.  `dst` points at (row0, n0).
+template <int kRowWords>
+__device__ __forceinline__ void store_block_bf16(uint32_t* stg, const uint32_t (&w)[16], __nv_bfloat16* dst, long ld,
+                                                 int rows_valid, int lane, bool accumulate) {
+  uint4* mine = reinterpret_cast<uint4*>(stg + lane * kRowWords);
+  mine[0] = make_uint4(w[0], w[1], w[2], w[3]);
+  mine[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  mine[2] = make_uint4(w[8], w[9], w[10], w[11]);
+  mine[3] = make_uint4(w[12], w[13], w[14], w[15]);
+  __syncwarp();
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rr = it * 8 + (lane >> 2), q = lane & 3;
+    uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kRowWords + q * 4);
+    if (rr < rows_valid) {
+      uint4* g = reinterpret_cast<uint4*>(dst + (long)rr * ld + q * 8);
+      if (accumulate) {
+        const uint4 old = *g;
+        val.x = add_bf16x2(val.x, old.x);
+        val.y = add_bf16x2(val.y, old.y);
+        val.z = add_bf16x2(val.z, old.z);
+        val.w = add_bf16x2(val.w, old.w);
+      }
+      *g = val;
+    }
+  }
+  __syncwarp();
+}
+
 template <int kBlockN>
 struct GemmCfg {
   static constexpr int kBlockM = 128;
@@ -77,12 +119,15 @@ struct GemmCfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kBlockN == 256) ? 4 : (kBlockN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * kBlockN < 32) ? 32 : 2 * kBlockN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
-  static constexpr int kThreads = 256;
+  static constexpr int kEpiWarps = 8;                        // two groups of 4, alternating tiles
+  static constexpr int kStageRowWords = 20;                  // 16 payload words + pad: conflict-free 128-bit access
+  static constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowWords * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kThreads = 384;
 };
 
 template <int kBlockN, bool kTF32>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmShape sh, const GemmEpi ep) {
   using Cfg = GemmCfg<kBlockN>;
@@ -96,7 +141,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint32_t* staging = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
@@ -211,25 +257,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue =====================
-    const int ew = warp & 3;  // TMEM lane quarter this warp may touch
-    int acc = 0;
+    // ===================== epilogue: two groups of 4 warps, alternating tiles =====================
+    const int ew = warp & 3;          // TMEM lane quarter this warp may touch
+    const int grp = (warp - 4) >> 2;  // group g drains accumulator stage g (tiles with local index % 2 == g)
+    uint32_t* stg = staging + (warp - 4) * 32 * Cfg::kStageRowWords;
     uint32_t acc_phase = 0;
     const uint32_t drop_thr = drop_threshold(ep.drop_p);
     const float drop_scale = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int ks = t / (m_tiles * n_tiles);
-      const int mn = t - ks * (m_tiles * n_tiles);
+    int li = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++li) {
+      if ((li & 1) != grp) continue;
+      const int acc = grp;
+      const int mn = t % (m_tiles * n_tiles);
       const int m_blk = mn / n_tiles, n_blk = mn - m_blk * n_tiles;
-      (void)ks;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int r = m_blk * 128 + ew * 32 + lane;
+      const int r0 = m_blk * 128 + ew * 32;  // first row of this warp's slab
+      const int r = r0 + lane;
       const bool row_ok = r < sh.M;
+      const int rows_valid = sh.M - r0;      // may be <= 0 or > 32
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN);
 
       float sc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      const float* qrow = nullptr;
+      const float* qrow = ep.qv;
       if (ep.kind == EPI_KEYPROJ && row_ok) qrow = ep.qv + (long)(r / ep.L) * ep.q_stride;
       U4 tw[4];
 
@@ -239,15 +289,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tmem_ld32(taddr + (uint32_t)(c * 32), acc_r);
         tmem_ld_wait();
         const int n0 = n_blk * kBlockN + c * 32;
-        if (!row_ok || n0 >= sh.N) continue;
+        if (n0 >= sh.N) continue;  // warp-uniform
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc_r[j]);
         const bool full = (n0 + 32 <= sh.N);
         if (ep.bias) {
+          if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < sh.N) v[j] += __ldg(ep.bias + n0 + j);
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
+              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < sh.N) v[j] += __ldg(ep.bias + n0 + j);
+          }
         }
         if (ep.act == ACT_RELU) {
 #pragma unroll
@@ -258,22 +316,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
 
         if (ep.kind == EPI_INPROJ) {
-          // plain H
+          uint32_t w[16];
           if (ep.out_bf16) {
-            __nv_bfloat16* dst = ep.out_bf16 + (long)r * ep.ld_bf16 + n0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&b0);
-              pk.y = *reinterpret_cast<uint32_t*>(&b1);
-              pk.z = *reinterpret_cast<uint32_t*>(&b2);
-              pk.w = *reinterpret_cast<uint32_t*>(&b3);
-              *reinterpret_cast<uint4*>(dst + j) = pk;
-            }
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
+                                                  rows_valid, lane, false);
           }
           // dropped copies: word (n0 >> 5) & 3 of Philox(row, n0 >> 7, site, step)
           if ((c & 3) == 0) {
@@ -286,46 +334,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             if (i >= ep.n_tgt) break;
             const int wsel = (n0 >> 5) & 3;
             const uint32_t bits = wsel == 0 ? tw[i].x : (wsel == 1 ? tw[i].y : (wsel == 2 ? tw[i].z : tw[i].w));
-            __nv_bfloat16* dst = ep.tgt[i] + (long)r * ep.ld_bf16 + n0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float w[8];
-#pragma unroll
-              for (int u = 0; u < 8; ++u) w[u] = ((bits >> (j + u)) & 1u) ? 2.f * v[j + u] : 0.f;
-              uint4 pk;
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(w[0], w[1]);
-              __nv_bfloat162 b1 = __floats2bfloat162_rn(w[2], w[3]);
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(w[4], w[5]);
-              __nv_bfloat162 b3 = __floats2bfloat162_rn(w[6], w[7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&b0);
-              pk.y = *reinterpret_cast<uint32_t*>(&b1);
-              pk.z = *reinterpret_cast<uint32_t*>(&b2);
-              pk.w = *reinterpret_cast<uint32_t*>(&b3);
-              *reinterpret_cast<uint4*>(dst + j) = pk;
-            }
+            for (int j = 0; j < 16; ++j)
+              w[j] = pack_bf16x2(((bits >> (2 * j)) & 1u) ? 2.f * v[2 * j] : 0.f,
+                                 ((bits >> (2 * j + 1)) & 1u) ? 2.f * v[2 * j + 1] : 0.f);
+            store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.tgt[i] + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
+                                                  rows_valid, lane, false);
           }
           continue;
         }
 
         if (ep.kind == EPI_KEYPROJ) {
           if (ep.out_bf16) {
-            __nv_bfloat16* dst = ep.out_bf16 + (long)r * ep.ld_bf16 + n0;
+            uint32_t w[16];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint4 pk;
-              __nv_bfloat162 b0 = __floats2bfloat162_rn(v[j], v[j + 1]);
-              __nv_bfloat162 b1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-              __nv_bfloat162 b2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]);
-              __nv_bfloat162 b3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-              pk.x = *reinterpret_cast<uint32_t*>(&b0);
-              pk.y = *reinterpret_cast<uint32_t*>(&b1);
-              pk.z = *reinterpret_cast<uint32_t*>(&b2);
-              pk.w = *reinterpret_cast<uint32_t*>(&b3);
-              *reinterpret_cast<uint4*>(dst + j) = pk;
-            }
+            for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
+                                                  rows_valid, lane, false);
             // the backward pass reads the bf16 K; score with the same rounded values
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+            for (int j = 0; j < 16; ++j) {
+              v[2 * j] = __uint_as_float(w[j] << 16);
+              v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
+            }
           }
 #pragma unroll
           for (int q = 0; q < 7; ++q) {
@@ -346,11 +377,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
 
         // ---- generic ----
-        if (ep.gate) {
+        if (ep.gate && row_ok) {
           const float* g = ep.gate + (long)r * ep.ld_gate + n0;
+          if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || n0 + j < sh.N) v[j] = (__ldg(g + j) > 0.f) ? v[j] * ep.gate_scale : 0.f;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 g4 = __ldg(reinterpret_cast<const float4*>(g + j));
+              v[j] = g4.x > 0.f ? v[j] * ep.gate_scale : 0.f;
+              v[j + 1] = g4.y > 0.f ? v[j + 1] * ep.gate_scale : 0.f;
+              v[j + 2] = g4.z > 0.f ? v[j + 2] * ep.gate_scale : 0.f;
+              v[j + 3] = g4.w > 0.f ? v[j + 3] * ep.gate_scale : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + j < sh.N) v[j] = (__ldg(g + j) > 0.f) ? v[j] * ep.gate_scale : 0.f;
+          }
         }
         if (ep.drop_p > 0.f) {
 #pragma unroll
@@ -371,7 +413,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? 2.f * v[j] : 0.f;
         }
-        if (ep.out_f32) {
+        if (ep.out_f32 && row_ok) {
           float* dst = ep.out_f32 + (long)r * ep.ld_f32 + n0;
           if (ep.f32_mode == OUT_ATOMIC) {
 #pragma unroll
@@ -393,16 +435,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               if (n0 + j < sh.N) dst[j] = (ep.f32_mode == OUT_ADD) ? dst[j] + v[j] : v[j];
           }
         }
-        if (ep.out_bf16) {
-          __nv_bfloat16* dst = ep.out_bf16 + (long)r * ep.ld_bf16 + n0;
+        if (ep.out_bf16) {  // host guarantees N % 32 == 0 for bf16 outputs
+          uint32_t w[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (full || n0 + j < sh.N) {
-              float o = v[j];
-              if (ep.bf16_mode == OUT_ADD) o += __bfloat162float(dst[j]);
-              dst[j] = __float2bfloat16_rn(o);
-            }
-          }
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
+                                                rows_valid, lane, ep.bf16_mode == OUT_ADD);
         }
       }
       if (ep.kind == EPI_KEYPROJ && row_ok) {
@@ -414,7 +452,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      acc_phase ^= 1u;
     }
   }
 

@@ -159,6 +159,55 @@ def run_case(name: str) -> dict:
         res["tflops"] = 2.0 * M * N * K / ms / 1e9
         res["gbs"] = (A.numel() * 2 + B.numel() * 2 + M * N * (2 if ks == 1 else 4)) / ms / 1e6
         res["ok"] = True
+    elif kind == "timeepi":
+        # timeepi:inproj:<ntgt>:<K>  |  timeepi:keyproj:<nq>:<store_k>
+        sub = rest[0]
+        if sub == "inproj":
+            ntgt, K = int(rest[1]), int(rest[2])
+            M, N = 196608, 256
+            A, B = mk((M, K), torch.bfloat16), mk((N, K), torch.bfloat16)
+            bias = torch.randn(N, device=dev)
+            H = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+            tg = [torch.zeros(M, N, device=dev, dtype=torch.bfloat16) for _ in range(ntgt)]
+
+            def go():
+                ops.gemm(A, B, M=M, N=N, K=K, bias=bias, out_bf16=H if ntgt == 0 else None, epi_kind=ops.EPI_INPROJ,
+                         targets=tg, target_sites=list(range(1, ntgt + 1)), seed=5, step=1)
+            nbytes = A.numel() * 2 + M * N * 2 * max(1, ntgt)
+        else:
+            nq, store_k = int(rest[1]), int(rest[2])
+            L, G = 384, 256
+            M = 512 * L
+            K = G
+            N = G
+            A, B = mk((M, G), torch.bfloat16), (torch.randn(G, G, device=dev) * 0.06).bfloat16()
+            bias = torch.randn(G, device=dev) * 0.1
+            q = torch.randn(512 if nq > 1 else 1, nq, G, device=dev)
+            S = torch.zeros(M, nq, device=dev)
+            Kout = torch.zeros(M, G, device=dev, dtype=torch.bfloat16) if store_k else None
+
+            def go():
+                ops.gemm(A, B, M=M, N=G, K=G, bias=bias, act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kout,
+                         qv=q, q_stride=(nq * G if nq > 1 else 0), nq=nq, L=L, scores=S)
+            nbytes = A.numel() * 2 + (M * G * 2 if store_k else 0) + M * nq * 4
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+        for _ in range(3):
+            go()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            go()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[len(ts) // 2]
+        res["ms"] = ms
+        res["tflops"] = 2.0 * M * N * K / ms / 1e9
+        res["gbs"] = nbytes / ms / 1e6
+        res["ok"] = True
     else:
         raise ValueError(name)
     return res
@@ -174,17 +223,11 @@ CASES = [
     # MN-major B (dX = dY W)
     "mm:bf16:01:300:256:256:256:1",
     "mm:bf16:01:300:256:256:64:1",
-    "mm:f32:01:300:256:128:64:1",
     # MN-major A
     "mm:bf16:10:256:256:1000:128:1",
     # both MN-major (dW = dY^T X), with split-K
     "mm:bf16:11:256:1024:5000:256:1",
     "mm:bf16:11:256:1024:5000:256:8",
-    "mm:f32:11:256:896:1024:64:4",
-    "mm:f32:11:128:256:7168:64:1",
-    # alternates for the MN-major descriptor (only informative if the default fails)
-    "mm:bf16:01:300:256:256:256:1:1024:8192",
-    "mm:bf16:11:256:1024:5000:256:1:1024:8192",
     "inproj",
     "keyproj:1",
     "keyproj:7",
@@ -193,6 +236,13 @@ CASES = [
     "time:32768:256:4096:00:1",
     "time:256:1024:196608:11:37",
     "time:196608:256:256:00:1",
+    "timeepi:inproj:0:1024",
+    "timeepi:inproj:4:1024",
+    "timeepi:inproj:0:4096",
+    "timeepi:keyproj:1:0",
+    "timeepi:keyproj:1:1",
+    "timeepi:keyproj:7:0",
+    "timeepi:keyproj:7:1",
 ]
 
 
