@@ -392,7 +392,7 @@ def seeded_mask(seed: int, pass_idx: int, site_idx: int, shape, p: float) -> tor
     """Dropout mask (0 or 1/(1-p)) used by the golden vectors: injected into the reference's
     nn.Dropout by oracle/make_golden.py and regenerated by the tests."""
     g = torch.Generator().manual_seed(seed * 1000003 + pass_idx * 1009 + site_idx)
-    return (torch.rand(tuple(shape), generator=g) >= p).to(torch.float64) / (1.0 - p)
+    return (torch.rand(tuple(shape), generator=g, dtype=torch.float64) >= p).to(torch.float64) / (1.0 - p)
 
 
 def grad_fingerprint(g: torch.Tensor, n: int = 64) -> torch.Tensor:

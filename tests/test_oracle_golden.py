@@ -1,0 +1,121 @@
+"""The oracle (oracle/sdumc_oracle.py) against vectors produced by the reference modules
+themselves (oracle/make_golden.py, run in the build container).  CPU only."""
+import re
+
+import numpy as np
+import torch
+
+from oracle import sdumc_oracle as O
+
+DIMS = (96, 160, 64, 160)
+FRAMES = (20, 7, 13, 9)
+B, SEED, GAIN = 6, 4321, 1.3
+
+
+def _meta(golden):
+    return dict(s.split("=", 1) for s in golden["meta"])
+
+
+def _setup(gain=GAIN):
+    P = O.init_params(DIMS, seed=100, gain=gain, dtype=torch.float64)
+    batch = {k: v.double() for k, v in O.synth_batch(B, DIMS, FRAMES, seed=SEED).items()}
+    return P, batch
+
+
+def _close(a, b, tol=1e-9, floor=1e-30):
+    a = (a.detach() if torch.is_tensor(a) else torch.as_tensor(np.asarray(a))).double()
+    b = (b.detach() if torch.is_tensor(b) else torch.as_tensor(np.asarray(b))).double()
+    assert a.shape == b.shape, (a.shape, b.shape)
+    scale = max(float(b.abs().max()), floor)
+    err = float((a - b).abs().max()) / scale
+    assert err < tol, err
+
+
+def test_meta_matches(golden):
+    m = _meta(golden)
+    assert m["dims"] == str(DIMS) and m["frames"] == str(FRAMES) and m["B"] == str(B)
+
+
+def test_param_spec_matches_reference_state_dict(golden):
+    spec = O.param_spec(O.S0_DIMS)
+    assert [n for n, _, _ in spec] == list(golden["spec_names"])
+    assert [",".join(map(str, s)) for _, s, _ in spec] == list(golden["spec_shapes"])
+    assert sum(int(np.prod(s)) for _, s, _ in spec) == 4268884
+    assert sum(int(np.prod(s)) for _, s, live in spec if live) == 3857291
+    dead = {n for n, _, live in spec if not live}
+    assert dead == set(golden["eval/dead"])
+
+
+def _check_pass(golden, tag, out0, out1, terms, loss, grads):
+    _close(out0[0], golden[f"{tag}/vals0"])
+    _close(out1[0], golden[f"{tag}/vals1"])
+    for i, nm in enumerate(("fused", "rnc", "text_hidden", "cross_text")):
+        _close(out0[1][i], golden[f"{tag}/emb0_{nm}"])
+        _close(out1[1][i], golden[f"{tag}/emb1_{nm}"])
+    got_terms = torch.stack([terms[k] for k in ("mse_full", "mse_missing", "rmse_text_hidden", "rmse_cross_text",
+                                                "rmse_fused", "rnc")])
+    _close(got_terms, golden[f"{tag}/terms"])
+    _close(loss, golden[f"{tag}/loss"])
+    n = 0
+    for name, g in grads.items():
+        key = f"{tag}/grad/{name}"
+        if g is None:
+            assert key not in golden.files
+            continue
+        # floor: orgin_linear_change.2.bias has a mathematically zero gradient (cancels in f_i - f_j)
+        _close(O.grad_fingerprint(g), golden[key], tol=1e-8, floor=1e-6)
+        n += 1
+    assert n == 83  # live parameter tensors (106 - 23 dead)
+
+
+def test_eval_forward_loss_grads(golden):
+    P, b = _setup()
+    loss, terms, grads, (out0, out1) = O.loss_and_grads(P, b["audio"], b["text"], b["feat4"], b["video"], b["vals"])
+    _check_pass(golden, "eval", out0, out1, terms, loss, grads)
+
+
+def test_two_adam_steps(golden):
+    P, b = _setup()
+    st = {}
+    for _ in range(2):
+        O.train_step(P, st, b["audio"], b["text"], b["feat4"], b["video"], b["vals"], lr=1e-4, weight_decay=1e-5)
+    for name in P:
+        _close(O.grad_fingerprint(P[name]), golden[f"eval/param_after/{name}"], tol=1e-10)
+
+
+def test_train_mode_with_injected_dropout_masks(golden):
+    P, b = _setup(gain=float(_meta(golden)["gain_train"]))
+    sites = O.dropout_sites()
+    assert len(sites) == 35
+
+    def make_drop(pass_idx):
+        idx = {name: i for i, (name, _p) in enumerate(sites)}
+        ps = dict(sites)
+
+        def drop(site, x):
+            return x * O.seeded_mask(SEED, pass_idx, idx[site], x.shape, ps[site]).to(x.dtype)
+        return drop
+
+    loss, terms, grads, (out0, out1) = O.loss_and_grads(P, b["audio"], b["text"], b["feat4"], b["video"], b["vals"],
+                                                         drop0=make_drop(0), drop1=make_drop(1))
+    _check_pass(golden, "train", out0, out1, terms, loss, grads)
+
+
+def test_standalone_losses(golden):
+    feats = torch.from_numpy(golden["rnc/feats"])
+    for tag in ("cont", "tied"):
+        y = torch.from_numpy(golden[f"rnc/{tag}/labels"])
+        ff = feats.clone().requires_grad_(True)
+        l = O.rnc_loss(ff, y)
+        l.backward()
+        _close(l.detach(), golden[f"rnc/{tag}/loss"])
+        _close(ff.grad, golden[f"rnc/{tag}/grad"], tol=1e-8)
+    a, b = torch.from_numpy(golden["loss/a"]), torch.from_numpy(golden["loss/b"])
+    _close(O.mse_loss(a, b), golden["loss/mse3d"])
+    _close(O.rmse_loss(a, b), golden["loss/rmse3d"])
+    _close(O.mse_loss(a[:, 0, :1], b[:, 0, 0]), golden["loss/mse1d"])
+
+
+def test_lr_schedule():
+    # main_frame_val_text_missing.py:318-320
+    assert [round(O.lr_lambda(e), 6) for e in (0, 4, 5, 13, 14, 24)] == [0.2, 1.0, 1.0, 1.0, 0.9, 0.81]
