@@ -80,10 +80,225 @@ typedef struct sdumc_gemm_desc {
 
 int sdumc_gemm(const sdumc_gemm_desc* d, void* stream);
 
-/* Test hooks: materialise the dropout masks the kernels apply (values 0 or 1/(1-p)). */
+/* ------------------------------------------------------------------------------------------
+ * 2. Dropout RNG: Philox4x32-10 keyed by (seed, step); `site` numbers the dropout site.
+ *    Test hooks materialise the masks the kernels apply (values 0 or 1/(1-p)).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdumc_dropkey {
+  uint32_t seed_lo, seed_hi, step;
+} sdumc_dropkey;
+
 int sdumc_frame_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t rows, int32_t cols, float* out,
                      void* stream);
 int sdumc_elem_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t n, float p, float* out, void* stream);
+
+#if defined(__CUDACC__) && defined(SDUMC_INTERNAL)
+#define SDUMC_BF16 __nv_bfloat16
+#else
+#define SDUMC_BF16 uint16_t /* raw bfloat16 bits */
+#endif
+
+/* ------------------------------------------------------------------------------------------
+ * 3. Pooling attention, frame level (FRA2UTT_new.forward :56-68, Cross_Attention.forward :79-95)
+ *    forward : scores come from sdumc_gemm(SDUMC_EPI_KEYPROJ); this op does softmax over the L
+ *              frames of each sample, the weighted pooling and the output dropout.
+ *    backward: row-wise part (dS, dZ, dQp, db_in, value path); the dense parts are sdumc_gemm.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdumc_pool_fwd_args {
+  const SDUMC_BF16* X; /* X' [B*L,256] dropped frames, row pitch ldx */
+  int64_t ldx;
+  float* S;            /* [B*L,nq] in: scores, out: attention probabilities */
+  int32_t B, L, nq;
+  float alpha;         /* softmax_scale = 0.3 */
+  float* O_pre;        /* [B,nq,256] pooled output before the output dropout */
+  float* out;          /* out[b*out_stride_b + q*256 + g] */
+  int64_t out_stride_b;
+  SDUMC_BF16* out_bf16; /* optional copy, same indexing */
+  float drop_p;
+  uint32_t site;
+  sdumc_dropkey key;
+} sdumc_pool_fwd_args;
+int sdumc_pool_fwd(const sdumc_pool_fwd_args* a, void* stream);
+
+typedef struct sdumc_attn_bwd_args {
+  const SDUMC_BF16* X;
+  int64_t ldx;
+  const SDUMC_BF16* Kt; /* tanh(X' W_in^T + b) [B*L,256] */
+  int64_t ldk;
+  const float* P;       /* [B*L,nq] */
+  const float* dOut;    /* gradient of the dropped pooled output: dOut[b*dout_stride_b + q*256 + g] */
+  int64_t dout_stride_b;
+  const float* O_pre;
+  const float* Qp;      /* projected queries [B,nq,256] (qp_stride_b = nq*256) or shared context (0) */
+  int64_t qp_stride_b;
+  int32_t B, L, nq;
+  float alpha;
+  float out_drop_p;
+  uint32_t out_site;
+  SDUMC_BF16* dZ;       /* [B*L,256] */
+  int64_t lddz;
+  SDUMC_BF16* dH;       /* value-path gradient, masked by fmask_site */
+  int64_t lddh;
+  int32_t dh_mode;      /* 0 store, 1 accumulate */
+  uint32_t fmask_site;  /* 0: no input dropout */
+  float* dQp;           /* [B,nq,256] stored, or [nq,256] atomicAdd when qp_stride_b == 0 */
+  int64_t dqp_stride_b;
+  float* db;            /* [256] atomicAdd */
+  sdumc_dropkey key;
+} sdumc_attn_bwd_args;
+int sdumc_attn_bwd(const sdumc_attn_bwd_args* a, void* stream);
+
+int sdumc_cast_bf16(const float* src, SDUMC_BF16* dst, int64_t n, void* stream);
+int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, float* out256, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 4. Utterance-level glue between the MLP GEMMs (reference :301-320, :346-364) and the
+ *    ReLU/dropout backward.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdumc_act_bwd_args {
+  const float* dY; int64_t ld_dy;
+  const float* dY2; int64_t ld_dy2; /* optional second addend (fan-in of two gradients) or NULL */
+  const float* Y;  int64_t ld_y;   /* saved post-activation output or NULL */
+  float scale;                     /* 1/(1-p) of the dropout after the ReLU */
+  int32_t rows, cols;
+  SDUMC_BF16* dZ; int64_t ld_dz;
+  float* db;                       /* [cols] atomicAdd or NULL */
+} sdumc_act_bwd_args;
+int sdumc_act_bwd(const sdumc_act_bwd_args* a, void* stream);
+
+typedef struct sdumc_gate_fwd_args {
+  const float* a2; int64_t ld_a2;  /* attention_mlp output [R,256] */
+  const float* Wg; const float* bg;/* fc_att [3,256], [3] */
+  const float* h; int64_t ld_h;    /* [R,768] = (h_a|h_t|h_v) */
+  int32_t R;
+  float* g;                        /* [R,4] (3 used): raw gate, not softmaxed (:303-304) */
+  float* qin; int64_t qin_stride;  /* 4 x [R,256]: fused, audio+text, text+video, audio+video */
+} sdumc_gate_fwd_args;
+int sdumc_gate_fwd(const sdumc_gate_fwd_args* a, void* stream);
+
+typedef struct sdumc_gate_bwd_args {
+  const float* dqin; int64_t dqin_stride;
+  const float* dg_extra;           /* [R,4] gradient of g from the cross weighting (:346-349) */
+  const float* g;
+  const float* h; int64_t ld_h;
+  const float* a2; int64_t ld_a2;
+  const float* Wg;
+  int32_t R;
+  float* dh; int64_t ld_dh;        /* [R,768] += */
+  float* da2; int64_t ld_da2;      /* [R,256] store */
+  float* dWg; float* dbg;          /* atomicAdd */
+} sdumc_gate_bwd_args;
+int sdumc_gate_bwd(const sdumc_gate_bwd_args* a, void* stream);
+
+typedef struct sdumc_weight_fwd_args {
+  const float* c[3];               /* each [R,7,128] */
+  const float* g;                  /* [R,4] */
+  int32_t R;
+  float* W;                        /* [R,7,128] */
+} sdumc_weight_fwd_args;
+int sdumc_weight_fwd(const sdumc_weight_fwd_args* a, void* stream);
+
+typedef struct sdumc_weight_bwd_args {
+  const float* dW;
+  const float* c[3];
+  const float* g;
+  int32_t R;
+  const float* dc_extra[3];        /* optional external gradient added to dc[m] (e.g. the cross_text output) */
+  float* dc[3];                    /* store */
+  float* dg;                       /* [R,4] store */
+} sdumc_weight_bwd_args;
+int sdumc_weight_bwd(const sdumc_weight_bwd_args* a, void* stream);
+
+typedef struct sdumc_final_fwd_args {
+  const float* x2; int64_t ld_x2;  /* [R,128] */
+  const float* Wr; const float* br;/* cross_fc_att [7,128],[7] */
+  const float* W;                  /* [R,7,128] */
+  const float* Wv; const float* bv;/* fc_out_v [1,128],[1] */
+  int32_t R;
+  float* r;                        /* [R,8] (7 used) */
+  float* f;                        /* [R,128] */
+  float* vals;                     /* [R] */
+} sdumc_final_fwd_args;
+int sdumc_final_fwd(const sdumc_final_fwd_args* a, void* stream);
+
+typedef struct sdumc_final_bwd_args {
+  const float* dvals;              /* [R] or NULL */
+  const float* df_ext;             /* [R,128] or NULL */
+  const float* x2; int64_t ld_x2;
+  const float* Wr;
+  const float* W;
+  const float* r;
+  const float* f;
+  const float* Wv;
+  int32_t R;
+  float* dWc;                      /* [R,7,128] store */
+  float* dx2; int64_t ld_dx2;      /* [R,128] store */
+  float* dWr; float* dbr; float* dWv; float* dbv; /* atomicAdd */
+} sdumc_final_bwd_args;
+int sdumc_final_bwd(const sdumc_final_bwd_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 5. Losses (toolkit/utils/loss.py:19-51, :243-315; combination main...:137-148)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdumc_loss_sums_args {
+  const float* v0; const float* v1; const float* y;  /* [B] */
+  const float* th0; const float* th1;                /* [B,256] */
+  const float* ct0; const float* ct1;                /* [B,896] */
+  const float* f0; const float* f1;                  /* [B,128] */
+  int32_t B;
+  float* sums;                                       /* [8], atomicAdd of 5 sums of squares */
+} sdumc_loss_sums_args;
+int sdumc_loss_sums(const sdumc_loss_sums_args* a, void* stream);
+
+typedef struct sdumc_loss_finish_args {
+  sdumc_loss_sums_args in;
+  const float* sums;   /* [8] reduced over the whole (global) batch */
+  const float* rnc;    /* [1] global RnC value or NULL */
+  int32_t B_global;
+  float w[6];          /* full_mse, missing_mse, text_feat, text_query_feat, features, rnc */
+  float* terms;        /* [8]: 6 terms, total, 0 */
+  float* d_v0; float* d_v1;
+  float* d_th1;        /* teacher side detached (:148) */
+  float* d_ct1;        /* teacher side detached */
+  float* d_f0; float* d_f1;
+} sdumc_loss_finish_args;
+int sdumc_loss_finish(const sdumc_loss_finish_args* a, void* stream);
+
+int sdumc_sqdiff_sum(const float* a, const float* b, int64_t n, float* out_sum, void* stream);
+int sdumc_sqdiff_grad(const float* a, const float* b, int64_t n, const float* coef_dev, float* da,
+                      float* db_or_null, void* stream);
+
+typedef struct sdumc_rnc_args {
+  const float* feats;  /* [n,D], rows = (view-0 samples..., view-1 samples...) */
+  const float* labels; /* [n] */
+  int32_t n, D;
+  int32_t row_begin, row_end; /* anchors of this call (a data-parallel rank passes its slice) */
+  float temperature;
+  float* loss;         /* [1] atomicAdd */
+  float* dfeats;       /* [n,D] atomicAdd, or NULL for forward only */
+  float grad_scale;
+  void* workspace;
+  uint64_t workspace_bytes;
+} sdumc_rnc_args;
+uint64_t sdumc_rnc_workspace_bytes(int32_t n, int32_t D);
+int sdumc_rnc(const sdumc_rnc_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * 6. Optimiser: torch.optim.Adam semantics (main...:317), fused with the bf16 shadow refresh
+ * ------------------------------------------------------------------------------------------ */
+typedef struct sdumc_adam_args {
+  float* p; const float* g; float* m; float* v;
+  SDUMC_BF16* p_bf16; /* optional */
+  int64_t n;
+  float lr, beta1, beta2, eps, weight_decay, grad_scale;
+  int32_t step; /* 1-based */
+} sdumc_adam_args;
+int sdumc_adam(const sdumc_adam_args* a, void* stream);
+
+/* sizeof() of every argument block, for binding self-checks: index = order of declaration above
+ * (0 gemm_desc, 1 pool_fwd, 2 attn_bwd, 3 act_bwd, 4 gate_fwd, 5 gate_bwd, 6 weight_fwd, 7 weight_bwd,
+ *  8 final_fwd, 9 final_bwd, 10 loss_sums, 11 loss_finish, 12 rnc, 13 adam) */
+int sdumc_struct_size(int which);
 
 #ifdef __cplusplus
 }

@@ -1,8 +1,7 @@
 // sdumc_b200 — extern "C" entry points (include/sdumc_b200.h).
-#include "../../include/sdumc_b200.h"
-
 #include "common.cuh"
 #include "gemm.cuh"
+#include "kernels.h"
 
 namespace sdumc {
 const char* last_error();
@@ -79,6 +78,61 @@ int sdumc_elem_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t n, floa
       key, site, n, drop_threshold(p), 1.f / (1.f - p), out);
   SDUMC_CUDA(cudaGetLastError());
   return 0;
+}
+
+#define SDUMC_FWD(name, type, launcher)                                        \
+  int name(const type* a, void* stream) {                                     \
+    SDUMC_CHECK_ARG(a != nullptr, #name ": null argument block");             \
+    return launcher(*a, static_cast<cudaStream_t>(stream));                   \
+  }
+SDUMC_FWD(sdumc_pool_fwd, sdumc_pool_fwd_args, launch_pool_fwd)
+SDUMC_FWD(sdumc_attn_bwd, sdumc_attn_bwd_args, launch_attn_bwd)
+SDUMC_FWD(sdumc_act_bwd, sdumc_act_bwd_args, launch_act_bwd)
+SDUMC_FWD(sdumc_gate_fwd, sdumc_gate_fwd_args, launch_gate_fwd)
+SDUMC_FWD(sdumc_gate_bwd, sdumc_gate_bwd_args, launch_gate_bwd)
+SDUMC_FWD(sdumc_weight_fwd, sdumc_weight_fwd_args, launch_weight_fwd)
+SDUMC_FWD(sdumc_weight_bwd, sdumc_weight_bwd_args, launch_weight_bwd)
+SDUMC_FWD(sdumc_final_fwd, sdumc_final_fwd_args, launch_final_fwd)
+SDUMC_FWD(sdumc_final_bwd, sdumc_final_bwd_args, launch_final_bwd)
+SDUMC_FWD(sdumc_loss_sums, sdumc_loss_sums_args, launch_loss_sums)
+SDUMC_FWD(sdumc_loss_finish, sdumc_loss_finish_args, launch_loss_finish)
+SDUMC_FWD(sdumc_rnc, sdumc_rnc_args, launch_rnc)
+SDUMC_FWD(sdumc_adam, sdumc_adam_args, launch_adam)
+#undef SDUMC_FWD
+
+int sdumc_cast_bf16(const float* src, SDUMC_BF16* dst, int64_t n, void* stream) {
+  return launch_cast_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
+}
+int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, float* out256, void* stream) {
+  return launch_colsum_bf16(X, ld, rows, out256, static_cast<cudaStream_t>(stream));
+}
+int sdumc_sqdiff_sum(const float* a, const float* b, int64_t n, float* out_sum, void* stream) {
+  return launch_sqdiff_sum(a, b, n, out_sum, static_cast<cudaStream_t>(stream));
+}
+int sdumc_sqdiff_grad(const float* a, const float* b, int64_t n, const float* coef_dev, float* da, float* db_or_null,
+                      void* stream) {
+  return launch_sqdiff_grad(a, b, n, coef_dev, da, db_or_null, static_cast<cudaStream_t>(stream));
+}
+uint64_t sdumc_rnc_workspace_bytes(int32_t n, int32_t D) { return rnc_workspace_bytes(n, D); }
+
+int sdumc_struct_size(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(sdumc_gemm_desc);
+    case 1: return (int)sizeof(sdumc_pool_fwd_args);
+    case 2: return (int)sizeof(sdumc_attn_bwd_args);
+    case 3: return (int)sizeof(sdumc_act_bwd_args);
+    case 4: return (int)sizeof(sdumc_gate_fwd_args);
+    case 5: return (int)sizeof(sdumc_gate_bwd_args);
+    case 6: return (int)sizeof(sdumc_weight_fwd_args);
+    case 7: return (int)sizeof(sdumc_weight_bwd_args);
+    case 8: return (int)sizeof(sdumc_final_fwd_args);
+    case 9: return (int)sizeof(sdumc_final_bwd_args);
+    case 10: return (int)sizeof(sdumc_loss_sums_args);
+    case 11: return (int)sizeof(sdumc_loss_finish_args);
+    case 12: return (int)sizeof(sdumc_rnc_args);
+    case 13: return (int)sizeof(sdumc_adam_args);
+    default: return -1;
+  }
 }
 
 }  // extern "C"

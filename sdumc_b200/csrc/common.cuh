@@ -10,6 +10,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define SDUMC_INTERNAL 1
+#include "../../include/sdumc_b200.h"
+
 namespace sdumc {
 
 // ---------------------------------------------------------------------------------
@@ -79,9 +82,7 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, u
 // Dropout RNG state handed to every kernel that drops.  `step` separates
 // optimisation steps, `site` separates the dropout sites of the model
 // (see engine.h: site numbering), seed is the user seed.
-struct DropKey {
-  uint32_t seed_lo, seed_hi, step;
-};
+using DropKey = sdumc_dropkey;  // {seed_lo, seed_hi, step}
 
 // Frame-level p=0.5 dropout: one random bit per element.
 //   counter = (row, col >> 7, site, step), word = (col >> 5) & 3, bit = col & 31

@@ -1,0 +1,438 @@
+"""Forward / backward orchestration of the UMC model on the sm_100a kernels.
+
+Host-side mirror of WengnetMOSEIMultViewsTextMissing.forward
+(reference toolkit/models/wengnet_mosei_mult_views_text_missing.py:275-370) and of its autograd
+backward.  Everything that touches data is a kernel launch through the C ABI (sdumc_b200.ops);
+torch supplies device buffers and the stream only.  One call processes NP passes (1 for the drop-in
+nn.Module path, 2 = full + text-missing for the fused train / scoring step) as one batch of
+R = NP*B utterance rows, so every utterance-level GEMM of both passes is a single launch and the
+audio / video in-projections are computed once for both passes.
+
+Data layout in HBM (all row-major):
+  X_s   bf16 [B*L_s, D_s]   input stream s in {a, v, t0, t1}
+  Xf/Xc bf16 [B*L_s, 256]   dropped copies of H_s = X_s W^T + b for the FRA2UTT_new / Cross_Attention
+                            blocks of each (pass, modality) unit; in eval mode both alias H_s
+  K     bf16 [B*L_s, 256]   tanh key projections (kept only when a backward pass will follow)
+  S     fp32 [B*L_s, nq]    attention scores, overwritten by the softmax probabilities
+  utterance-level activations fp32 [R, .] with bf16 copies where a weight-gradient GEMM reads them
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import ops
+from .params import CROSS_MLPS, MODALITY_MLPS, QUERY_MLPS, ParamLayout
+
+G = 256
+NQ = 7
+FRAME_P = 0.5   # nn.Dropout(0.5) inside FRA2UTT_new / Cross_Attention (reference :54, :77)
+MLP_P = 0.3     # MLP() dropout (reference :187, :270)
+NUM_SMS = 148
+
+
+def dropout_site_names() -> List[str]:
+    """Dropout sites in the order the reference forward() visits its nn.Dropout modules."""
+    s: List[str] = []
+    for i in range(3):
+        s += [f"fra2utt_{i}.in", f"fra2utt_{i}.out"]
+    for m in (*MODALITY_MLPS, "attention_mlp"):
+        s += [f"{m}.0", f"{m}.1"]
+    for q in QUERY_MLPS:
+        s.append(f"{q}.0")
+    for i in range(3):
+        s += [f"cross_att_fra2utt_{i}.in", f"cross_att_fra2utt_{i}.out"]
+    for m in (*CROSS_MLPS, "cross_attention_mlp"):
+        s += [f"{m}.0", f"{m}.1"]
+    return s
+
+
+_SITE_INDEX = {n: i for i, n in enumerate(dropout_site_names())}
+
+
+def site_id(name: str, pass_idx: int = 0) -> int:
+    """RNG site of a dropout layer.  Frame-level and pooled-output sites are per pass (both passes index
+    the same rows); utterance-level MLP sites are shared, their rows r = pass*B + b already differ."""
+    return 1 + 64 * pass_idx + _SITE_INDEX[name]
+
+
+class Weights:
+    """Flat fp32 master, bf16 shadow and fp32 gradient buffers sharing one ParamLayout."""
+
+    def __init__(self, layout: ParamLayout, master: torch.Tensor, shadow: torch.Tensor,
+                 grads: Optional[torch.Tensor] = None):
+        self.layout, self.master, self.shadow, self.grads = layout, master, shadow, grads
+
+    def f32(self, name):
+        return self.layout.view(self.master, name)
+
+    def bf16(self, name):
+        return self.layout.view(self.shadow, name)
+
+    def grad(self, name):
+        return self.layout.view(self.grads, name)
+
+    def refresh_shadow(self):
+        ops.cast_bf16(self.master, self.shadow)
+
+
+@dataclass
+class Cfg:
+    B: int
+    n_pass: int                       # 1 or 2
+    frames: Dict[str, int]            # stream -> L   (streams: a, v, t0[, t1])
+    dropout: bool                     # train-mode dropout
+    need_grad: bool                   # keep what the backward pass needs
+    seed: int = 0
+    step: int = 0
+
+
+@dataclass
+class State:
+    cfg: Cfg
+    t: Dict[str, torch.Tensor] = field(default_factory=dict)   # named buffers
+
+
+def _unit_stream(p: int, m: int) -> str:
+    return ("a", f"t{p}", "v")[m]
+
+
+INPROJ = ("frame_dim_reshape_0", "frame_dim_reshape_1", "frame_dim_reshape_2")
+
+
+def _stream_mod(s: str) -> int:
+    return {"a": 0, "t": 1, "v": 2}[s[0]]
+
+
+def _ksplits(rows_k: int, m_gemm: int, n_gemm: int) -> int:
+    tiles = ((m_gemm + 127) // 128) * ((n_gemm + 255) // 256)
+    nkb = max(1, (rows_k + 63) // 64)
+    return max(1, min(nkb, (NUM_SMS + tiles - 1) // tiles))
+
+
+class Engine:
+    def __init__(self, layout: ParamLayout, device):
+        self.layout = layout
+        self.device = device
+
+    # ------------------------------------------------------------------ helpers
+    def _new(self, st: State, name: str, shape, dtype=torch.float32, zero=False):
+        fn = torch.zeros if zero else torch.empty
+        t = fn(shape, dtype=dtype, device=self.device)
+        st.t[name] = t
+        return t
+
+    def _linear_fwd(self, W: Weights, st: State, lname: str, x: torch.Tensor, y: torch.Tensor, *, relu: bool,
+                    drop_site: int = 0, y_bf16: Optional[torch.Tensor] = None):
+        """y = [dropout(relu(]x W^T + b[))]  as one tf32 tcgen05 GEMM (fp32 activations and master weights)."""
+        cfg = st.cfg
+        w = W.f32(lname + ".weight")
+        N, K = w.shape
+        p = MLP_P if (cfg.dropout and drop_site) else 0.0
+        ops.gemm(x, w, M=x.shape[0], N=N, K=K, bias=W.f32(lname + ".bias"),
+                 act=ops.ACT_RELU if relu else ops.ACT_NONE, drop_p=p, drop_site=drop_site, out_f32=y,
+                 out_bf16=y_bf16, seed=cfg.seed, step=cfg.step)
+
+    def _linear_bwd(self, W: Weights, st: State, lname: str, dY: torch.Tensor, x_bf16: torch.Tensor, *,
+                    Y: Optional[torch.Tensor], dropped: bool, dX: Optional[torch.Tensor], dX_mode=ops.OUT_STORE,
+                    dY2: Optional[torch.Tensor] = None):
+        """Backward of y = [drop(relu(]x W^T + b[))]: bias/weight gradients accumulate into W.grads."""
+        cfg = st.cfg
+        rows, N = dY.shape
+        K = W.f32(lname + ".weight").shape[1]
+        dZ = torch.empty(rows, N, dtype=torch.bfloat16, device=self.device)
+        scale = 1.0 / (1.0 - MLP_P) if (dropped and cfg.dropout) else 1.0
+        ops.act_bwd(dY, dZ, rows=rows, cols=N, Y=Y, scale=scale, db=W.grad(lname + ".bias"), dY2=dY2)
+        # dW[N,K] += dZ^T x : both operands MN-major (reduction over the rows), split-K with fp32 atomics
+        ops.gemm(dZ, x_bf16, M=N, N=K, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, N, K),
+                 out_f32=W.grad(lname + ".weight"), f32_mode=ops.OUT_ATOMIC)
+        if dX is not None:
+            # dX[rows,K] = dZ W : A K-major, B = W[N,K] read MN-major
+            ops.gemm(dZ, W.bf16(lname + ".weight"), M=rows, N=K, K=N, b_mn=True, out_f32=dX, f32_mode=dX_mode)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, W: Weights, inputs: Dict[str, torch.Tensor], cfg: Cfg) -> State:
+        st = State(cfg)
+        B, NP = cfg.B, cfg.n_pass
+        R = NP * B
+        dev = self.device
+        drop, keep = cfg.dropout, cfg.need_grad
+        seed, step = cfg.seed, cfg.step
+        streams = ["a", "v"] + [f"t{p}" for p in range(NP)]
+        units = [(p, m) for p in range(NP) for m in range(3)]
+
+        # 1. inputs -> bf16, in-projection (+ the dropped copies each attention block consumes)
+        for s in streams:
+            x = inputs[s]
+            L, D = cfg.frames[s], x.shape[-1]
+            assert x.shape[0] == B and x.shape[1] == L, f"stream {s}: expected [{B},{L},D], got {tuple(x.shape)}"
+            x2 = x.reshape(B * L, D)
+            if x2.dtype == torch.float32:
+                xb = torch.empty(B * L, D, dtype=torch.bfloat16, device=dev)
+                ops.cast_bf16(x2.contiguous(), xb)
+            else:
+                assert x2.dtype == torch.bfloat16
+                xb = x2.contiguous()
+            st.t[f"X.{s}"] = xb
+            mod = _stream_mod(s)
+            users = [(p, m) for (p, m) in units if _unit_stream(p, m) == s]
+            wname = INPROJ[mod]
+            if drop:
+                tg, sites = [], []
+                for (p, m) in users:
+                    for blk in ("fra2utt", "cross_att_fra2utt"):
+                        t = self._new(st, f"X{blk[0]}.{p}.{m}", (B * L, G), torch.bfloat16)
+                        tg.append(t)
+                        sites.append(site_id(f"{blk}_{m}.in", p))
+                ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
+                         epi_kind=ops.EPI_INPROJ, targets=tg, target_sites=sites, seed=seed, step=step)
+            else:
+                H = self._new(st, f"H.{s}", (B * L, G), torch.bfloat16)
+                ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
+                         epi_kind=ops.EPI_INPROJ, out_bf16=H)
+                for (p, m) in users:
+                    st.t[f"Xf.{p}.{m}"] = H
+                    st.t[f"Xc.{p}.{m}"] = H
+
+        # 2. FRA2UTT_new per unit: key projection + scores (GEMM epilogue), softmax + pooling
+        u_pool = [self._new(st, f"u.{m}", (R, G)) for m in range(3)]
+        u_pool_b = [self._new(st, f"u_bf16.{m}", (R, G), torch.bfloat16) for m in range(3)]
+        for (p, m) in units:
+            L = cfg.frames[_unit_stream(p, m)]
+            X = st.t[f"Xf.{p}.{m}"]
+            S = self._new(st, f"Sf.{p}.{m}", (B * L, 1))
+            Kt = self._new(st, f"Kf.{p}.{m}", (B * L, G), torch.bfloat16) if keep else None
+            pre = f"fra2utt_{m}"
+            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                     act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt,
+                     qv=W.f32(pre + ".attention_context_vector"), q_stride=0, nq=1, L=L, scores=S)
+            Opre = self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
+            ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=Opre, out=u_pool[m][p * B:(p + 1) * B], out_stride_b=G,
+                         out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
+                         site=site_id(pre + ".out", p), seed=seed, step=step)
+
+        # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
+        cat = self._new(st, "cat", (R, 3 * G))
+        cat_b = self._new(st, "cat_bf16", (R, 3 * G), torch.bfloat16)
+        for m, name in enumerate(MODALITY_MLPS):
+            h1 = self._new(st, f"h1.{m}", (R, G))
+            h1b = self._new(st, f"h1_bf16.{m}", (R, G), torch.bfloat16)
+            self._linear_fwd(W, st, name + ".0", u_pool[m], h1, relu=True, drop_site=site_id(name + ".0"), y_bf16=h1b)
+            self._linear_fwd(W, st, name + ".3", h1, cat[:, m * G:(m + 1) * G], relu=True,
+                             drop_site=site_id(name + ".1"), y_bf16=cat_b[:, m * G:(m + 1) * G])
+        a1 = self._new(st, "a1", (R, G))
+        a1b = self._new(st, "a1_bf16", (R, G), torch.bfloat16)
+        a2 = self._new(st, "a2", (R, G))
+        self._linear_fwd(W, st, "attention_mlp.0", cat, a1, relu=True, drop_site=site_id("attention_mlp.0"), y_bf16=a1b)
+        self._linear_fwd(W, st, "attention_mlp.3", a1, a2, relu=True, drop_site=site_id("attention_mlp.1"))
+        g = self._new(st, "g", (R, 4))
+        qin = self._new(st, "qin", (4, R, G))
+        ops.gate_fwd(a2, W.f32("fc_att.weight"), W.f32("fc_att.bias"), cat, R=R, g=g, qin=qin)
+        qin_b = self._new(st, "qin_bf16", (4, R, G), torch.bfloat16)
+        if keep:
+            ops.cast_bf16(qin, qin_b)
+        Q = self._new(st, "Q", (R, NQ * G))
+        Q_b = self._new(st, "Q_bf16", (R, NQ * G), torch.bfloat16)
+        for i, name in enumerate(QUERY_MLPS):
+            x = qin[i] if i < 4 else cat[:, (i - 4) * G:(i - 3) * G]
+            self._linear_fwd(W, st, name + ".0", x, Q[:, i * G:(i + 1) * G], relu=True, drop_site=site_id(name + ".0"),
+                             y_bf16=Q_b[:, i * G:(i + 1) * G])
+        Qp = [self._new(st, f"Qp.{m}", (R * NQ, G)) for m in range(3)]
+        for m in range(3):
+            self._linear_fwd(W, st, f"cross_att_fra2utt_{m}.query_proj", Q.view(R * NQ, G), Qp[m], relu=False)
+
+        # 4. Cross_Attention per unit
+        C = [self._new(st, f"C.{m}", (R * NQ, G)) for m in range(3)]
+        C_b = [self._new(st, f"C_bf16.{m}", (R * NQ, G), torch.bfloat16) for m in range(3)]
+        for (p, m) in units:
+            L = cfg.frames[_unit_stream(p, m)]
+            X = st.t[f"Xc.{p}.{m}"]
+            S = self._new(st, f"Sc.{p}.{m}", (B * L, NQ))
+            Kt = self._new(st, f"Kc.{p}.{m}", (B * L, G), torch.bfloat16) if keep else None
+            pre = f"cross_att_fra2utt_{m}"
+            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                     act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=Qp[m][p * B * NQ:(p + 1) * B * NQ],
+                     q_stride=NQ * G, nq=NQ, L=L, scores=S)
+            Opre = self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
+            ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=Opre, out=C[m][p * B * NQ:(p + 1) * B * NQ],
+                         out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
+                         drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step)
+
+        # 5. utterance chain B
+        c = []
+        for m, name in enumerate(CROSS_MLPS):
+            c1 = self._new(st, f"c1.{m}", (R * NQ, 256))
+            c1b = self._new(st, f"c1_bf16.{m}", (R * NQ, 256), torch.bfloat16)
+            cm = self._new(st, f"c.{m}", (R * NQ, 128))
+            self._linear_fwd(W, st, name + ".0", C[m], c1, relu=True, drop_site=site_id(name + ".0"), y_bf16=c1b)
+            self._linear_fwd(W, st, name + ".3", c1, cm, relu=True, drop_site=site_id(name + ".1"))
+            c.append(cm)
+        Wc = self._new(st, "Wc", (R, NQ * 128))
+        ops.weight_fwd(c, g, R=R, W=Wc)
+        Wc_b = self._new(st, "Wc_bf16", (R, NQ * 128), torch.bfloat16)
+        if keep:
+            ops.cast_bf16(Wc, Wc_b)
+        x1 = self._new(st, "x1", (R, 256))
+        x1b = self._new(st, "x1_bf16", (R, 256), torch.bfloat16)
+        x2 = self._new(st, "x2", (R, 128))
+        self._linear_fwd(W, st, "cross_attention_mlp.0", Wc, x1, relu=True, drop_site=site_id("cross_attention_mlp.0"),
+                         y_bf16=x1b)
+        self._linear_fwd(W, st, "cross_attention_mlp.3", x1, x2, relu=True, drop_site=site_id("cross_attention_mlp.1"))
+        r = self._new(st, "r", (R, 8))
+        f = self._new(st, "f", (R, 128))
+        vals = self._new(st, "vals", (R,))
+        ops.final_fwd(x2, W.f32("cross_fc_att.weight"), W.f32("cross_fc_att.bias"), Wc, W.f32("fc_out_v.weight"),
+                      W.f32("fc_out_v.bias"), R=R, r=r, f=f, vals=vals)
+        f_b = self._new(st, "f_bf16", (R, 128), torch.bfloat16)
+        if keep:
+            ops.cast_bf16(f, f_b)
+        o1 = self._new(st, "o1", (R, 64))
+        o1b = self._new(st, "o1_bf16", (R, 64), torch.bfloat16)
+        rnc = self._new(st, "rnc", (R, 64))
+        self._linear_fwd(W, st, "orgin_linear_change.0", f, o1, relu=True, y_bf16=o1b)
+        self._linear_fwd(W, st, "orgin_linear_change.2", o1, rnc, relu=False)
+        return st
+
+    @staticmethod
+    def outputs(st: State):
+        """(vals [NP,B,1], fused [NP,B,128], rnc [NP,B,64], text_hidden [NP,B,256] (strided), cross_text [NP,B,7,128])"""
+        cfg = st.cfg
+        NP, B = cfg.n_pass, cfg.B
+        t = st.t
+        return (t["vals"].view(NP, B, 1), t["f"].view(NP, B, 128), t["rnc"].view(NP, B, 64),
+                t["Q"].view(NP, B, NQ, G)[:, :, 5, :], t["c.1"].view(NP, B, NQ, 128))
+
+    # ------------------------------------------------------------------ backward
+    def backward(self, W: Weights, st: State, d_vals=None, d_fused=None, d_rnc=None, d_th=None, d_ct=None):
+        """Accumulates parameter gradients into W.grads.  d_* are fp32, contiguous, shaped like outputs()
+        flattened over passes ([R,...]); None = zero."""
+        cfg = st.cfg
+        assert cfg.need_grad, "forward was run without need_grad"
+        B, NP = cfg.B, cfg.n_pass
+        R = NP * B
+        t = st.t
+        dev = self.device
+        drop = cfg.dropout
+        seed, step = cfg.seed, cfg.step
+        units = [(p, m) for p in range(NP) for m in range(3)]
+        z = lambda *shape: torch.zeros(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+        e = lambda *shape: torch.empty(*shape, dtype=torch.float32, device=dev)  # noqa: E731
+
+        # B1. RnC head  rnc = Linear(64,64)(relu(Linear(128,64)(f)))
+        df = d_fused.reshape(R, 128).clone() if d_fused is not None else z(R, 128)
+        if d_rnc is not None:
+            d_o1 = e(R, 64)
+            self._linear_bwd(W, st, "orgin_linear_change.2", d_rnc.reshape(R, 64), t["o1_bf16"], Y=None, dropped=False,
+                             dX=d_o1)
+            self._linear_bwd(W, st, "orgin_linear_change.0", d_o1, t["f_bf16"], Y=t["o1"], dropped=False, dX=df,
+                             dX_mode=ops.OUT_ADD)
+        # B2. head + query gate
+        dWc = e(R, NQ * 128)
+        dx2 = e(R, 128)
+        dv = d_vals.reshape(R).contiguous() if d_vals is not None else None
+        ops.final_bwd(dv, df, t["x2"], W.f32("cross_fc_att.weight"), t["Wc"], t["r"], t["f"], W.f32("fc_out_v.weight"),
+                      R=R, dWc=dWc, dx2=dx2, dWr=W.grad("cross_fc_att.weight"), dbr=W.grad("cross_fc_att.bias"),
+                      dWv=W.grad("fc_out_v.weight"), dbv=W.grad("fc_out_v.bias"))
+        # B3. cross_attention_mlp
+        dx1 = e(R, 256)
+        self._linear_bwd(W, st, "cross_attention_mlp.3", dx2, t["x1_bf16"], Y=t["x2"], dropped=True, dX=dx1)
+        self._linear_bwd(W, st, "cross_attention_mlp.0", dx1, t["Wc_bf16"], Y=t["x1"], dropped=True, dX=dWc,
+                         dX_mode=ops.OUT_ADD)
+        # B4. gate-weighted sum
+        dc = [e(R * NQ, 128) for _ in range(3)]
+        dg_extra = e(R, 4)
+        extra = (None, d_ct.reshape(R * NQ, 128).contiguous() if d_ct is not None else None, None)
+        ops.weight_bwd(dWc, [t[f"c.{m}"] for m in range(3)], t["g"], R=R, dc=dc, dg=dg_extra, dc_extra=extra)
+        # B5. cross MLPs -> gradient of the (dropped) pooled cross-attention outputs
+        dC = []
+        for m, name in enumerate(CROSS_MLPS):
+            dc1 = e(R * NQ, 256)
+            self._linear_bwd(W, st, name + ".3", dc[m], t[f"c1_bf16.{m}"], Y=t[f"c.{m}"], dropped=True, dX=dc1)
+            dCm = e(R * NQ, G)
+            self._linear_bwd(W, st, name + ".0", dc1, t[f"C_bf16.{m}"], Y=t[f"c1.{m}"], dropped=True, dX=dCm)
+            dC.append(dCm)
+        # B6. Cross_Attention blocks
+        dH: Dict[str, torch.Tensor] = {}
+        dQp = [e(R * NQ, G) for _ in range(3)]
+        for (p, m) in units:
+            self._attn_block_bwd(W, st, p, m, "cross_att_fra2utt", NQ, dOut=dC[m][p * B * NQ:(p + 1) * B * NQ],
+                                 Qp=t[f"Qp.{m}"][p * B * NQ:(p + 1) * B * NQ], qp_stride=NQ * G,
+                                 dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH)
+        # B7. query projections -> dQ
+        dQ = e(R * NQ, G)
+        for m in range(3):
+            self._linear_bwd(W, st, f"cross_att_fra2utt_{m}.query_proj", dQp[m], t["Q_bf16"].view(R * NQ, G), Y=None,
+                             dropped=False, dX=dQ, dX_mode=ops.OUT_STORE if m == 0 else ops.OUT_ADD)
+        dQ = dQ.view(R, NQ * G)
+        # B8. 7 query MLPs
+        dqin = e(4, R, G)
+        dcat = e(R, 3 * G)
+        Qv = t["Q"]
+        dth = d_th.reshape(R, G).contiguous() if d_th is not None else None
+        for i, name in enumerate(QUERY_MLPS):
+            xb = t["qin_bf16"][i] if i < 4 else t["cat_bf16"][:, (i - 4) * G:(i - 3) * G]
+            dX = dqin[i] if i < 4 else dcat[:, (i - 4) * G:(i - 3) * G]
+            self._linear_bwd(W, st, name + ".0", dQ[:, i * G:(i + 1) * G], xb, Y=Qv[:, i * G:(i + 1) * G],
+                             dropped=True, dX=dX, dY2=dth if i == 5 else None)
+        # gate + partial fusions
+        da2 = e(R, G)
+        ops.gate_bwd(dqin, dg_extra, t["g"], t["cat"], t["a2"], W.f32("fc_att.weight"), R=R, dh=dcat, da2=da2,
+                     dWg=W.grad("fc_att.weight"), dbg=W.grad("fc_att.bias"))
+        da1 = e(R, G)
+        self._linear_bwd(W, st, "attention_mlp.3", da2, t["a1_bf16"], Y=t["a2"], dropped=True, dX=da1)
+        self._linear_bwd(W, st, "attention_mlp.0", da1, t["cat_bf16"], Y=t["a1"], dropped=True, dX=dcat,
+                         dX_mode=ops.OUT_ADD)
+        # B9. modality MLPs -> gradient of the (dropped) FRA2UTT outputs
+        du = []
+        for m, name in enumerate(MODALITY_MLPS):
+            dh1 = e(R, G)
+            self._linear_bwd(W, st, name + ".3", dcat[:, m * G:(m + 1) * G], t[f"h1_bf16.{m}"],
+                             Y=t["cat"][:, m * G:(m + 1) * G], dropped=True, dX=dh1)
+            dum = e(R, G)
+            self._linear_bwd(W, st, name + ".0", dh1, t[f"u_bf16.{m}"], Y=t[f"h1.{m}"], dropped=True, dX=dum)
+            du.append(dum)
+        # B10. FRA2UTT_new blocks
+        for (p, m) in units:
+            pre = f"fra2utt_{m}"
+            self._attn_block_bwd(W, st, p, m, "fra2utt", 1, dOut=du[m][p * B:(p + 1) * B],
+                                 Qp=W.f32(pre + ".attention_context_vector"), qp_stride=0,
+                                 dQp=W.grad(pre + ".attention_context_vector"), dH=dH)
+        # B11. in-projection weight / bias gradients (inputs carry no gradient)
+        for s, dHs in dH.items():
+            wname = INPROJ[_stream_mod(s)]
+            X = t[f"X.{s}"]
+            rows, D = X.shape
+            ops.gemm(dHs, X, M=G, N=D, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, G, D),
+                     out_f32=W.grad(wname + ".weight"), f32_mode=ops.OUT_ATOMIC)
+            ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
+
+    def _attn_block_bwd(self, W: Weights, st: State, p: int, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
+                        dH: Dict[str, torch.Tensor]):
+        cfg = st.cfg
+        t = st.t
+        B = cfg.B
+        s = _unit_stream(p, m)
+        L = cfg.frames[s]
+        tag = blk[0]  # 'f' or 'c'
+        pre = f"{blk}_{m}"
+        X = t[f"X{tag}.{p}.{m}"]
+        Kt = t[f"K{tag}.{p}.{m}"]
+        P = t[f"S{tag}.{p}.{m}"]
+        Opre = t[f"O{tag}_pre.{p}.{m}"]
+        dZ = torch.empty(B * L, G, dtype=torch.bfloat16, device=self.device)
+        first = s not in dH
+        if first:
+            dH[s] = torch.empty(B * L, G, dtype=torch.bfloat16, device=self.device)
+        fmask = site_id(pre + ".in", p) if cfg.dropout else 0
+        ops.attn_bwd(X, Kt, P, dOut, dout_stride_b=nq * G, O_pre=Opre, Qp=Qp, qp_stride_b=qp_stride, B=B, L=L, nq=nq,
+                     out_drop_p=FRAME_P if cfg.dropout else 0.0, out_site=site_id(pre + ".out", p), dZ=dZ, dH=dH[s],
+                     dh_mode=0 if first else 1, fmask_site=fmask, dQp=dQp, dqp_stride_b=nq * G,
+                     db=W.grad(pre + ".input_proj.bias"), seed=cfg.seed, step=cfg.step)
+        # dH += (dZ W_in) * M_in
+        ops.gemm(dZ, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, b_mn=True, fmask_site=fmask,
+                 out_bf16=dH[s], bf16_mode=ops.OUT_ADD, seed=cfg.seed, step=cfg.step)
+        # dW_in += dZ^T X'
+        ops.gemm(dZ, X, M=G, N=G, K=B * L, a_mn=True, b_mn=True, k_splits=_ksplits(B * L, G, G),
+                 out_f32=W.grad(pre + ".input_proj.weight"), f32_mode=ops.OUT_ATOMIC)

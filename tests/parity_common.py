@@ -1,0 +1,111 @@
+"""Shared helpers of the GPU parity tests: run the CUDA path and the oracle on the same seeded
+inputs / parameters / dropout masks and report normalised errors per tensor."""
+from __future__ import annotations
+
+import types
+from typing import Dict
+
+import torch
+
+from oracle import sdumc_oracle as O
+
+
+def nerr(got: torch.Tensor, ref: torch.Tensor, floor: float = 1e-12) -> float:
+    """max |got - ref| / max |ref|"""
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    return float((got - ref).abs().max() / ref.abs().max().clamp_min(floor))
+
+
+def build_model(dims, P: Dict[str, torch.Tensor], seed=100, device="cuda"):
+    from sdumc_b200.model import WengnetMOSEIMultViewsTextMissing
+    net = WengnetMOSEIMultViewsTextMissing(types.SimpleNamespace(input_dims=dims, seed=seed))
+    net.load_state_dict({k: v.float() for k, v in P.items()}, strict=True)
+    return net.to(device)
+
+
+def kernel_masks(net, B, frames_amv, pass_idx: int):
+    """The dropout masks the kernels applied in the forward that just ran (net._step), keyed by the
+    oracle's site names, shaped like the tensors the oracle drops."""
+    from sdumc_b200 import ops
+    from sdumc_b200.engine import FRAME_P, MLP_P, dropout_site_names, site_id
+    seed, step = net.dropout_seed, net._step
+    La, Lt, Lv = frames_amv
+    Ls = (La, Lt, Lv)
+    masks = {}
+    for name in dropout_site_names():
+        # the nn.Module path runs one pass per call: every site uses pass index 0 of that call
+        sid = site_id(name, 0)
+        if name.endswith(".in"):
+            m = int(name.split(".")[0][-1])
+            masks[name] = ops.frame_mask(seed, step, sid, B * Ls[m], 256).view(B, Ls[m], 256)
+        elif name.endswith(".out"):
+            nq = 1 if name.startswith("fra2utt") else 7
+            mk = ops.elem_mask(seed, step, sid, B * nq * 256, FRAME_P).view(B, nq, 256)
+            masks[name] = mk[:, 0] if nq == 1 else mk
+        else:
+            base, idx = name.rsplit(".", 1)
+            seven = base.startswith("cross_") and base.endswith("_mlp") and base not in ("cross_attention_mlp",) \
+                and "query" not in base
+            width = {"cross_audio_mlp": (256, 128), "cross_text_mlp": (256, 128), "cross_video_mlp": (256, 128),
+                     "cross_attention_mlp": (256, 128)}.get(base, (256, 256))[int(idx)]
+            rows = B * 7 if seven else B
+            mk = ops.elem_mask(seed, step, sid, rows * width, MLP_P).view(rows, width)
+            masks[name] = mk.view(B, 7, width) if seven else mk
+    return {k: v.double().cpu() for k, v in masks.items()}
+
+
+def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda", loss_w=None):
+    """Returns dict of normalised errors: outputs of both passes, the 6 loss terms, every live gradient."""
+    from sdumc_b200.losses import MSELoss, RMSELoss, RnCLoss
+    P = O.init_params(dims, seed=100, gain=gain, dtype=torch.float64)
+    batch = O.synth_batch(B, dims, frames, seed=data_seed)
+    # the CUDA path stores its inputs as bf16: hand the oracle the same rounded values
+    b64 = {k: (v.bfloat16().double() if k != "vals" else v.double()) for k, v in batch.items()}
+    P_bf = {k: v for k, v in P.items()}
+    net = build_model(dims, P, device=device)
+    net.train(train)
+    dev = {k: v.bfloat16().float().to(device) if k != "vals" else v.to(device) for k, v in batch.items()}
+
+    La, Lt, Lv, L4 = frames
+    v0, e0 = net([dev["audio"], dev["text"], dev["video"], False])
+    masks0 = kernel_masks(net, B, (La, Lt, Lv), 0) if train else None
+    v1, e1 = net([dev["audio"], dev["feat4"], dev["video"], True])
+    masks1 = kernel_masks(net, B, (La, L4, Lv), 1) if train else None
+
+    w = {**O.DEFAULT_LOSS_W, **(loss_w or {})}
+    mse, rmse, rnc = MSELoss(), RMSELoss(), RnCLoss()
+    f0, r0, th0, ct0 = e0
+    f1, r1, th1, ct1 = e1
+    terms = [mse(v0, dev["vals"]), mse(v1, dev["vals"]), rmse(th1, th0.detach()), rmse(ct1, ct0.detach()),
+             rmse(f1, f0), rnc(torch.stack((r0, r1), dim=1), dev["vals"].unsqueeze(1))]
+    loss = (w["full_mse_loss_w"] * terms[0] + w["missing_mse_loss_w"] * terms[1] + w["text_feat_loss_w"] * terms[2]
+            + w["text_query_feat_loss_w"] * terms[3] + w["features_loss_w"] * terms[4] + w["rnc_loss_w"] * terms[5])
+    loss.backward()
+    torch.cuda.synchronize()
+
+    d0 = O.make_drop_from_masks(masks0) if train else None
+    d1 = O.make_drop_from_masks(masks1) if train else None
+    oloss, oterms, ograds, (o0, o1) = O.loss_and_grads(P_bf, b64["audio"], b64["text"], b64["feat4"], b64["video"],
+                                                       b64["vals"], w, d0, d1)
+    res = {}
+    for tag, (v, e), (ov, oe) in (("p0", (v0, e0), o0), ("p1", (v1, e1), o1)):
+        res[f"{tag}/vals"] = nerr(v, ov)
+        for nm, a, b in zip(("fused", "rnc", "text_hidden", "cross_text"), e, oe):
+            res[f"{tag}/{nm}"] = nerr(a, b)
+    for nm, a, key in zip(("mse_full", "mse_missing", "rmse_text_hidden", "rmse_cross_text", "rmse_fused", "rnc"),
+                          terms, ("mse_full", "mse_missing", "rmse_text_hidden", "rmse_cross_text", "rmse_fused",
+                                  "rnc")):
+        res[f"term/{nm}"] = nerr(a.reshape(()), oterms[key].reshape(()))
+    res["loss"] = nerr(loss.reshape(()), oloss.reshape(()))
+    params = dict(net.named_parameters())
+    gmax = max(float(g.abs().max()) for g in ograds.values() if g is not None)
+    for name, og in ograds.items():
+        p = params[name]
+        if og is None:
+            assert p.grad is None or float(p.grad.abs().max()) == 0.0, f"dead parameter {name} received a gradient"
+            continue
+        assert p.grad is not None, f"{name}: no gradient"
+        # tensors whose true gradient is (numerically) zero are compared against the global scale
+        res[f"grad/{name}"] = nerr(p.grad, og, floor=1e-6 * gmax)
+    return res
