@@ -28,8 +28,7 @@ class _Node(nn.Module):
 
 class _UMCFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, audio, text, video, *params):
-        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+    def forward(ctx, module, need_grad, audio, text, video, *params):
         W = module._weights()
         B = audio.shape[0]
         cfg = Cfg(B=B, n_pass=1, frames={"a": audio.shape[1], "t0": text.shape[1], "v": video.shape[1]},
@@ -52,7 +51,7 @@ class _UMCFunction(torch.autograd.Function):
         module._engine.backward(W, st, d_vals=c(d_vals), d_fused=c(d_fused), d_rnc=c(d_rnc), d_th=c(d_th), d_ct=c(d_ct))
         grads = [layout.view(W.grads, n) if is_live(n) else None for n in layout.names]
         ctx.st = None
-        return (None, None, None, None, *grads)
+        return (None, None, None, None, None, *grads)
 
 
 class WengnetMOSEIMultViewsTextMissing(nn.Module):
@@ -153,7 +152,9 @@ class WengnetMOSEIMultViewsTextMissing(nn.Module):
             raise RuntimeError(f"model is on {W.master.device}, batch on {audio.device}")
         W.refresh_shadow()
         params: List[torch.Tensor] = [self._named_param_dict()[n] for n in self.layout.names]
-        vals, fused, rnc, th, ct = _UMCFunction.apply(self, audio, text, video, *params)
+        # (inside autograd.Function.forward grad mode is always off, so decide here)
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        vals, fused, rnc, th, ct = _UMCFunction.apply(self, need_grad, audio, text, video, *params)
         return vals, [fused, rnc, th, ct]
 
 
