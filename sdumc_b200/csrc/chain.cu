@@ -37,9 +37,7 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(ActBwdArgs a) {
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(a.dZ + (long)r * a.ld_dz + c) = pk;
-      // bias gradient from the rounded values the GEMMs see
-      acc[0] += __low2float(lo); acc[1] += __high2float(lo);
-      acc[2] += __low2float(hi); acc[3] += __high2float(hi);
+      acc[0] += z[0]; acc[1] += z[1]; acc[2] += z[2]; acc[3] += z[3];
     }
     if (a.db) {
 #pragma unroll

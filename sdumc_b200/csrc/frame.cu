@@ -232,8 +232,6 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       dZ[j] = dK[j] * (1.f - k[j] * k[j]);
-      // accumulate the bias gradient from the bf16-rounded value the GEMMs will consume
-      dZ[j] = __bfloat162float(__float2bfloat16_rn(dZ[j]));
       db_acc[j] += dZ[j];
     }
     *reinterpret_cast<uint4*>(a.dZ + row * a.lddz + g0) = pack8(dZ);
