@@ -17,6 +17,32 @@ def nerr(got: torch.Tensor, ref: torch.Tensor, floor: float = 1e-12) -> float:
     return float((got - ref).abs().max() / ref.abs().max().clamp_min(floor))
 
 
+def _r16(x):
+    return x.float().bfloat16().to(x.dtype)
+
+
+class _LinearBf16Bwd(torch.autograd.Function):
+    """Exact forward; backward with the rounding points of the CUDA chain backward: dZ, the saved input and
+    the weight enter the two backward GEMMs as bf16, products accumulate exactly, the bias gradient is summed
+    unrounded."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return x @ w.t() + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, w = ctx.saved_tensors
+        dz = _r16(dy)
+        dz2, x2 = dz.reshape(-1, dz.shape[-1]), _r16(x).reshape(-1, x.shape[-1])
+        return (dz @ _r16(w)), dz2.t() @ x2, dy.reshape(-1, dy.shape[-1]).sum(0)
+
+
+def emu_linear(P, name, x):
+    return _LinearBf16Bwd.apply(x, P[f"{name}.weight"], P[f"{name}.bias"])
+
+
 def build_model(dims, P: Dict[str, torch.Tensor], seed=100, device="cuda"):
     from sdumc_b200.model import WengnetMOSEIMultViewsTextMissing
     net = WengnetMOSEIMultViewsTextMissing(types.SimpleNamespace(input_dims=dims, seed=seed))
@@ -55,7 +81,7 @@ def kernel_masks(net, B, frames_amv, pass_idx: int):
     return {k: v.double().cpu() for k, v in masks.items()}
 
 
-def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda", loss_w=None):
+def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda", loss_w=None, emulate=False):
     """Returns dict of normalised errors: outputs of both passes, the 6 loss terms, every live gradient."""
     from sdumc_b200.losses import MSELoss, RMSELoss, RnCLoss
     P = O.init_params(dims, seed=100, gain=gain, dtype=torch.float64)
@@ -87,7 +113,7 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
     d0 = O.make_drop_from_masks(masks0) if train else None
     d1 = O.make_drop_from_masks(masks1) if train else None
     oloss, oterms, ograds, (o0, o1) = O.loss_and_grads(P_bf, b64["audio"], b64["text"], b64["feat4"], b64["video"],
-                                                       b64["vals"], w, d0, d1)
+                                                       b64["vals"], w, d0, d1, emu_linear if emulate else None)
     res = {}
     for tag, (v, e), (ov, oe) in (("p0", (v0, e0), o0), ("p1", (v1, e1), o1)):
         res[f"{tag}/vals"] = nerr(v, ov)

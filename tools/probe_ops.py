@@ -16,7 +16,7 @@ G = 256
 
 
 def nerr(a, b):
-    a, b = a.detach().double(), b.detach().double()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
 
 
