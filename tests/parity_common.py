@@ -81,8 +81,13 @@ def kernel_masks(net, B, frames_amv, pass_idx: int):
     return {k: v.double().cpu() for k, v in masks.items()}
 
 
-def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda", loss_w=None, emulate=False):
-    """Returns dict of normalised errors: outputs of both passes, the 6 loss terms, every live gradient."""
+def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda", loss_w=None, emulate=False,
+               cotangent=False):
+    """Returns dict of normalised errors: outputs of both passes, the 6 loss terms, every live gradient.
+
+    cotangent=True replaces the distillation loss by sum_p <output_p, C_p> with fixed random cotangents C:
+    the vector-Jacobian product of the model alone (the RMSE / RnC terms are direction-like functions of
+    differences of nearly equal features at initialisation and amplify forward rounding noise)."""
     from sdumc_b200.losses import MSELoss, RMSELoss, RnCLoss
     P = O.init_params(dims, seed=100, gain=gain, dtype=torch.float64)
     batch = O.synth_batch(B, dims, frames, seed=data_seed)
@@ -100,6 +105,36 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
     masks1 = kernel_masks(net, B, (La, L4, Lv), 1) if train else None
 
     w = {**O.DEFAULT_LOSS_W, **(loss_w or {})}
+    d0 = O.make_drop_from_masks(masks0) if train else None
+    d1 = O.make_drop_from_masks(masks1) if train else None
+    if cotangent:
+        g = torch.Generator().manual_seed(data_seed + 17)
+        outs_dev = [v0, *e0, v1, *e1]
+        cts = [torch.randn(tuple(t.shape), generator=g, dtype=torch.float64) for t in outs_dev]
+        loss = sum((t * c.float().to(device)).sum() for t, c in zip(outs_dev, cts))
+        loss.backward()
+        torch.cuda.synchronize()
+        leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
+        lin = emu_linear if emulate else None
+        o0 = O.forward(leaves, b64["audio"], b64["text"], b64["video"], d0, lin)
+        o1 = O.forward(leaves, b64["audio"], b64["feat4"], b64["video"], d1, lin)
+        outs_ref = [o0[0], *o0[1], o1[0], *o1[1]]
+        oloss = sum((t * c).sum() for t, c in zip(outs_ref, cts))
+        names = list(leaves)
+        gs = torch.autograd.grad(oloss, [leaves[k] for k in names], allow_unused=True)
+        ograds = dict(zip(names, gs))
+        res = {"loss": nerr(loss.reshape(()), oloss.reshape(()))}
+        for tag, (v, e), (ov, oe) in (("p0", (v0, e0), o0), ("p1", (v1, e1), o1)):
+            res[f"{tag}/vals"] = nerr(v, ov)
+            for nm, a, b in zip(("fused", "rnc", "text_hidden", "cross_text"), e, oe):
+                res[f"{tag}/{nm}"] = nerr(a, b)
+        params = dict(net.named_parameters())
+        gmax = max(float(x.abs().max()) for x in ograds.values() if x is not None)
+        for name, og in ograds.items():
+            if og is None:
+                continue
+            res[f"grad/{name}"] = nerr(params[name].grad, og, floor=1e-6 * gmax)
+        return res
     mse, rmse, rnc = MSELoss(), RMSELoss(), RnCLoss()
     f0, r0, th0, ct0 = e0
     f1, r1, th1, ct1 = e1
@@ -110,8 +145,6 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
     loss.backward()
     torch.cuda.synchronize()
 
-    d0 = O.make_drop_from_masks(masks0) if train else None
-    d1 = O.make_drop_from_masks(masks1) if train else None
     oloss, oterms, ograds, (o0, o1) = O.loss_and_grads(P_bf, b64["audio"], b64["text"], b64["feat4"], b64["video"],
                                                        b64["vals"], w, d0, d1, emu_linear if emulate else None)
     res = {}

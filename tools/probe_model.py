@@ -16,6 +16,12 @@ CASES = {
     "small_train": dict(dims=(96, 160, 64, 160), frames=(20, 7, 13, 9), B=6, gain=1.0, train=True),
     "s0_eval": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=False),
     "s0_train": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=True),
+    "s0_eval_ct": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=False,
+                       cotangent=True),
+    "s0_train_ct": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=True,
+                        cotangent=True),
+    "small_eval_ct": dict(dims=(96, 160, 64, 160), frames=(20, 7, 13, 9), B=6, gain=1.0, train=False, cotangent=True),
+    "small_train_ct": dict(dims=(96, 160, 64, 160), frames=(20, 7, 13, 9), B=6, gain=1.0, train=True, cotangent=True),
     "s0_eval_emu": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=False,
                         emulate=True),
     "s0_eval_b64": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=64, gain=1.0, train=False),
