@@ -139,18 +139,21 @@ def _mlp(P: Params, name: str, x: torch.Tensor, n_layers: int, drop: DropFn, lin
 
 
 def pool_attention(P: Params, prefix: str, H: torch.Tensor, queries: Optional[torch.Tensor],
-                   drop: DropFn, lin=None) -> Tuple[torch.Tensor, torch.Tensor]:
+                   drop: DropFn, lin=None, rnd=None) -> Tuple[torch.Tensor, torch.Tensor]:
     """FRA2UTT_new.forward (:56-68, queries=None) and Cross_Attention.forward (:79-95).
 
     H [B,L,G]; queries [B,Nq,G] or None.  Returns (out [B,Nq,G] (or [B,G]), P [B,L,Nq]).
     Every one of the L frames takes part in the softmax, padded or not (no mask in the reference).
     """
+    lin = lin or _linear
     X = drop(f"{prefix}.in", H)
-    K = torch.tanh(_linear(P, f"{prefix}.input_proj", X))
+    K = torch.tanh(lin(P, f"{prefix}.input_proj", X))
+    if rnd is not None:
+        K = rnd("K", K)
     if queries is None:
         Qp = P[f"{prefix}.attention_context_vector"].expand(H.shape[0], 1, H.shape[2])
     else:
-        Qp = (lin or _linear)(P, f"{prefix}.query_proj", queries)
+        Qp = lin(P, f"{prefix}.query_proj", queries)
     S = K @ Qp.transpose(1, 2)                         # [B,L,Nq]
     A = torch.softmax(SOFTMAX_SCALE * S, dim=1)
     O = A.transpose(1, 2) @ X                          # [B,Nq,G]  values are the dropped, un-projected frames
@@ -160,29 +163,30 @@ def pool_attention(P: Params, prefix: str, H: torch.Tensor, queries: Optional[to
 
 
 def forward(P: Params, audio: torch.Tensor, text: torch.Tensor, video: torch.Tensor,
-            drop: Optional[DropFn] = None, lin=None):
+            drop: Optional[DropFn] = None, lin=None, rnd=None):
     """WengnetMOSEIMultViewsTextMissing.forward (:275-370).
 
     Returns (vals_out [B,1], [fused [B,128], feat4rnc [B,64], text_hidden [B,256], cross_text [B,7,128]]).
     `drop(site, x)` applies dropout at the named site (None = eval mode).  `lin(P, name, x)` optionally
-    replaces the utterance-level nn.Linear evaluations (tests use it to emulate the rounding points of
-    the CUDA backward); the math is unchanged.
+    replaces every nn.Linear evaluation and `rnd(tag, x)` is applied to the tanh key projections (tests use
+    the two hooks to emulate the rounding points of the CUDA path); the math is unchanged.
     """
     drop = drop or _identity_drop
+    lin = lin or _linear
     mlp = lambda name, x, n: _mlp(P, name, x, n, drop, lin)  # noqa: E731
-    Ha = _linear(P, "frame_dim_reshape_0", audio)
-    Ht = _linear(P, "frame_dim_reshape_1", text)
-    Hv = _linear(P, "frame_dim_reshape_2", video)
+    Ha = lin(P, "frame_dim_reshape_0", audio)
+    Ht = lin(P, "frame_dim_reshape_1", text)
+    Hv = lin(P, "frame_dim_reshape_2", video)
 
-    ua, _ = pool_attention(P, "fra2utt_0", Ha, None, drop)
-    ut, _ = pool_attention(P, "fra2utt_1", Ht, None, drop)
-    uv, _ = pool_attention(P, "fra2utt_2", Hv, None, drop)
+    ua, _ = pool_attention(P, "fra2utt_0", Ha, None, drop, lin, rnd)
+    ut, _ = pool_attention(P, "fra2utt_1", Ht, None, drop, lin, rnd)
+    uv, _ = pool_attention(P, "fra2utt_2", Hv, None, drop, lin, rnd)
 
     ha = mlp("audio_mlp", ua, 2)
     ht = mlp("text_mlp", ut, 2)
     hv = mlp("video_mlp", uv, 2)
 
-    gate = _linear(P, "fc_att", mlp("attention_mlp", torch.cat([ha, ht, hv], dim=1), 2))  # [B,3] raw
+    gate = lin(P, "fc_att", mlp("attention_mlp", torch.cat([ha, ht, hv], dim=1), 2))  # [B,3] raw
     ga, gt, gv = gate[:, 0:1], gate[:, 1:2], gate[:, 2:3]
     fused = ga * ha + gt * ht + gv * hv
     fused_at = ga * ha + gt * ht
@@ -194,21 +198,20 @@ def forward(P: Params, audio: torch.Tensor, text: torch.Tensor, video: torch.Ten
     text_hidden = qs[5]                                   # re-bound at :329; this is embedding #3
     Q = torch.stack(qs, dim=1)                            # [B,7,G]
 
-    Ca, _ = pool_attention(P, "cross_att_fra2utt_0", Ha, Q, drop, lin)
-    Ct, _ = pool_attention(P, "cross_att_fra2utt_1", Ht, Q, drop, lin)
-    Cv, _ = pool_attention(P, "cross_att_fra2utt_2", Hv, Q, drop, lin)
+    Ca, _ = pool_attention(P, "cross_att_fra2utt_0", Ha, Q, drop, lin, rnd)
+    Ct, _ = pool_attention(P, "cross_att_fra2utt_1", Ht, Q, drop, lin, rnd)
+    Cv, _ = pool_attention(P, "cross_att_fra2utt_2", Hv, Q, drop, lin, rnd)
 
     ca = mlp("cross_audio_mlp", Ca, 2)                    # [B,7,128]
     ct = mlp("cross_text_mlp", Ct, 2)
     cv = mlp("cross_video_mlp", Cv, 2)
 
     W = ga.unsqueeze(2) * ca + gt.unsqueeze(2) * ct + gv.unsqueeze(2) * cv      # [B,7,128] (:346-349)
-    r = _linear(P, "cross_fc_att", mlp("cross_attention_mlp", W.reshape(W.shape[0], -1), 2))  # [B,7]
+    r = lin(P, "cross_fc_att", mlp("cross_attention_mlp", W.reshape(W.shape[0], -1), 2))  # [B,7]
     f = (W * r.unsqueeze(2)).sum(dim=1)                                         # [B,128] (:356-358)
 
-    vals_out = _linear(P, "fc_out_v", f)
-    lin2 = lin or _linear
-    feat4rnc = lin2(P, "orgin_linear_change.2", torch.relu(lin2(P, "orgin_linear_change.0", f)))
+    vals_out = lin(P, "fc_out_v", f)
+    feat4rnc = lin(P, "orgin_linear_change.2", torch.relu(lin(P, "orgin_linear_change.0", f)))
     return vals_out, [f, feat4rnc, text_hidden, ct]
 
 
@@ -336,11 +339,11 @@ def adam_update(P: Params, grads: Dict[str, Optional[torch.Tensor]], state: dict
 
 
 def loss_and_grads(P: Params, audio, text, feat4, video, vals, w: Optional[dict] = None,
-                   drop0: Optional[DropFn] = None, drop1: Optional[DropFn] = None, lin=None):
+                   drop0: Optional[DropFn] = None, drop1: Optional[DropFn] = None, lin=None, rnd=None):
     """Both passes + loss + autograd gradients w.r.t. every parameter (None for dead ones)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
-    out0 = forward(leaves, audio, text, video, drop0, lin)
-    out1 = forward(leaves, audio, feat4, video, drop1, lin)
+    out0 = forward(leaves, audio, text, video, drop0, lin, rnd)
+    out1 = forward(leaves, audio, feat4, video, drop1, lin, rnd)
     loss, terms = distill_loss(out0, out1, vals, w)
     names = list(leaves)
     gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)

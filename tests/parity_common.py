@@ -21,15 +21,25 @@ def _r16(x):
     return x.float().bfloat16().to(x.dtype)
 
 
-class _LinearBf16Bwd(torch.autograd.Function):
-    """Exact forward; backward with the rounding points of the CUDA chain backward: dZ, the saved input and
-    the weight enter the two backward GEMMs as bf16, products accumulate exactly, the bias gradient is summed
-    unrounded."""
+def _tf32(x):
+    """fp32 value as the tensor core reads it for kind::tf32: low 13 mantissa bits ignored."""
+    y = x.float().contiguous()
+    return (y.view(torch.int32) & -8192).view(torch.float32).to(x.dtype)
+
+
+def _st(x, fn):
+    """straight-through rounding: value fn(x), gradient of x"""
+    return x + (fn(x.detach()) - x.detach())
+
+
+class _ChainLinear(torch.autograd.Function):
+    """Utterance-level nn.Linear with the rounding points of the CUDA path: forward = tf32 operands, exact
+    accumulation; backward = dZ, saved input and weight as bf16 into the two GEMMs, bias gradient unrounded."""
 
     @staticmethod
     def forward(ctx, x, w, b):
         ctx.save_for_backward(x, w)
-        return x @ w.t() + b
+        return _tf32(x) @ _tf32(w).t() + b
 
     @staticmethod
     def backward(ctx, dy):
@@ -39,8 +49,23 @@ class _LinearBf16Bwd(torch.autograd.Function):
         return (dz @ _r16(w)), dz2.t() @ x2, dy.reshape(-1, dy.shape[-1]).sum(0)
 
 
+_EXACT = ("fc_att", "cross_fc_att", "fc_out_v")       # SIMT fp32 dot products
+
+
 def emu_linear(P, name, x):
-    return _LinearBf16Bwd.apply(x, P[f"{name}.weight"], P[f"{name}.bias"])
+    """Every nn.Linear of the model with the CUDA path's storage / operand precisions."""
+    w, b = P[f"{name}.weight"], P[f"{name}.bias"]
+    if name.startswith("frame_dim_reshape"):          # bf16 operands, fp32 accumulate, H stored as bf16
+        return _st(x @ _st(w, _r16).t() + b, _r16)
+    if name.endswith("input_proj"):                   # bf16 operands (x is already bf16-valued), fp32 result
+        return x @ _st(w, _r16).t() + b
+    if name in _EXACT:
+        return x @ w.t() + b
+    return _ChainLinear.apply(x, w, b)
+
+
+def emu_round(tag, x):
+    return _st(x, _r16)                               # K = tanh(...) is stored (and scored) as bf16
 
 
 def build_model(dims, P: Dict[str, torch.Tensor], seed=100, device="cuda"):
@@ -115,9 +140,9 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
         loss.backward()
         torch.cuda.synchronize()
         leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
-        lin = emu_linear if emulate else None
-        o0 = O.forward(leaves, b64["audio"], b64["text"], b64["video"], d0, lin)
-        o1 = O.forward(leaves, b64["audio"], b64["feat4"], b64["video"], d1, lin)
+        lin, rnd = (emu_linear, emu_round) if emulate else (None, None)
+        o0 = O.forward(leaves, b64["audio"], b64["text"], b64["video"], d0, lin, rnd)
+        o1 = O.forward(leaves, b64["audio"], b64["feat4"], b64["video"], d1, lin, rnd)
         outs_ref = [o0[0], *o0[1], o1[0], *o1[1]]
         oloss = sum((t * c).sum() for t, c in zip(outs_ref, cts))
         names = list(leaves)
@@ -146,7 +171,8 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
     torch.cuda.synchronize()
 
     oloss, oterms, ograds, (o0, o1) = O.loss_and_grads(P_bf, b64["audio"], b64["text"], b64["feat4"], b64["video"],
-                                                       b64["vals"], w, d0, d1, emu_linear if emulate else None)
+                                                       b64["vals"], w, d0, d1, emu_linear if emulate else None,
+                                                       emu_round if emulate else None)
     res = {}
     for tag, (v, e), (ov, oe) in (("p0", (v0, e0), o0), ("p1", (v1, e1), o1)):
         res[f"{tag}/vals"] = nerr(v, ov)

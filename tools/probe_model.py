@@ -20,6 +20,14 @@ CASES = {
                        cotangent=True),
     "s0_train_ct": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=True,
                         cotangent=True),
+    "s0_eval_ct_emu": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=False,
+                           cotangent=True, emulate=True),
+    "s0_train_ct_emu": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=True,
+                            cotangent=True, emulate=True),
+    "s0_train_emu": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=True,
+                         emulate=True),
+    "small_train_ct_emu": dict(dims=(96, 160, 64, 160), frames=(20, 7, 13, 9), B=6, gain=1.0, train=True,
+                               cotangent=True, emulate=True),
     "small_eval_ct": dict(dims=(96, 160, 64, 160), frames=(20, 7, 13, 9), B=6, gain=1.0, train=False, cotangent=True),
     "small_train_ct": dict(dims=(96, 160, 64, 160), frames=(20, 7, 13, 9), B=6, gain=1.0, train=True, cotangent=True),
     "s0_eval_emu": dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=8, gain=1.0, train=False,
