@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""Benchmark of the SDUMC hot path (BASELINE.json: train samples/sec, fwd + bwd + distill + Adam).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+N = 1 runs BASELINE config 2: full + text-missing self-distillation train step, bf16 storage / fp32
+accumulate, batch 512 per GPU, synthetic MER2024-shaped features "S0" (dims 1024/4096/1024/4096, frames
+384/64/256/64).  N > 1 (launched by torch.distributed.run) is data parallel, 512 samples per GPU (weak
+scaling), global RnC / RMSE semantics kept by the exchanges in sdumc_b200/trainer.py.
+
+`--impl reference` times the reference algorithm on the host CPU cores (the oracle port of the reference
+modules: /root/reference is not present on the GPU box) on a bounded sample of the same workload.
+
+Prints ONE JSON line (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "train_samples_per_sec"
+UNIT = "samples/s"
+F_TRAIN_PER_SAMPLE = 2.408e9      # algorithmic FLOPs / sample of the S0 train step
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(hbm=d["hbm_gbs"], tc_burst=d["bf16_tflops"], tc_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+
+    def summary(self):
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the oracle port of the reference train step on the host cores
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_steps(n_steps: int, warmup: int, B: int = 32):
+    import torch
+    from oracle import sdumc_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    P = O.init_params(O.S0_DIMS, seed=100, gain=1.0)
+    b = O.synth_batch(B, O.S0_DIMS, O.S0_FRAMES, seed=1234)
+    sites = O.dropout_sites()
+    ps = dict(sites)
+    st = {}
+
+    def make_drop():
+        def drop(site, x):   # train mode: torch dropout, as the reference's nn.Dropout modules
+            return torch.nn.functional.dropout(x, ps[site], True)
+        return drop
+
+    times = []
+    for i in range(warmup + n_steps):
+        t0 = time.perf_counter()
+        O.train_step(P, st, b["audio"], b["text"], b["feat4"], b["video"], b["vals"], lr=1e-4, weight_decay=1e-5,
+                     drop0=make_drop(), drop1=make_drop())
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return B, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, times = cpu_reference_steps(args.steps, args.warmup, B=32)
+    total = sum(times)
+    value = B * len(times) / total
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": {"workload": "SDUMC full + text-missing self-distill train step, S0 features "
+                               "(dims 1024/4096/1024/4096, frames 384/64/256/64)", "batch_per_step": B,
+                   "note": "reference algorithm on the host CPU (oracle port of the reference modules), torch eager "
+                           "fp32, bounded sample: batch 32 per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} train steps of batch {B} (S0 shapes), torch fp32, {cores} threads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sdumc_b200 import _lib, ops
+    from sdumc_b200.data import S0_DIMS, S0_FRAMES, pin, synth_batch
+    from sdumc_b200.trainer import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (sdumc_b200 has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    pg = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    B = args.batch
+    peaks = load_peaks()
+
+    tr = Trainer(S0_DIMS, B, S0_FRAMES, dev, lr=1e-4, weight_decay=1e-5, seed=100, process_group=pg)
+    batch = synth_batch(B, S0_DIMS, S0_FRAMES, seed=1234 + rank, device=dev)
+    host = pin(batch)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("audio", "text", "video", "feat4", "vals"))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident inputs: whole-step throughput ----
+    tr.load_batch(batch["audio"], batch["text"], batch["video"], batch["feat4"], batch["vals"])
+    _lib.KERNEL_LAUNCHES[0] = 0
+    tr.train_step()                       # eager step: counts our kernel launches per step
+    launches = _lib.KERNEL_LAUNCHES[0]
+    for _ in range(max(args.warmup, 3) - 1):
+        tr.train_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            tr.train_step()
+        e1.record()
+        barrier()
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    ms_step = ms_total / args.steps
+    value = world * B * args.steps / (ms_total / 1e3)
+    terms = tr.terms.tolist()
+
+    # ---- end to end: pinned host batch -> H2D -> step -> D2H of the loss, every step ----
+    for _ in range(2):
+        tr.load_batch(host["audio"], host["text"], host["video"], host["feat4"], host["vals"])
+        tr.train_step()
+        float(tr.terms[6].item())
+    barrier()
+    n_e2e = max(3, min(args.steps, 10))
+    e0.record()
+    for _ in range(n_e2e):
+        tr.load_batch(host["audio"], host["text"], host["video"], host["feat4"], host["vals"])
+        tr.train_step()
+        float(tr.terms[6].item())
+    e1.record()
+    barrier()
+    ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * n_e2e / (ms_e2e / 1e3)
+
+    # ---- dominant kernel alone: the audio in-projection GEMM (tcgen05, bf16, [B*384,1024] x [1024,256]) ----
+    roof = None
+    if rank == 0:
+        X = tr.inputs["a"].view(B * S0_FRAMES[0], S0_DIMS[0])
+        Wt = tr.W.bf16("frame_dim_reshape_0.weight")
+        bias = tr.W.f32("frame_dim_reshape_0.bias")
+        H = torch.empty(X.shape[0], 256, dtype=torch.bfloat16, device=dev)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def go():
+            ops.gemm(X, Wt, M=X.shape[0], N=256, K=X.shape[1], bias=bias, epi_kind=ops.EPI_INPROJ, out_bf16=H)
+        for _ in range(3):
+            go()
+        ts = []
+        for _ in range(10):
+            flush.zero_()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            go()
+            b_.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b_))
+        ms_k = sum(ts) / len(ts)
+        flops = 2.0 * X.shape[0] * 256 * X.shape[1]
+        ach = flops / (ms_k * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,bf16> (audio in-projection)", "achieved": ach,
+                "peak": peaks["tc_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tc_burst"], "traffic": None,
+                "peak_source": peaks["src"] + " (burst: kernel timed alone)", "ms_per_launch": ms_k,
+                "hbm_gbs": (X.numel() * 2 + H.numel() * 2 + Wt.numel() * 2) / (ms_k * 1e-3) / 1e9,
+                "hbm_frac": (X.numel() * 2 + H.numel() * 2 + Wt.numel() * 2) / (ms_k * 1e-3) / 1e9 / peaks["hbm"],
+                "step_tensor_frac": value / world * F_TRAIN_PER_SAMPLE / (peaks["tc_sustained"] * 1e12)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        Bc, times = cpu_reference_steps(n_steps=8, warmup=1, B=32)
+        cores = os.cpu_count() or 1
+        cpu = {"value": Bc * len(times) / sum(times), "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{len(times)} train steps of batch {Bc} (S0 shapes) of the oracle port, torch fp32, "
+                         f"{cores} threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "SDUMC full + text-missing self-distill train step (fwd + bwd + 6-term loss + Adam), "
+                                   "S0 features dims 1024/4096/1024/4096, frames 384/64/256/64",
+                       "batch_per_gpu": B, "global_batch": B * world, "parallelism": f"dp{world}",
+                       "l2": "inputs (1.2 GB bf16 per GPU) larger than L2; no explicit flush",
+                       "cuda_graph": bool(tr.use_graph)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "steps": n_e2e},
+            "gpu_launches": launches * args.steps,
+            "gpu_launches_per_step": launches,
+            "clocks": clk.summary(),
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "loss_terms": dict(zip(("mse_full", "mse_missing", "rmse_text_hidden", "rmse_cross_text", "rmse_fused",
+                                    "rnc", "total"), terms[:7])),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    ap.add_argument("--batch", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -75,6 +75,7 @@ typedef struct sdumc_gemm_desc {
   float* scores; /* [M, nq] */
   uint64_t seed; /* dropout RNG */
   uint32_t step;
+  const uint32_t* step_dev; /* optional device counter added to step */
   uint32_t dbg_lbo, dbg_sbo; /* test-only descriptor overrides, 0 = default */
 } sdumc_gemm_desc;
 
@@ -86,6 +87,8 @@ int sdumc_gemm(const sdumc_gemm_desc* d, void* stream);
  * ------------------------------------------------------------------------------------------ */
 typedef struct sdumc_dropkey {
   uint32_t seed_lo, seed_hi, step;
+  uint32_t reserved;
+  const uint32_t* step_dev; /* optional device counter added to `step` at run time (CUDA-graph replay) */
 } sdumc_dropkey;
 
 int sdumc_frame_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t rows, int32_t cols, float* out,
@@ -292,6 +295,8 @@ typedef struct sdumc_adam_args {
   int64_t n;
   float lr, beta1, beta2, eps, weight_decay, grad_scale;
   int32_t step; /* 1-based */
+  const int32_t* step_dev; /* optional: device-resident step (overrides `step`), for CUDA-graph replay */
+  const float* lr_dev;     /* optional: device-resident learning rate (overrides `lr`) */
 } sdumc_adam_args;
 int sdumc_adam(const sdumc_adam_args* a, void* stream);
 

@@ -142,7 +142,11 @@ def exported_symbols():
     return list(FUNCTIONS.keys())
 
 
-def check(rc: int, what: str = "") -> None:
+KERNEL_LAUNCHES = [0]   # kernels launched through this binding (bench.py reports it per step)
+
+
+def check(rc: int, what: str = "", launches: int = 1) -> None:
+    KERNEL_LAUNCHES[0] += launches
     if rc != 0:
         msg = lib().sdumc_last_error()
         raise SdumcError(f"{what or 'sdumc call'} failed (rc={rc}): {msg.decode() if msg else ''}")
@@ -158,10 +162,10 @@ def current_stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
 
-def dropkey(seed: int, step: int):
-    return DropKey(seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, step & 0xFFFFFFFF)
+def dropkey(seed: int, step: int, step_dev=None):
+    return DropKey(seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, step & 0xFFFFFFFF, 0, ptr(step_dev))
 
 
-def call(name: str, args_struct, what: str = "") -> None:
+def call(name: str, args_struct, what: str = "", launches: int = 1) -> None:
     """Invoke `int name(const struct*, void* stream)` on the current stream."""
-    check(getattr(lib(), name)(C.byref(args_struct), current_stream()), what or name)
+    check(getattr(lib(), name)(C.byref(args_struct), current_stream()), what or name, launches)

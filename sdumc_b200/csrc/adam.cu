@@ -11,6 +11,12 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a, float step_size, 
   const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= a.n) return;
   const float b1 = a.beta1, b2 = a.beta2;
+  if (a.step_dev || a.lr_dev) {  // device-resident step / learning rate (CUDA-graph replay)
+    const double t = (double)(a.step_dev ? __ldg(a.step_dev) : a.step);
+    const double lr = (double)(a.lr_dev ? __ldg(a.lr_dev) : a.lr);
+    step_size = (float)(lr / (1.0 - pow((double)b1, t)));
+    inv_bc2_sqrt = (float)(1.0 / sqrt(1.0 - pow((double)b2, t)));
+  }
   if (i4 + 4 <= a.n) {
     float4 p = *reinterpret_cast<float4*>(a.p + i4);
     const float4 g = *reinterpret_cast<const float4*>(a.g + i4);
@@ -51,12 +57,13 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a, float step_size, 
 }
 
 int launch_adam(const AdamArgs& a, cudaStream_t stream) {
-  SDUMC_CHECK_ARG(a.p && a.g && a.m && a.v && a.n > 0 && a.step >= 1, "adam: bad arguments");
+  SDUMC_CHECK_ARG(a.p && a.g && a.m && a.v && a.n > 0 && (a.step >= 1 || a.step_dev), "adam: bad arguments");
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.p) | reinterpret_cast<uintptr_t>(a.g) | reinterpret_cast<uintptr_t>(a.m) |
                     reinterpret_cast<uintptr_t>(a.v)) & 15u) == 0,
                   "adam: buffers must be 16-byte aligned");
-  const double bc1 = 1.0 - pow((double)a.beta1, (double)a.step);
-  const double bc2 = 1.0 - pow((double)a.beta2, (double)a.step);
+  const int st = a.step >= 1 ? a.step : 1;
+  const double bc1 = 1.0 - pow((double)a.beta1, (double)st);
+  const double bc2 = 1.0 - pow((double)a.beta2, (double)st);
   const float step_size = (float)((double)a.lr / bc1);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   const long nthreads = (a.n + 3) / 4;

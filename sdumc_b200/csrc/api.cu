@@ -55,7 +55,7 @@ int sdumc_gemm(const sdumc_gemm_desc* d, void* stream) {
     ep.tgt_site[i] = d->tgt_site[i];
   }
   ep.qv = d->qv; ep.q_stride = d->q_stride; ep.nq = d->nq; ep.L = d->L; ep.scores = d->scores;
-  ep.key = DropKey{(uint32_t)(d->seed & 0xffffffffu), (uint32_t)(d->seed >> 32), d->step};
+  ep.key = make_dropkey(d->seed, d->step, d->step_dev);
   GemmOperand A{d->A, d->lda}, B{d->B, d->ldb};
   return launch_gemm(A, B, sh, ep, d->tf32 != 0, d->block_n, d->max_ctas, static_cast<cudaStream_t>(stream));
 }
@@ -63,7 +63,7 @@ int sdumc_gemm(const sdumc_gemm_desc* d, void* stream) {
 int sdumc_frame_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t rows, int32_t cols, float* out,
                      void* stream) {
   SDUMC_CHECK_ARG(out && rows > 0 && cols > 0, "sdumc_frame_mask: bad arguments");
-  DropKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), step};
+  DropKey key = make_dropkey(seed, step);
   const long n = rows * ((cols + 31) / 32);
   frame_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(key, site, rows, cols,
                                                                                                  out);
@@ -73,7 +73,7 @@ int sdumc_frame_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t rows, 
 
 int sdumc_elem_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t n, float p, float* out, void* stream) {
   SDUMC_CHECK_ARG(out && n > 0 && p >= 0.f && p < 1.f, "sdumc_elem_mask: bad arguments");
-  DropKey key{(uint32_t)(seed & 0xffffffffu), (uint32_t)(seed >> 32), step};
+  DropKey key = make_dropkey(seed, step);
   elem_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       key, site, n, drop_threshold(p), 1.f / (1.f - p), out);
   SDUMC_CUDA(cudaGetLastError());

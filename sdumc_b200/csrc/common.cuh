@@ -82,7 +82,16 @@ __host__ __device__ __forceinline__ U4 philox4x32_10(uint32_t c0, uint32_t c1, u
 // Dropout RNG state handed to every kernel that drops.  `step` separates
 // optimisation steps, `site` separates the dropout sites of the model
 // (see engine.h: site numbering), seed is the user seed.
-using DropKey = sdumc_dropkey;  // {seed_lo, seed_hi, step}
+using DropKey = sdumc_dropkey;  // {seed_lo, seed_hi, step, step_dev}
+inline DropKey make_dropkey(uint64_t seed, uint32_t step, const uint32_t* step_dev = nullptr) {
+  DropKey k;
+  k.seed_lo = (uint32_t)(seed & 0xffffffffu);
+  k.seed_hi = (uint32_t)(seed >> 32);
+  k.step = step;
+  k.reserved = 0;
+  k.step_dev = step_dev;
+  return k;
+}
 
 // Frame-level p=0.5 dropout: one random bit per element.
 //   counter = (row, col >> 7, site, step), word = (col >> 5) & 3, bit = col & 31
@@ -107,6 +116,13 @@ __host__ __device__ __forceinline__ uint32_t drop_threshold(float p) {
 }
 
 #ifdef __CUDACC__
+// fold the optional device-resident step counter into the key (once per thread, at kernel start)
+__device__ __forceinline__ DropKey resolve_key(const DropKey& k) {
+  DropKey r = k;
+  if (k.step_dev) r.step = k.step + __ldg(k.step_dev);
+  r.step_dev = nullptr;
+  return r;
+}
 // ---------------------------------------------------------------------------------
 // PTX wrappers (device)
 // ---------------------------------------------------------------------------------

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolFwdArgs a) {
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = a.L;
+  const DropKey key = resolve_key(a.key);
   float* Sg = a.S + (long)b * L * NQ;
 
   for (int i = tid; i < L * NQ; i += 256) Ps[i] = Sg[i];
@@ -108,7 +109,7 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolFwdArgs a) {
     float y = o;
     if (a.drop_p > 0.f) {
       const uint32_t e = (uint32_t)b * (uint32_t)(NQ * G) + (uint32_t)i;
-      y = elem_rand(a.key, a.site, e) >= thr ? o * scale : 0.f;
+      y = elem_rand(key, a.site, e) >= thr ? o * scale : 0.f;
     }
     a.out[(long)b * a.out_stride_b + i] = y;
     if (a.out_bf16) a.out_bf16[(long)b * a.out_stride_b + i] = __float2bfloat16_rn(y);
@@ -154,12 +155,13 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
   const int L = a.L;
   const uint32_t thr = drop_threshold(a.out_drop_p);
   const float oscale = a.out_drop_p > 0.f ? 1.f / (1.f - a.out_drop_p) : 1.f;
+  const DropKey key = resolve_key(a.key);
 
   for (int i = tid; i < NQ * G; i += 256) {
     float g = a.dOut[(long)b * a.dout_stride_b + i];
     if (a.out_drop_p > 0.f) {
       const uint32_t e = (uint32_t)b * (uint32_t)(NQ * G) + (uint32_t)i;
-      g = elem_rand(a.key, a.out_site, e) >= thr ? g * oscale : 0.f;
+      g = elem_rand(key, a.out_site, e) >= thr ? g * oscale : 0.f;
     }
     (&dO_s[0][0])[i] = g;
     (&Qp_s[0][0])[i] = a.Qp[(long)b * a.qp_stride_b + i];
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
     *reinterpret_cast<uint4*>(a.dZ + row * a.lddz + g0) = pack8(dZ);
 
     if (a.fmask_site) {
-      const U4 w = frame_mask_words(a.key, a.fmask_site, (uint32_t)row, (uint32_t)(g0 >> 7));
+      const U4 w = frame_mask_words(key, a.fmask_site, (uint32_t)row, (uint32_t)(g0 >> 7));
       const int wsel = (g0 >> 5) & 3;
       const uint32_t bits = (wsel == 0 ? w.x : (wsel == 1 ? w.y : (wsel == 2 ? w.z : w.w))) >> (g0 & 31);
 #pragma unroll

@@ -264,6 +264,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t acc_phase = 0;
     const uint32_t drop_thr = drop_threshold(ep.drop_p);
     const float drop_scale = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
+    const DropKey key = resolve_key(ep.key);
     int li = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++li) {
       if ((li & 1) != grp) continue;
@@ -327,7 +328,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if ((c & 3) == 0) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-              if (i < ep.n_tgt) tw[i] = frame_mask_words(ep.key, ep.tgt_site[i], (uint32_t)r, (uint32_t)(n0 >> 7));
+              if (i < ep.n_tgt) tw[i] = frame_mask_words(key, ep.tgt_site[i], (uint32_t)r, (uint32_t)(n0 >> 7));
           }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -399,7 +400,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 32; j += 4) {
             // e = r * N + n0 + j is a multiple of 4 whenever N % 4 == 0 (checked on the host)
             const uint32_t e = (uint32_t)r * (uint32_t)sh.N + (uint32_t)(n0 + j);
-            const U4 rw = philox4x32_10(e >> 2, 0x5D0Cu, ep.drop_site, ep.key.step, ep.key.seed_lo, ep.key.seed_hi);
+            const U4 rw = philox4x32_10(e >> 2, 0x5D0Cu, ep.drop_site, key.step, key.seed_lo, key.seed_hi);
             v[j] = rw.x >= drop_thr ? v[j] * drop_scale : 0.f;
             v[j + 1] = rw.y >= drop_thr ? v[j + 1] * drop_scale : 0.f;
             v[j + 2] = rw.z >= drop_thr ? v[j + 2] * drop_scale : 0.f;
@@ -407,7 +408,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (ep.fmask_site) {
-          const U4 w4 = frame_mask_words(ep.key, ep.fmask_site, (uint32_t)r, (uint32_t)(n0 >> 7));
+          const U4 w4 = frame_mask_words(key, ep.fmask_site, (uint32_t)r, (uint32_t)(n0 >> 7));
           const int wsel = (n0 >> 5) & 3;
           const uint32_t bits = wsel == 0 ? w4.x : (wsel == 1 ? w4.y : (wsel == 2 ? w4.z : w4.w));
 #pragma unroll

@@ -87,6 +87,7 @@ class Cfg:
     need_grad: bool                   # keep what the backward pass needs
     seed: int = 0
     step: int = 0
+    step_dev: Optional[torch.Tensor] = None   # device uint32 counter added to step (CUDA-graph replay)
 
 
 @dataclass
@@ -133,7 +134,7 @@ class Engine:
         p = MLP_P if (cfg.dropout and drop_site) else 0.0
         ops.gemm(x, w, M=x.shape[0], N=N, K=K, bias=W.f32(lname + ".bias"),
                  act=ops.ACT_RELU if relu else ops.ACT_NONE, drop_p=p, drop_site=drop_site, out_f32=y,
-                 out_bf16=y_bf16, seed=cfg.seed, step=cfg.step)
+                 out_bf16=y_bf16, seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev)
 
     def _linear_bwd(self, W: Weights, st: State, lname: str, dY: torch.Tensor, x_bf16: torch.Tensor, *,
                     Y: Optional[torch.Tensor], dropped: bool, dX: Optional[torch.Tensor], dX_mode=ops.OUT_STORE,
@@ -187,7 +188,7 @@ class Engine:
                         tg.append(t)
                         sites.append(site_id(f"{blk}_{m}.in", p))
                 ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
-                         epi_kind=ops.EPI_INPROJ, targets=tg, target_sites=sites, seed=seed, step=step)
+                         epi_kind=ops.EPI_INPROJ, targets=tg, target_sites=sites, seed=seed, step=step, step_dev=cfg.step_dev)
             else:
                 H = self._new(st, f"H.{s}", (B * L, G), torch.bfloat16)
                 ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
@@ -211,7 +212,7 @@ class Engine:
             Opre = self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
             ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=Opre, out=u_pool[m][p * B:(p + 1) * B], out_stride_b=G,
                          out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
-                         site=site_id(pre + ".out", p), seed=seed, step=step)
+                         site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev)
 
         # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
         cat = self._new(st, "cat", (R, 3 * G))
@@ -258,7 +259,7 @@ class Engine:
             Opre = self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
             ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=Opre, out=C[m][p * B * NQ:(p + 1) * B * NQ],
                          out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
-                         drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step)
+                         drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev)
 
         # 5. utterance chain B
         c = []
@@ -429,10 +430,10 @@ class Engine:
         ops.attn_bwd(X, Kt, P, dOut, dout_stride_b=nq * G, O_pre=Opre, Qp=Qp, qp_stride_b=qp_stride, B=B, L=L, nq=nq,
                      out_drop_p=FRAME_P if cfg.dropout else 0.0, out_site=site_id(pre + ".out", p), dZ=dZ, dH=dH[s],
                      dh_mode=0 if first else 1, fmask_site=fmask, dQp=dQp, dqp_stride_b=nq * G,
-                     db=W.grad(pre + ".input_proj.bias"), seed=cfg.seed, step=cfg.step)
+                     db=W.grad(pre + ".input_proj.bias"), seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev)
         # dH += (dZ W_in) * M_in
         ops.gemm(dZ, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, b_mn=True, fmask_site=fmask,
-                 out_bf16=dH[s], bf16_mode=ops.OUT_ADD, seed=cfg.seed, step=cfg.step)
+                 out_bf16=dH[s], bf16_mode=ops.OUT_ADD, seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev)
         # dW_in += dZ^T X'
         ops.gemm(dZ, X, M=G, N=G, K=B * L, a_mn=True, b_mn=True, k_splits=_ksplits(B * L, G, G),
                  out_f32=W.grad(pre + ".input_proj.weight"), f32_mode=ops.OUT_ATOMIC)

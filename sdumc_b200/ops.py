@@ -24,8 +24,8 @@ def _ld(t: torch.Tensor) -> int:
 def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_mn=False, b_mn=False, k_splits=1,
          block_n=0, max_ctas=0, bias=None, act=ACT_NONE, gate=None, gate_scale=1.0, drop_p=0.0, drop_site=0,
          fmask_site=0, out_f32=None, f32_mode=OUT_STORE, out_bf16=None, bf16_mode=OUT_STORE, epi_kind=EPI_GENERIC,
-         targets=(), target_sites=(), qv=None, q_stride=0, nq=0, L=1, scores=None, seed=0, step=0, dbg_lbo=0,
-         dbg_sbo=0) -> None:
+         targets=(), target_sites=(), qv=None, q_stride=0, nq=0, L=1, scores=None, seed=0, step=0, step_dev=None,
+         dbg_lbo=0, dbg_sbo=0) -> None:
     """C[M,N] = epilogue(op(A) op(B)) — tcgen05/TMA GEMM.
 
     A is stored [M,K] (a_mn=False) or [K,M]; B is stored [N,K] (b_mn=False, the nn.Linear weight
@@ -51,7 +51,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_mn=False
         if d.ld_bf16 == 0:
             d.ld_bf16 = _ld(t)
     d.qv, d.q_stride, d.nq, d.L, d.scores = ptr(qv), q_stride, nq, L, ptr(scores)
-    d.seed, d.step = seed, step
+    d.seed, d.step, d.step_dev = seed, step, ptr(step_dev)
     d.dbg_lbo, d.dbg_sbo = dbg_lbo, dbg_sbo
     check(_lib.lib().sdumc_gemm(C.byref(d), current_stream()), "sdumc_gemm")
 
@@ -81,17 +81,17 @@ def colsum_bf16(X: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def pool_fwd(X, S, *, B, L, nq, O_pre, out, out_stride_b, out_bf16=None, drop_p=0.0, site=0, seed=0, step=0,
-             alpha=0.3) -> None:
+             step_dev=None, alpha=0.3) -> None:
     a = STRUCTS["sdumc_pool_fwd_args"]()
     a.X, a.ldx, a.S = ptr(X), _ld(X), ptr(S)
     a.B, a.L, a.nq, a.alpha = B, L, nq, alpha
     a.O_pre, a.out, a.out_stride_b, a.out_bf16 = ptr(O_pre), ptr(out), out_stride_b, ptr(out_bf16)
-    a.drop_p, a.site, a.key = drop_p, site, dropkey(seed, step)
+    a.drop_p, a.site, a.key = drop_p, site, dropkey(seed, step, step_dev)
     call("sdumc_pool_fwd", a)
 
 
 def attn_bwd(X, Kt, P, dOut, *, dout_stride_b, O_pre, Qp, qp_stride_b, B, L, nq, out_drop_p, out_site, dZ, dH,
-             dh_mode, fmask_site, dQp, dqp_stride_b, db, seed=0, step=0, alpha=0.3) -> None:
+             dh_mode, fmask_site, dQp, dqp_stride_b, db, seed=0, step=0, step_dev=None, alpha=0.3) -> None:
     a = STRUCTS["sdumc_attn_bwd_args"]()
     a.X, a.ldx, a.Kt, a.ldk, a.P = ptr(X), _ld(X), ptr(Kt), _ld(Kt), ptr(P)
     a.dOut, a.dout_stride_b, a.O_pre = ptr(dOut), dout_stride_b, ptr(O_pre)
@@ -100,7 +100,7 @@ def attn_bwd(X, Kt, P, dOut, *, dout_stride_b, O_pre, Qp, qp_stride_b, B, L, nq,
     a.out_drop_p, a.out_site = out_drop_p, out_site
     a.dZ, a.lddz, a.dH, a.lddh, a.dh_mode, a.fmask_site = ptr(dZ), _ld(dZ), ptr(dH), _ld(dH), dh_mode, fmask_site
     a.dQp, a.dqp_stride_b, a.db = ptr(dQp), dqp_stride_b, ptr(db)
-    a.key = dropkey(seed, step)
+    a.key = dropkey(seed, step, step_dev)
     call("sdumc_attn_bwd", a)
 
 
@@ -214,14 +214,15 @@ def rnc(feats, labels, *, loss, dfeats=None, row_begin=0, row_end=None, temperat
     if workspace is None:
         workspace = torch.empty(rnc_workspace_bytes(n, D), dtype=torch.uint8, device=feats.device)
     a.workspace, a.workspace_bytes = ptr(workspace), workspace.numel()
-    call("sdumc_rnc", a)
+    call("sdumc_rnc", a, launches=4 if dfeats is not None else 2)
 
 
 def adam(p, g, m, v, *, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0,
-         p_bf16=None, n=None) -> None:
+         p_bf16=None, n=None, step_dev=None, lr_dev=None) -> None:
     a = STRUCTS["sdumc_adam_args"]()
     a.p, a.g, a.m, a.v, a.p_bf16 = ptr(p), ptr(g), ptr(m), ptr(v), ptr(p_bf16)
     a.n = p.numel() if n is None else n
     a.lr, a.beta1, a.beta2, a.eps, a.weight_decay, a.grad_scale, a.step = lr, beta1, beta2, eps, weight_decay, \
         grad_scale, step
+    a.step_dev, a.lr_dev = ptr(step_dev), ptr(lr_dev)
     call("sdumc_adam", a)

@@ -1,0 +1,214 @@
+"""Fused self-distillation train step and two-pass scoring on the sm_100a kernels.
+
+Replaces the hot loop of train_or_eval_model() (reference main_frame_val_text_missing.py:89-158;
+inference variant main_frame_val_text_missing_inference.py:158-175): both passes (full / text-missing)
+run as ONE batch of 2B utterance rows, the audio and video in-projections are shared by the two passes,
+the 6-term loss (:148), its backward, and Adam (:317, :150) follow on the same stream, and for a
+single GPU the whole step is captured into one CUDA graph (dropout step counter, Adam step and learning
+rate live in device memory so replays differ).
+
+Data parallel (one process per GPU, torch.distributed / NCCL): the batch is sharded; the only
+exchanges are the ones the algorithm needs to stay identical to a single-process batch —
+  all_reduce of the 5 sums of squares (RMSE is the sqrt of the GLOBAL mean, loss.py:50),
+  all_gather of the RnC features / labels (RnC couples all 2B x 2B pairs, loss.py:282-313) and an
+  all_reduce of their gradient, and the gradient all_reduce over the contiguous live-parameter range.
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from . import _lib, ops
+from .engine import Cfg, Engine, Weights
+from .params import ParamLayout
+
+DEFAULT_LOSS_W = (0.5, 0.5, 0.1, 0.7, 0.1, 0.8)   # main_frame_val_text_missing.py:234-239
+LOSS_TERMS = ("mse_full", "mse_missing", "rmse_text_hidden", "rmse_cross_text", "rmse_fused", "rnc")
+
+
+def lr_lambda(epoch: int, warm_up_epochs: int = 5, gamma: float = 0.9, stepsize: int = 10) -> float:
+    """LambdaLR schedule of the reference (main…:318-320), stepped once per epoch."""
+    return (epoch + 1) / warm_up_epochs if epoch < warm_up_epochs else gamma ** ((epoch + 1 - warm_up_epochs) // stepsize)
+
+
+class Trainer:
+    """Owns the flat parameter / gradient / Adam buffers and static batch buffers of one rank."""
+
+    def __init__(self, input_dims: Sequence[int], B: int, frames: Sequence[int], device, *, lr=1e-4,
+                 weight_decay=1e-5, loss_w: Sequence[float] = DEFAULT_LOSS_W, seed: int = 100,
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None, process_group=None, use_graph: bool = True):
+        _lib.lib()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.SdumcError("sdumc_b200.Trainer needs a CUDA (sm_100a) device; there is no CPU fallback")
+        self.layout = ParamLayout(input_dims)
+        self.dims = tuple(int(d) for d in input_dims)          # (Da, Dt, Dv[, D4 == Dt])
+        self.B = int(B)
+        self.frames = dict(zip(("a", "t0", "v", "t1"), (int(f) for f in frames)))   # (La, Lt, Lv, L4)
+        self.lr, self.weight_decay, self.loss_w, self.seed = float(lr), float(weight_decay), tuple(loss_w), int(seed)
+        self.pg = process_group
+        if process_group is not None:
+            import torch.distributed as dist
+            self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+        else:
+            self.world, self.rank = 1, 0
+        self.use_graph = use_graph and self.world == 1
+        dev, L = self.device, self.layout
+        z = lambda n, dt=torch.float32: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
+        self.master, self.grads, self.m, self.v = z(L.n_total), z(L.n_total), z(L.n_live), z(L.n_live)
+        self.shadow = z(L.n_total, torch.bfloat16)
+        self.W = Weights(L, self.master, self.shadow, self.grads)
+        self.engine = Engine(L, dev)
+        if state_dict is None:
+            from .model import WengnetMOSEIMultViewsTextMissing
+            state_dict = {}
+            for name, shape in L.spec:
+                state_dict[name] = WengnetMOSEIMultViewsTextMissing._init_tensor(name, shape)
+            for name, shape in L.spec:   # biases need fan_in of their weight
+                if name.endswith(".bias") and not name.startswith("layer_normali"):
+                    bound = 1.0 / (state_dict[name[:-5] + ".weight"].shape[1] ** 0.5)
+                    state_dict[name] = torch.empty(shape).uniform_(-bound, bound)
+        self.load_state_dict(state_dict)
+        Da, Dt, Dv = self.dims[:3]
+        fr = self.frames
+        bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
+        self.inputs = {"a": bf(B, fr["a"], Da), "t0": bf(B, fr["t0"], Dt), "v": bf(B, fr["v"], Dv),
+                       "t1": bf(B, fr["t1"], Dt)}
+        self.labels = z(B)
+        # device-resident scalars (CUDA-graph replay)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # optimisation step, 1-based after the bump
+        self.lr_dev = torch.full((1,), self.lr, dtype=torch.float32, device=dev)
+        self.sums = z(8)
+        self.terms = z(8)
+        self.rnc_val = z(1)
+        R = 2 * B
+        self.d_vals, self.d_f, self.d_rnc = z(R), z(R * 128).view(R, 128), z(R * 64).view(R, 64)
+        self.d_th, self.d_ct = z(R * 256).view(R, 256), z(R * 896).view(R, 896)
+        self.y2 = z(R)
+        n_g = 2 * B * self.world
+        self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64), dtype=torch.uint8, device=dev)
+        self.dfeats_g = z(n_g * 64).view(n_g, 64) if self.world > 1 else None
+        self.n_steps = 0
+        self._graph = None
+        self._outputs = None
+
+    # ---- parameters ------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+        for name in self.layout.names:
+            key = name if name in sd else "model." + name      # get_models() prefixes keys with `model.`
+            if key in sd:
+                self.layout.view(self.master, name).copy_(sd[key].to(self.device, torch.float32))
+        self.W.refresh_shadow()
+
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        return {name: self.layout.view(self.master, name).clone() for name in self.layout.names}
+
+    def set_lr(self, lr: float):
+        self.lr = float(lr)
+        self.lr_dev.fill_(self.lr)
+
+    # ---- batch -----------------------------------------------------------------------------
+    def load_batch(self, audio, text, video, feat4, vals):
+        """Copies a batch into the static device buffers (H2D when given pinned host tensors).  bf16 tensors
+        are copied as they are; fp32 tensors are converted on the device."""
+        for key, src in (("a", audio), ("t0", text), ("v", video), ("t1", feat4)):
+            dst = self.inputs[key]
+            if src.dtype == torch.bfloat16:
+                dst.copy_(src.view(dst.shape), non_blocking=True)
+            else:
+                tmp = src.to(self.device, non_blocking=True).float().contiguous()
+                ops.cast_bf16(tmp.view(-1), dst.view(-1))
+        self.labels.copy_(vals.view(-1), non_blocking=True)
+
+    # ---- the step --------------------------------------------------------------------------
+    def _forward(self, dropout: bool, need_grad: bool):
+        cfg = Cfg(B=self.B, n_pass=2, frames=self.frames, dropout=dropout, need_grad=need_grad, seed=self.seed, step=0,
+                  step_dev=self.step_dev)
+        return self.engine.forward(self.W, self.inputs, cfg)
+
+    def _loss_and_seeds(self, st):
+        """6-term loss (:134-148) -> self.terms, gradient seeds -> self.d_*."""
+        B, W_, rank = self.B, self.world, self.rank
+        vals, f, rnc, th, ct = Engine.outputs(st)
+        th = th.contiguous()                                      # [2,B,256] out of the strided Q buffer
+        y = self.labels
+        self.sums.zero_()
+        ops.loss_sums(vals[0], vals[1], y, th[0], th[1], ct[0], ct[1], f[0], f[1], B=B, sums=self.sums)
+        self.rnc_val.zero_()
+        self.d_rnc.zero_()
+        w6 = self.loss_w[5]
+        if W_ == 1:
+            self.y2[:B].copy_(y)
+            self.y2[B:].copy_(y)
+            ops.rnc(st.t["rnc"], self.y2, loss=self.rnc_val, dfeats=self.d_rnc, grad_scale=w6, workspace=self.rnc_ws)
+        else:
+            import torch.distributed as dist
+            dist.all_reduce(self.sums, group=self.pg)
+            feats_all = torch.empty(W_, 2, B, 64, device=self.device)
+            y_all = torch.empty(W_, B, device=self.device)
+            dist.all_gather_into_tensor(feats_all, rnc.contiguous(), group=self.pg)
+            dist.all_gather_into_tensor(y_all, y.contiguous(), group=self.pg)
+            Bg = B * W_
+            feats_g = feats_all.permute(1, 0, 2, 3).reshape(2 * Bg, 64).contiguous()     # (view, rank, b)
+            y_g = y_all.reshape(Bg).repeat(2).contiguous()
+            self.dfeats_g.zero_()
+            for v in range(2):                                                           # this rank's anchors
+                lo = v * Bg + rank * B
+                ops.rnc(feats_g, y_g, loss=self.rnc_val, dfeats=self.dfeats_g, row_begin=lo, row_end=lo + B,
+                        grad_scale=w6, workspace=self.rnc_ws)
+            dist.all_reduce(self.rnc_val, group=self.pg)
+            dist.all_reduce(self.dfeats_g, group=self.pg)
+            dg = self.dfeats_g.view(2, W_, B, 64)[:, rank]
+            self.d_rnc.view(2, B, 64).copy_(dg)
+        ops.loss_finish(vals[0], vals[1], y, th[0], th[1], ct[0], ct[1], f[0], f[1], B=B, sums=self.sums,
+                        rnc=self.rnc_val, B_global=B * W_, w=self.loss_w, terms=self.terms,
+                        d_v0=self.d_vals[:B], d_v1=self.d_vals[B:], d_th1=self.d_th[B:], d_ct1=self.d_ct[B:],
+                        d_f0=self.d_f[:B], d_f1=self.d_f[B:])
+
+    def _step_body(self):
+        self.step_dev.add_(1)
+        st = self._forward(dropout=True, need_grad=True)
+        self._loss_and_seeds(st)
+        self.grads.zero_()
+        self.engine.backward(self.W, st, d_vals=self.d_vals, d_fused=self.d_f, d_rnc=self.d_rnc, d_th=self.d_th,
+                             d_ct=self.d_ct)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.grads[:self.layout.n_live], group=self.pg)
+        n = self.layout.n_live
+        ops.adam(self.master, self.grads, self.m, self.v, lr=self.lr, step=1, weight_decay=self.weight_decay,
+                 p_bf16=self.shadow, n=n, step_dev=self.step_dev, lr_dev=self.lr_dev)
+        self._outputs = Engine.outputs(st)
+
+    def train_step(self):
+        """One optimisation step on the batch currently in the static buffers.  Returns nothing; read
+        `terms` (device tensor: 6 loss terms + total) and `predictions()` when needed."""
+        if not self.use_graph or self.n_steps == 0:
+            self._step_body()          # first step eager: one-time kernel attribute setup, allocator warm-up
+        elif self._graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):   # capture does not execute ...
+                self._step_body()
+            self._graph = g
+            self._graph.replay()        # ... so this replay is the step
+        else:
+            self._graph.replay()
+        self.n_steps += 1
+
+    def predictions(self):
+        """(vals_full [B,1], vals_missing [B,1]) of the last step (device tensors)."""
+        vals = self._outputs[0]
+        return vals[0], vals[1]
+
+    # ---- scoring (main_frame_val_text_missing_inference.py:158-175) --------------------------
+    @torch.no_grad()
+    def score(self):
+        """Both passes in eval mode on the batch in the static buffers.  Returns the dict of device tensors
+        the inference CLI collects: predictions + the 4 embeddings of each pass."""
+        st = self._forward(dropout=False, need_grad=False)
+        vals, f, rnc, th, ct = Engine.outputs(st)
+        return {"val_preds_full": vals[0], "val_preds_missing": vals[1], "full_rep": f[0], "missing_rep": f[1],
+                "full_rnc": rnc[0], "missing_rnc": rnc[1], "text_rep_query_full": th[0].contiguous(),
+                "text_rep_query_missing": th[1].contiguous(), "text_rep_full": ct[0], "text_rep_missing": ct[1]}

@@ -68,6 +68,12 @@ def emu_round(tag, x):
     return _st(x, _r16)                               # K = tanh(...) is stored (and scored) as bf16
 
 
+def l2err(got: torch.Tensor, ref: torch.Tensor, floor: float = 1e-12) -> float:
+    """||got - ref||_2 / ||ref||_2"""
+    got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
+    return float((got - ref).norm() / ref.norm().clamp_min(floor))
+
+
 def build_model(dims, P: Dict[str, torch.Tensor], seed=100, device="cuda"):
     from sdumc_b200.model import WengnetMOSEIMultViewsTextMissing
     net = WengnetMOSEIMultViewsTextMissing(types.SimpleNamespace(input_dims=dims, seed=seed))
@@ -159,6 +165,7 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
             if og is None:
                 continue
             res[f"grad/{name}"] = nerr(params[name].grad, og, floor=1e-6 * gmax)
+            res[f"gradl2/{name}"] = l2err(params[name].grad, og, floor=1e-6 * gmax * og.numel() ** 0.5)
         return res
     mse, rmse, rnc = MSELoss(), RMSELoss(), RnCLoss()
     f0, r0, th0, ct0 = e0
@@ -193,4 +200,5 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
         assert p.grad is not None, f"{name}: no gradient"
         # tensors whose true gradient is (numerically) zero are compared against the global scale
         res[f"grad/{name}"] = nerr(p.grad, og, floor=1e-6 * gmax)
+        res[f"gradl2/{name}"] = l2err(p.grad, og, floor=1e-6 * gmax * og.numel() ** 0.5)
     return res
