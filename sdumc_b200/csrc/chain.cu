@@ -13,35 +13,44 @@ static constexpr int G = 256;
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) act_bwd_kernel(ActBwdArgs a) {
+  // 64 column-quads x 4 row lanes; the bias gradient is reduced inside the block before the atomics
+  // (one atomic per column per block: same-address atomics serialise in L2).
+  __shared__ float red[4][256];
   const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
   for (int cb = 0; cb < a.cols; cb += 256) {
     const int c = cb + tx * 4;
-    if (c >= a.cols) continue;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int r = blockIdx.x * 4 + ty; r < a.rows; r += gridDim.x * 4) {
-      const float4 dy = *reinterpret_cast<const float4*>(a.dY + (long)r * a.ld_dy + c);
-      float z[4] = {dy.x, dy.y, dy.z, dy.w};
-      if (a.dY2) {
-        const float4 e = *reinterpret_cast<const float4*>(a.dY2 + (long)r * a.ld_dy2 + c);
-        z[0] += e.x; z[1] += e.y; z[2] += e.z; z[3] += e.w;
+    if (c < a.cols) {
+      for (int r = blockIdx.x * 4 + ty; r < a.rows; r += gridDim.x * 4) {
+        const float4 dy = *reinterpret_cast<const float4*>(a.dY + (long)r * a.ld_dy + c);
+        float z[4] = {dy.x, dy.y, dy.z, dy.w};
+        if (a.dY2) {
+          const float4 e = *reinterpret_cast<const float4*>(a.dY2 + (long)r * a.ld_dy2 + c);
+          z[0] += e.x; z[1] += e.y; z[2] += e.z; z[3] += e.w;
+        }
+        if (a.Y) {
+          const float4 y = *reinterpret_cast<const float4*>(a.Y + (long)r * a.ld_y + c);
+          z[0] = y.x > 0.f ? z[0] * a.scale : 0.f;
+          z[1] = y.y > 0.f ? z[1] * a.scale : 0.f;
+          z[2] = y.z > 0.f ? z[2] * a.scale : 0.f;
+          z[3] = y.w > 0.f ? z[3] * a.scale : 0.f;
+        }
+        __nv_bfloat162 lo = __floats2bfloat162_rn(z[0], z[1]), hi = __floats2bfloat162_rn(z[2], z[3]);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&lo);
+        pk.y = *reinterpret_cast<uint32_t*>(&hi);
+        *reinterpret_cast<uint2*>(a.dZ + (long)r * a.ld_dz + c) = pk;
+        acc[0] += z[0]; acc[1] += z[1]; acc[2] += z[2]; acc[3] += z[3];
       }
-      if (a.Y) {
-        const float4 y = *reinterpret_cast<const float4*>(a.Y + (long)r * a.ld_y + c);
-        z[0] = y.x > 0.f ? z[0] * a.scale : 0.f;
-        z[1] = y.y > 0.f ? z[1] * a.scale : 0.f;
-        z[2] = y.z > 0.f ? z[2] * a.scale : 0.f;
-        z[3] = y.w > 0.f ? z[3] * a.scale : 0.f;
-      }
-      __nv_bfloat162 lo = __floats2bfloat162_rn(z[0], z[1]), hi = __floats2bfloat162_rn(z[2], z[3]);
-      uint2 pk;
-      pk.x = *reinterpret_cast<uint32_t*>(&lo);
-      pk.y = *reinterpret_cast<uint32_t*>(&hi);
-      *reinterpret_cast<uint2*>(a.dZ + (long)r * a.ld_dz + c) = pk;
-      acc[0] += z[0]; acc[1] += z[1]; acc[2] += z[2]; acc[3] += z[3];
     }
     if (a.db) {
+      __syncthreads();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) atomicAdd(a.db + c + j, acc[j]);
+      for (int j = 0; j < 4; ++j) red[ty][tx * 4 + j] = acc[j];
+      __syncthreads();
+      const int col = cb + threadIdx.x;
+      if (col < a.cols)
+        atomicAdd(a.db + col, (red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]));
     }
   }
 }
@@ -49,8 +58,8 @@ int launch_act_bwd(const ActBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.dY && a.dZ && a.rows > 0 && a.cols > 0 && a.cols % 4 == 0, "act_bwd: bad arguments");
   SDUMC_CHECK_ARG(a.ld_dy % 4 == 0 && a.ld_dz % 4 == 0 && (!a.Y || a.ld_y % 4 == 0) && (!a.dY2 || a.ld_dy2 % 4 == 0),
                   "act_bwd: ld %% 4");
-  int blocks = (a.rows + 3) / 4;
-  if (blocks > 296) blocks = 296;
+  int blocks = (a.rows + 63) / 64;
+  if (blocks > 148) blocks = 148;
   act_bwd_kernel<<<blocks, 256, 0, stream>>>(a);
   SDUMC_CUDA(cudaGetLastError());
   return 0;

@@ -144,7 +144,7 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
 //   dH_l (+)= (sum_q P_lq dO_q) * M_in                (value path; the GEMM adds dZ W_in)
 // ------------------------------------------------------------------------------------------
 template <int NQ>
-__global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
+__global__ void __launch_bounds__(256, 2) attn_bwd_kernel(AttnBwdArgs a) {
   __shared__ float dO_s[NQ][G];
   __shared__ float Qp_s[NQ][G];
   __shared__ float red_q[NQ][G];
@@ -187,11 +187,26 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) db_acc[j] = 0.f;
 
+  // software pipeline: the next row's X', K (and dH when accumulating) are in flight while this row computes
+  uint4 nx = make_uint4(0, 0, 0, 0), nk = nx, nh = nx;
+  if (warp < L) {
+    const long row0 = (long)b * L + warp;
+    nx = __ldg(reinterpret_cast<const uint4*>(a.X + row0 * a.ldx + g0));
+    nk = __ldg(reinterpret_cast<const uint4*>(a.Kt + row0 * a.ldk + g0));
+    if (a.dh_mode == 1) nh = *reinterpret_cast<const uint4*>(a.dH + row0 * a.lddh + g0);
+  }
   for (int l = warp; l < L; l += 8) {
     const long row = (long)b * L + l;
     float x[8], k[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a.X + row * a.ldx + g0)), x);
-    unpack8(__ldg(reinterpret_cast<const uint4*>(a.Kt + row * a.ldk + g0)), k);
+    unpack8(nx, x);
+    unpack8(nk, k);
+    const uint4 oldh = nh;
+    if (l + 8 < L) {
+      const long rown = row + 8;
+      nx = __ldg(reinterpret_cast<const uint4*>(a.X + rown * a.ldx + g0));
+      nk = __ldg(reinterpret_cast<const uint4*>(a.Kt + rown * a.ldk + g0));
+      if (a.dh_mode == 1) nh = *reinterpret_cast<const uint4*>(a.dH + rown * a.lddh + g0);
+    }
     float dP[NQ];
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
@@ -248,7 +263,7 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(AttnBwdArgs a) {
     uint4* hp = reinterpret_cast<uint4*>(a.dH + row * a.lddh + g0);
     if (a.dh_mode == 1) {
       float old[8];
-      unpack8(*hp, old);
+      unpack8(oldh, old);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dXv[j] += old[j];
     }

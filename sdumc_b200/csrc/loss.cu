@@ -358,10 +358,12 @@ __global__ void __launch_bounds__(256) rnc_col_kernel(RncArgs a, const float* Cm
   const int jl = threadIdx.x & 31, dg = threadIdx.x >> 5;  // dims [dg*8, dg*8+8)
   const int j = blockIdx.x * 32 + jl;
   if (j >= n) return;
+  // anchor rows are split over gridDim.y blocks (partial sums meet in the fp32 atomics below)
+  const int il0 = (int)(((long)rows * blockIdx.y) / gridDim.y), il1 = (int)(((long)rows * (blockIdx.y + 1)) / gridDim.y);
   for (int d0 = dg * 8; d0 < D; d0 += 64) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float csum = 0.f;
-    for (int il = 0; il < rows; ++il) {
+    for (int il = il0; il < il1; ++il) {
       const float c = Cmat[(long)il * n + j];
       const float4* fi = reinterpret_cast<const float4*>(a.feats + (long)(a.row_begin + il) * D + d0);
       const float4 u = __ldg(fi), v = __ldg(fi + 1);
@@ -449,7 +451,8 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
   if (a.dfeats) {
     rnc_rowgrad_kernel<<<rows, 256, 0, stream>>>(a, Cmat);
     SDUMC_CUDA(cudaGetLastError());
-    rnc_col_kernel<<<(a.n + 31) / 32, 256, 0, stream>>>(a, Cmat);
+    const int ysplit = rows >= 512 ? 16 : (rows >= 64 ? 4 : 1);
+    rnc_col_kernel<<<dim3((a.n + 31) / 32, ysplit), 256, 0, stream>>>(a, Cmat);
     SDUMC_CUDA(cudaGetLastError());
   }
   return 0;
