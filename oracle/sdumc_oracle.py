@@ -130,11 +130,15 @@ def _identity_drop(_site: str, x: torch.Tensor) -> torch.Tensor:
     return x
 
 
-def _mlp(P: Params, name: str, x: torch.Tensor, n_layers: int, drop: DropFn, lin=None) -> torch.Tensor:
+def _relu(_name: str, z: torch.Tensor) -> torch.Tensor:
+    return torch.relu(z)
+
+
+def _mlp(P: Params, name: str, x: torch.Tensor, n_layers: int, drop: DropFn, lin=None, relu=None) -> torch.Tensor:
     """MLP() factory :264-273 — Linear, ReLU, Dropout per layer; layer i lives at index 3*i."""
-    lin = lin or _linear
+    lin, relu = lin or _linear, relu or _relu
     for i in range(n_layers):
-        x = drop(f"{name}.{i}", torch.relu(lin(P, f"{name}.{3 * i}", x)))
+        x = drop(f"{name}.{i}", relu(f"{name}.{3 * i}", lin(P, f"{name}.{3 * i}", x)))
     return x
 
 
@@ -163,17 +167,19 @@ def pool_attention(P: Params, prefix: str, H: torch.Tensor, queries: Optional[to
 
 
 def forward(P: Params, audio: torch.Tensor, text: torch.Tensor, video: torch.Tensor,
-            drop: Optional[DropFn] = None, lin=None, rnd=None):
+            drop: Optional[DropFn] = None, lin=None, rnd=None, relu=None):
     """WengnetMOSEIMultViewsTextMissing.forward (:275-370).
 
     Returns (vals_out [B,1], [fused [B,128], feat4rnc [B,64], text_hidden [B,256], cross_text [B,7,128]]).
     `drop(site, x)` applies dropout at the named site (None = eval mode).  `lin(P, name, x)` optionally
-    replaces every nn.Linear evaluation and `rnd(tag, x)` is applied to the tanh key projections (tests use
-    the two hooks to emulate the rounding points of the CUDA path); the math is unchanged.
+    replaces every nn.Linear evaluation, `rnd(tag, x)` is applied to the tanh key projections and
+    `relu(name, z)` replaces the ReLUs (tests use the hooks to emulate the rounding points of the CUDA path
+    and to pin the ReLU on/off pattern to the one the CUDA forward took); the math is unchanged.
     """
     drop = drop or _identity_drop
     lin = lin or _linear
-    mlp = lambda name, x, n: _mlp(P, name, x, n, drop, lin)  # noqa: E731
+    relu = relu or _relu
+    mlp = lambda name, x, n: _mlp(P, name, x, n, drop, lin, relu)  # noqa: E731
     Ha = lin(P, "frame_dim_reshape_0", audio)
     Ht = lin(P, "frame_dim_reshape_1", text)
     Hv = lin(P, "frame_dim_reshape_2", video)
@@ -211,7 +217,7 @@ def forward(P: Params, audio: torch.Tensor, text: torch.Tensor, video: torch.Ten
     f = (W * r.unsqueeze(2)).sum(dim=1)                                         # [B,128] (:356-358)
 
     vals_out = lin(P, "fc_out_v", f)
-    feat4rnc = lin(P, "orgin_linear_change.2", torch.relu(lin(P, "orgin_linear_change.0", f)))
+    feat4rnc = lin(P, "orgin_linear_change.2", relu("orgin_linear_change.0", lin(P, "orgin_linear_change.0", f)))
     return vals_out, [f, feat4rnc, text_hidden, ct]
 
 
@@ -339,11 +345,12 @@ def adam_update(P: Params, grads: Dict[str, Optional[torch.Tensor]], state: dict
 
 
 def loss_and_grads(P: Params, audio, text, feat4, video, vals, w: Optional[dict] = None,
-                   drop0: Optional[DropFn] = None, drop1: Optional[DropFn] = None, lin=None, rnd=None):
+                   drop0: Optional[DropFn] = None, drop1: Optional[DropFn] = None, lin=None, rnd=None,
+                   relu0=None, relu1=None):
     """Both passes + loss + autograd gradients w.r.t. every parameter (None for dead ones)."""
     leaves = {k: v.detach().clone().requires_grad_(True) for k, v in P.items()}
-    out0 = forward(leaves, audio, text, video, drop0, lin, rnd)
-    out1 = forward(leaves, audio, feat4, video, drop1, lin, rnd)
+    out0 = forward(leaves, audio, text, video, drop0, lin, rnd, relu0)
+    out1 = forward(leaves, audio, feat4, video, drop1, lin, rnd, relu1)
     loss, terms = distill_loss(out0, out1, vals, w)
     names = list(leaves)
     gs = torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)

@@ -36,6 +36,7 @@ class _UMCFunction(torch.autograd.Function):
         st = module._engine.forward(W, {"a": audio, "t0": text, "v": video}, cfg)
         vals, fused, rnc, th, ct = Engine.outputs(st)
         ctx.module, ctx.st = module, (st if need_grad else None)
+        module._last_state = st if module.keep_last_state else None   # test hook (tests/parity_common.py)
         ctx.set_materialize_grads(False)
         return vals[0].clone(), fused[0].clone(), rnc[0].clone(), th[0].contiguous(), ct[0].clone()
 
@@ -64,6 +65,8 @@ class WengnetMOSEIMultViewsTextMissing(nn.Module):
         self.layout = ParamLayout(args.input_dims)
         self.dropout_seed = int(getattr(args, "seed", 100))
         self._step = 0
+        self.keep_last_state = False
+        self._last_state = None
         self._engine = None
         self._flat = None
         self._shadow = None

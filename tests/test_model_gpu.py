@@ -6,14 +6,16 @@ Tolerances (BASELINE.json north_star: bf16 operands, fp32 accumulation):
   * vs the EXACT fp64 oracle: predictions and loss terms max|err| / max|ref| <= 1e-2, embeddings
     <= 2.5e-2 (the reference's own bf16-autocast forward differs from its fp32 forward
     by 0.5-2.1e-2 on the embeddings);
-  * gradients vs the oracle evaluated with the CUDA path's rounding points (bf16 storage of H / K / the
-    backward GEMM operands, tf32 forward MLP operands — tests/parity_common.emu_*): relative L2 error
-    <= 2e-2 for every parameter tensor and max|err| / max|ref| <= 2e-2 for at least 85 % of them.
-    Why not the exact oracle / a pure max-norm for gradients: a ReLU unit whose pre-activation is within
-    forward rounding noise of 0 flips between the two implementations and changes one row of a weight
-    gradient by O(1/rows) of its magnitude — a discontinuity of the model, not an error of the kernels
-    (measured: with the rounding points emulated the forward agrees to 4e-4 and gradients to ~5e-3, except
-    those isolated rows).
+  * gradients vs the oracle evaluated (a) with the CUDA path's rounding points (bf16 storage of H / K /
+    the backward GEMM operands, tf32 forward MLP operands — tests/parity_common.emu_*) and (b) with every
+    ReLU's on/off pattern pinned to the one the CUDA forward took (the saved activations are read back
+    through a test hook; the fraction of units on which the oracle's own sign disagrees is asserted to be
+    < 0.2 %): relative L2 error <= 2e-2 for every parameter tensor and max|err| / max|ref| <= 2e-2 for at
+    least 85 % of them.
+    Why (b): a ReLU unit whose pre-activation is within forward rounding noise of 0 flips between two
+    implementations and changes a whole sample's backward signal — a discontinuity of the model, not an
+    error of the kernels (measured without (b): forward agrees to 4e-4, gradients to ~5e-3 except where a
+    flipped unit sits upstream).
 """
 import pytest
 import torch
@@ -33,7 +35,9 @@ S0DIMS = dict(dims=(1024, 4096, 1024, 4096), frames=(150, 40, 100, 37), B=32)
 def _check_outputs(res):
     def tol(k):
         return OUT_TOL if (k.endswith("/vals") or k.startswith("term/") or k == "loss") else EMB_TOL
-    bad = {k: v for k, v in res.items() if not k.startswith("grad") and not (v <= tol(k))}
+    bad = {k: v for k, v in res.items() if not k.startswith(("grad", "stat/")) and not (v <= tol(k))}
+    if "stat/relu_flip_frac" in res:   # units within rounding noise of 0: must be rare
+        assert res["stat/relu_flip_frac"] < 2e-3, res["stat/relu_flip_frac"]
     assert not bad, "outputs out of tolerance: " + ", ".join(f"{k}={v:.3g}" for k, v in sorted(bad.items()))
 
 
