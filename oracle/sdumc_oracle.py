@@ -267,9 +267,11 @@ def rmse_loss(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     return torch.sqrt(((p - t) ** 2).mean())
 
 
-def rnc_loss(features: torch.Tensor, labels: torch.Tensor, temperature: float = 2.0) -> torch.Tensor:
+def rnc_loss(features: torch.Tensor, labels: torch.Tensor, temperature: float = 2.0, anchors=None) -> torch.Tensor:
     """RnCLoss.forward (loss.py:278-315) with LabelDifference 'l1' (:248-254) and
-    FeatureSimilarity 'l2' (:262-268).  features [B,2,D], labels [B,1]."""
+    FeatureSimilarity 'l2' (:262-268).  features [B,2,D], labels [B,1].
+    `anchors` (iterable of row indices of the 2B x 2B problem) restricts the outer sum to those anchor rows:
+    the share of the loss a data-parallel rank computes; the shares of all ranks add up to the loss."""
     f = torch.cat([features[:, 0], features[:, 1]], dim=0)        # [n,D]
     y = labels.repeat(2, 1)                                       # [n,1]
     n = f.shape[0]
@@ -283,7 +285,7 @@ def rnc_loss(features: torch.Tensor, labels: torch.Tensor, temperature: float = 
     d = d[off].view(n, n - 1)
     # for anchor i and positive k: negatives are the j with d_ij >= d_ik - 1e-4 (:303)
     total = logit.new_zeros(())
-    for i in range(n):
+    for i in (range(n) if anchors is None else anchors):
         member = d[i][None, :] >= (d[i][:, None] - 0.0001)        # [k, j]
         denom = (member.to(e.dtype) * e[i][None, :]).sum(dim=1)
         total = total - (logit[i] - denom.log()).sum() / (n * (n - 1))

@@ -88,7 +88,6 @@ class Trainer:
         self.y2 = z(R)
         n_g = 2 * B * self.world
         self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64), dtype=torch.uint8, device=dev)
-        self.dfeats_g = z(n_g * 64).view(n_g, 64) if self.world > 1 else None
         self.n_steps = 0
         self._graph = None
         self._outputs = None
@@ -143,24 +142,15 @@ class Trainer:
             self.y2[B:].copy_(y)
             ops.rnc(st.t["rnc"], self.y2, loss=self.rnc_val, dfeats=self.d_rnc, grad_scale=w6, workspace=self.rnc_ws)
         else:
-            import torch.distributed as dist
-            dist.all_reduce(self.sums, group=self.pg)
-            feats_all = torch.empty(W_, 2, B, 64, device=self.device)
-            y_all = torch.empty(W_, B, device=self.device)
-            dist.all_gather_into_tensor(feats_all, rnc.contiguous(), group=self.pg)
-            dist.all_gather_into_tensor(y_all, y.contiguous(), group=self.pg)
-            Bg = B * W_
-            feats_g = feats_all.permute(1, 0, 2, 3).reshape(2 * Bg, 64).contiguous()     # (view, rank, b)
-            y_g = y_all.reshape(Bg).repeat(2).contiguous()
-            self.dfeats_g.zero_()
-            for v in range(2):                                                           # this rank's anchors
-                lo = v * Bg + rank * B
-                ops.rnc(feats_g, y_g, loss=self.rnc_val, dfeats=self.dfeats_g, row_begin=lo, row_end=lo + B,
-                        grad_scale=w6, workspace=self.rnc_ws)
-            dist.all_reduce(self.rnc_val, group=self.pg)
-            dist.all_reduce(self.dfeats_g, group=self.pg)
-            dg = self.dfeats_g.view(2, W_, B, 64)[:, rank]
-            self.d_rnc.view(2, B, 64).copy_(dg)
+            from . import dp
+            dp.reduce_sums(self.sums, self.pg)
+
+            def rnc_fn(feats_g, y_g, lo, hi, loss, dfeats):
+                ops.rnc(feats_g, y_g, loss=loss, dfeats=dfeats, row_begin=lo, row_end=hi, grad_scale=w6,
+                        workspace=self.rnc_ws)
+            loss_g, d_local = dp.rnc_global(rnc.contiguous(), y.contiguous(), self.pg, rnc_fn)
+            self.rnc_val.copy_(loss_g)
+            self.d_rnc.view(2, B, 64).copy_(d_local)
         ops.loss_finish(vals[0], vals[1], y, th[0], th[1], ct[0], ct[1], f[0], f[1], B=B, sums=self.sums,
                         rnc=self.rnc_val, B_global=B * W_, w=self.loss_w, terms=self.terms,
                         d_v0=self.d_vals[:B], d_v1=self.d_vals[B:], d_th1=self.d_th[B:], d_ct1=self.d_ct[B:],

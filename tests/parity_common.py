@@ -192,7 +192,9 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
         names = list(leaves)
         gs = torch.autograd.grad(oloss, [leaves[k] for k in names], allow_unused=True)
         ograds = dict(zip(names, gs))
-        res = {"loss": nerr(loss.reshape(()), oloss.reshape(()))}
+        # <outputs, C> is a random-sign sum: normalise its error by the sum of |contributions|
+        scale = float(sum((t.detach() * c).abs().sum() for t, c in zip(outs_ref, cts)))
+        res = {"loss": abs(float(loss) - float(oloss)) / scale}
         if stats:
             res["stat/relu_flip_frac"] = stats["flipped"] / max(1, stats["units"])
         for tag, (v, e), (ov, oe) in (("p0", (v0, e0), o0), ("p1", (v1, e1), o1)):

@@ -20,7 +20,11 @@ def nerr(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-20))
 
 
+RESULTS = {}
+
+
 def report(tag, d):
+    RESULTS[tag] = d
     print(f"== {tag}: " + "  ".join(f"{k}={v:.2e}" for k, v in d.items()), flush=True)
 
 
