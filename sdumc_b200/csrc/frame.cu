@@ -34,8 +34,8 @@ __device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
 template <int NQ>
 __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolFwdArgs a) {
   extern __shared__ float sm[];
-  float* Ps = sm;                 // [L][NQ]
-  float* red = sm + a.L * NQ;     // [NQ][G]
+  float* Ps = sm;                                   // [L][NQ]
+  float* red = sm + ((a.L * NQ + 3) & ~3);          // [8 warps][NQ][G], 16-byte aligned
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = a.L;
@@ -43,7 +43,6 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolFwdArgs a) {
   float* Sg = a.S + (long)b * L * NQ;
 
   for (int i = tid; i < L * NQ; i += 256) Ps[i] = Sg[i];
-  for (int i = tid; i < NQ * G; i += 256) red[i] = 0.f;
   __syncthreads();
   for (int q = warp; q < NQ; q += 8) {
     float m = -INFINITY;
@@ -95,16 +94,21 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolFwdArgs a) {
       for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(p, x[j], acc[q][j]);
     }
   }
+  // per-warp partials -> shared memory [8][NQ][G], summed by the writer loop below (no atomics)
 #pragma unroll
-  for (int q = 0; q < NQ; ++q)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red[q * G + lane * 8 + j], acc[q][j]);
+  for (int q = 0; q < NQ; ++q) {
+    float* dst = red + (warp * NQ + q) * G + lane * 8;
+    *reinterpret_cast<float4*>(dst) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
+  }
   __syncthreads();
 
   const uint32_t thr = drop_threshold(a.drop_p);
   const float scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   for (int i = tid; i < NQ * G; i += 256) {
-    const float o = red[i];
+    float o = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) o += red[w * NQ * G + i];
     a.O_pre[(long)b * NQ * G + i] = o;
     float y = o;
     if (a.drop_p > 0.f) {
@@ -120,7 +124,7 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.X && a.S && a.O_pre && a.out, "pool_fwd: null pointer");
   SDUMC_CHECK_ARG(a.B > 0 && a.L > 0 && (a.nq == 1 || a.nq == 7), "pool_fwd: bad shape B=%d L=%d nq=%d", a.B, a.L, a.nq);
   SDUMC_CHECK_ARG(a.ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(a.X) & 15u) == 0, "pool_fwd: X must be 16-byte aligned");
-  const size_t smem = (size_t)(a.L * a.nq + a.nq * G) * sizeof(float);
+  const size_t smem = (size_t)(((a.L * a.nq + 3) & ~3) + 8 * a.nq * G) * sizeof(float);
   SDUMC_CHECK_ARG(smem <= 200 * 1024, "pool_fwd: L=%d too long for the shared-memory softmax", a.L);
   if (a.nq == 1) {
     static bool done1 = false;
@@ -142,14 +146,18 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
 //   dZ_l = (sum_q dS_lq Qp_q) * (1 - K_l^2)          -> bf16, feeds the two tcgen05 GEMMs
 //   dQp_q = sum_l dS_lq K_l;  db_in = sum_l dZ_l
 //   dH_l (+)= (sum_q P_lq dO_q) * M_in                (value path; the GEMM adds dZ W_in)
+// One CTA per sample, one warp per frame row, a lane owns 8 of the 256 columns.  dO and Qp slices live in
+// registers (no shared-memory traffic in the row loop), the sample's probabilities in shared memory, the
+// next row's X'/K/dH loads are in flight while a row computes, and the NQ per-row dot products are
+// reduced with a halving butterfly (9 shuffles + NQ broadcasts instead of 5 * NQ).
 // ------------------------------------------------------------------------------------------
 template <int NQ>
-__global__ void __launch_bounds__(256, 2) attn_bwd_kernel(AttnBwdArgs a) {
+__global__ void __launch_bounds__(256, (NQ == 1) ? 3 : 1) attn_bwd_kernel(AttnBwdArgs a) {
+  extern __shared__ float P_s[];  // [L][8] probabilities of this sample (padded to 8 per row)
   __shared__ float dO_s[NQ][G];
-  __shared__ float Qp_s[NQ][G];
   __shared__ float red_q[NQ][G];
   __shared__ float red_b[G];
-  __shared__ float delta_s[NQ];
+  __shared__ float delta_s[8];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = a.L;
@@ -164,10 +172,14 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(AttnBwdArgs a) {
       g = elem_rand(key, a.out_site, e) >= thr ? g * oscale : 0.f;
     }
     (&dO_s[0][0])[i] = g;
-    (&Qp_s[0][0])[i] = a.Qp[(long)b * a.qp_stride_b + i];
     (&red_q[0][0])[i] = 0.f;
   }
+  for (int i = tid; i < L * 8; i += 256) {
+    const int l = i >> 3, q = i & 7;
+    P_s[i] = q < NQ ? __ldg(a.P + ((long)b * L + l) * NQ + q) : 0.f;
+  }
   if (tid < G) red_b[tid] = 0.f;
+  if (tid < 8) delta_s[tid] = 0.f;
   __syncthreads();
   for (int q = warp; q < NQ; q += 8) {
     float s = 0.f;
@@ -178,16 +190,27 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(AttnBwdArgs a) {
   __syncthreads();
 
   const int g0 = lane * 8;
-  float dq_acc[NQ][8];
-  float db_acc[8];
+  float dO[NQ][8], Qp[NQ][8], dq_acc[NQ][8], db_acc[8];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q)
+  for (int q = 0; q < NQ; ++q) {
+    const float4 d0 = *reinterpret_cast<const float4*>(&dO_s[q][g0]);
+    const float4 d1 = *reinterpret_cast<const float4*>(&dO_s[q][g0 + 4]);
+    const float* qp = a.Qp + (long)b * a.qp_stride_b + q * G + g0;
+    const float4 q0 = __ldg(reinterpret_cast<const float4*>(qp));
+    const float4 q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
+    dO[q][0] = d0.x; dO[q][1] = d0.y; dO[q][2] = d0.z; dO[q][3] = d0.w;
+    dO[q][4] = d1.x; dO[q][5] = d1.y; dO[q][6] = d1.z; dO[q][7] = d1.w;
+    Qp[q][0] = q0.x; Qp[q][1] = q0.y; Qp[q][2] = q0.z; Qp[q][3] = q0.w;
+    Qp[q][4] = q1.x; Qp[q][5] = q1.y; Qp[q][6] = q1.z; Qp[q][7] = q1.w;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dq_acc[q][j] = 0.f;
+  }
 #pragma unroll
   for (int j = 0; j < 8; ++j) db_acc[j] = 0.f;
+  // which of the (up to 8) per-row sums this lane ends up owning after the butterfly
+  const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+  const float my_delta = delta_s[own];
 
-  // software pipeline: the next row's X', K (and dH when accumulating) are in flight while this row computes
   uint4 nx = make_uint4(0, 0, 0, 0), nk = nx, nh = nx;
   if (warp < L) {
     const long row0 = (long)b * L + warp;
@@ -207,41 +230,58 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(AttnBwdArgs a) {
       nk = __ldg(reinterpret_cast<const uint4*>(a.Kt + rown * a.ldk + g0));
       if (a.dh_mode == 1) nh = *reinterpret_cast<const uint4*>(a.dH + rown * a.lddh + g0);
     }
-    float dP[NQ];
+    const float4 p0 = *reinterpret_cast<const float4*>(&P_s[l * 8]);
+    const float4 p1 = *reinterpret_cast<const float4*>(&P_s[l * 8 + 4]);
+    const float Pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+
+    // partial dot products of this lane's 8 columns
+    float v[8];
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float4 d0 = *reinterpret_cast<const float4*>(&dO_s[q][g0]);
-      const float4 d1 = *reinterpret_cast<const float4*>(&dO_s[q][g0 + 4]);
-      float s = x[0] * d0.x;
-      s = fmaf(x[1], d0.y, s); s = fmaf(x[2], d0.z, s); s = fmaf(x[3], d0.w, s);
-      s = fmaf(x[4], d1.x, s); s = fmaf(x[5], d1.y, s); s = fmaf(x[6], d1.z, s); s = fmaf(x[7], d1.w, s);
-      dP[q] = s;
+    for (int q = 0; q < 8; ++q) {
+      if (q < NQ) {
+        float s = x[0] * dO[q][0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) s = fmaf(x[j], dO[q][j], s);
+        v[q] = s;
+      } else {
+        v[q] = 0.f;
+      }
     }
+    float dS[NQ];
+    if (NQ == 1) {
+      const float dP = warp_sum(v[0]);
+      dS[0] = a.alpha * Pv[0] * (dP - delta_s[0]);
+    } else {
+      // halving butterfly: after 4+2+1+2 shuffles lane `own` holds the full sum of index `own`
+      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+      float w[4], u[2];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
+      for (int i = 0; i < 4; ++i) {
+        const float keep = b4 ? v[4 + i] : v[i], send = b4 ? v[i] : v[4 + i];
+        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
 #pragma unroll
-      for (int q = 0; q < NQ; ++q) dP[q] += __shfl_xor_sync(0xffffffffu, dP[q], o);
-    float dS[NQ], Pv[NQ];
+      for (int i = 0; i < 2; ++i) {
+        const float keep = b3 ? w[2 + i] : w[i], send = b3 ? w[i] : w[2 + i];
+        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      float t = (b2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u[0] : u[1], 4);
+      t += __shfl_xor_sync(0xffffffffu, t, 2);
+      t += __shfl_xor_sync(0xffffffffu, t, 1);
+      const float mine = a.alpha * P_s[l * 8 + own] * (t - my_delta);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      Pv[q] = __ldg(a.P + row * NQ + q);
-      dS[q] = a.alpha * Pv[q] * (dP[q] - delta_s[q]);
+      for (int q = 0; q < NQ; ++q)
+        dS[q] = __shfl_sync(0xffffffffu, mine, ((q & 4) ? 16 : 0) + ((q & 2) ? 8 : 0) + ((q & 1) ? 4 : 0));
     }
     float dK[8], dXv[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { dK[j] = 0.f; dXv[j] = 0.f; }
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
-      const float4 q0 = *reinterpret_cast<const float4*>(&Qp_s[q][g0]);
-      const float4 q1 = *reinterpret_cast<const float4*>(&Qp_s[q][g0 + 4]);
-      const float4 d0 = *reinterpret_cast<const float4*>(&dO_s[q][g0]);
-      const float4 d1 = *reinterpret_cast<const float4*>(&dO_s[q][g0 + 4]);
-      const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-      const float dd[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        dK[j] = fmaf(dS[q], qq[j], dK[j]);
-        dXv[j] = fmaf(Pv[q], dd[j], dXv[j]);
+        dK[j] = fmaf(dS[q], Qp[q][j], dK[j]);
+        dXv[j] = fmaf(Pv[q], dO[q][j], dXv[j]);
         dq_acc[q][j] = fmaf(dS[q], k[j], dq_acc[q][j]);
       }
     }
@@ -254,20 +294,19 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(AttnBwdArgs a) {
     *reinterpret_cast<uint4*>(a.dZ + row * a.lddz + g0) = pack8(dZ);
 
     if (a.fmask_site) {
-      const U4 w = frame_mask_words(key, a.fmask_site, (uint32_t)row, (uint32_t)(g0 >> 7));
+      const U4 wm = frame_mask_words(key, a.fmask_site, (uint32_t)row, (uint32_t)(g0 >> 7));
       const int wsel = (g0 >> 5) & 3;
-      const uint32_t bits = (wsel == 0 ? w.x : (wsel == 1 ? w.y : (wsel == 2 ? w.z : w.w))) >> (g0 & 31);
+      const uint32_t bits = (wsel == 0 ? wm.x : (wsel == 1 ? wm.y : (wsel == 2 ? wm.z : wm.w))) >> (g0 & 31);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dXv[j] = ((bits >> j) & 1u) ? 2.f * dXv[j] : 0.f;
     }
-    uint4* hp = reinterpret_cast<uint4*>(a.dH + row * a.lddh + g0);
     if (a.dh_mode == 1) {
       float old[8];
       unpack8(oldh, old);
 #pragma unroll
       for (int j = 0; j < 8; ++j) dXv[j] += old[j];
     }
-    *hp = pack8(dXv);
+    *reinterpret_cast<uint4*>(a.dH + row * a.lddh + g0) = pack8(dXv);
   }
 
 #pragma unroll
@@ -278,9 +317,9 @@ __global__ void __launch_bounds__(256, 2) attn_bwd_kernel(AttnBwdArgs a) {
   for (int j = 0; j < 8; ++j) atomicAdd(&red_b[g0 + j], db_acc[j]);
   __syncthreads();
   for (int i = tid; i < NQ * G; i += 256) {
-    const float v = (&red_q[0][0])[i];
-    if (a.qp_stride_b == 0) atomicAdd(a.dQp + i, v);            // shared context vector: sum over the batch
-    else a.dQp[(long)b * a.dqp_stride_b + i] = v;
+    const float val = (&red_q[0][0])[i];
+    if (a.qp_stride_b == 0) atomicAdd(a.dQp + i, val);            // shared context vector: sum over the batch
+    else a.dQp[(long)b * a.dqp_stride_b + i] = val;
   }
   if (tid < G) atomicAdd(a.db + tid, red_b[tid]);
 }
@@ -290,8 +329,16 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
                   "attn_bwd: null pointer");
   SDUMC_CHECK_ARG(a.B > 0 && a.L > 0 && (a.nq == 1 || a.nq == 7), "attn_bwd: bad shape");
   SDUMC_CHECK_ARG(a.ldx % 8 == 0 && a.ldk % 8 == 0 && a.lddz % 8 == 0 && a.lddh % 8 == 0, "attn_bwd: ld %% 8");
-  if (a.nq == 1) attn_bwd_kernel<1><<<a.B, 256, 0, stream>>>(a);
-  else           attn_bwd_kernel<7><<<a.B, 256, 0, stream>>>(a);
+  const size_t smem = (size_t)a.L * 8 * sizeof(float);
+  SDUMC_CHECK_ARG(smem <= 160 * 1024, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    attr_done = true;
+  }
+  if (a.nq == 1) attn_bwd_kernel<1><<<a.B, 256, smem, stream>>>(a);
+  else           attn_bwd_kernel<7><<<a.B, 256, smem, stream>>>(a);
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

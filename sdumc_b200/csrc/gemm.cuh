@@ -288,19 +288,24 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       for (int c = 0; c < kBlockN / 32; ++c) {
         uint32_t acc_r[32];
         tmem_ld32(taddr + (uint32_t)(c * 32), acc_r);
-        tmem_ld_wait();
         const int n0 = n_blk * kBlockN + c * 32;
+        const bool full = (n0 + 32 <= sh.N);
+        // the bias chunk is fetched while the TMEM load is in flight
+        float4 bia[8];
+        if (ep.bias && full) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bia[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+        }
+        tmem_ld_wait();
         if (n0 >= sh.N) continue;  // warp-uniform
         float v[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc_r[j]);
-        const bool full = (n0 + 32 <= sh.N);
         if (ep.bias) {
           if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(ep.bias + n0 + j));
-              v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] += bia[j].x; v[4 * j + 1] += bia[j].y; v[4 * j + 2] += bia[j].z; v[4 * j + 3] += bia[j].w;
             }
           } else {
 #pragma unroll
@@ -359,20 +364,38 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
             }
           }
-#pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            if (q >= ep.nq) break;
-            const float4* qp = reinterpret_cast<const float4*>(qrow + (long)q * sh.N + n0);
-            float s = 0.f;
+          // column groups outer, queries inner: 7 independent accumulators, no serial FMA chain per query
+          if (ep.nq == 7) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float4 w4 = __ldg(qp + j);
-              s = fmaf(v[4 * j], w4.x, s);
-              s = fmaf(v[4 * j + 1], w4.y, s);
-              s = fmaf(v[4 * j + 2], w4.z, s);
-              s = fmaf(v[4 * j + 3], w4.w, s);
+              float4 w4[7];
+#pragma unroll
+              for (int q = 0; q < 7; ++q)
+                w4[q] = __ldg(reinterpret_cast<const float4*>(qrow + (long)q * sh.N + n0) + j);
+#pragma unroll
+              for (int q = 0; q < 7; ++q) {
+                sc[q] = fmaf(v[4 * j], w4[q].x, sc[q]);
+                sc[q] = fmaf(v[4 * j + 1], w4[q].y, sc[q]);
+                sc[q] = fmaf(v[4 * j + 2], w4[q].z, sc[q]);
+                sc[q] = fmaf(v[4 * j + 3], w4[q].w, sc[q]);
+              }
             }
-            sc[q] += s;
+          } else {
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+              if (q >= ep.nq) break;
+              const float4* qp = reinterpret_cast<const float4*>(qrow + (long)q * sh.N + n0);
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 w4 = __ldg(qp + j);
+                s0 = fmaf(v[4 * j], w4.x, s0);
+                s1 = fmaf(v[4 * j + 1], w4.y, s1);
+                s2 = fmaf(v[4 * j + 2], w4.z, s2);
+                s3 = fmaf(v[4 * j + 3], w4.w, s3);
+              }
+              sc[q] += (s0 + s1) + (s2 + s3);
+            }
           }
           continue;
         }

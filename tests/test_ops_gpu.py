@@ -18,7 +18,7 @@ def _run(fn, *a, **kw):
 
 
 @pytest.mark.parametrize("nq,train,B,L", [(1, False, 5, 70), (7, False, 5, 70), (1, True, 5, 70), (7, True, 5, 70),
-                                          (7, True, 3, 300), (7, False, 130, 1)])
+                                          (7, True, 3, 300), (7, False, 130, 2), (1, True, 2, 1000)])
 def test_pooling_attention_block_forward_backward(nq, train, B, L):
     res = _run(lambda p: p.attention_block(nq, train, B=B, L=L))
     (d,) = res.values()
