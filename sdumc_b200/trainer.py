@@ -88,6 +88,7 @@ class Trainer:
         self.y2 = z(R)
         n_g = 2 * B * self.world
         self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64), dtype=torch.uint8, device=dev)
+        self.train_dropout = True      # tests switch dropout off to compare against a deterministic reference
         self.n_steps = 0
         self._graph = None
         self._outputs = None
@@ -158,7 +159,7 @@ class Trainer:
 
     def _step_body(self):
         self.step_dev.add_(1)
-        st = self._forward(dropout=True, need_grad=True)
+        st = self._forward(dropout=self.train_dropout, need_grad=True)
         self._loss_and_seeds(st)
         self.grads.zero_()
         self.engine.backward(self.W, st, d_vals=self.d_vals, d_fused=self.d_f, d_rnc=self.d_rnc, d_th=self.d_th,
