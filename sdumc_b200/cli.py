@@ -1,0 +1,246 @@
+"""Shared driver of the two drop-in CLIs (main_frame_val_text_missing.py and ..._inference.py).
+
+Every flag of the reference parsers (main_frame_val_text_missing.py:213-252, ..._inference.py:251-288) is
+kept with its default; additive flags select the data source because the reference hard-codes dataset
+paths in config.py (:8-66): --feat_root / --label_path for the reference's on-disk layout, or --synthetic N
+for S0-shaped synthetic utterances.  Multi-GPU: launch with torch.distributed.run (one process per GPU).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import time
+
+import numpy as np
+import torch
+
+
+def build_parser(inference: bool) -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser()
+    # ---- reference flags (kept verbatim) ----
+    p.add_argument('--dataset', type=str, default=None, help='dataset')
+    p.add_argument('--train_dataset', type=str, default=None, help='dataset')
+    p.add_argument('--valid_dataset', type=str, default=None, help='dataset')
+    p.add_argument('--test_dataset', type=str, default=None, help='dataset')
+    p.add_argument('--audio_feature', type=str, default=None, help='audio feature name')
+    p.add_argument('--text_feature', type=str, default=None, help='text feature name')
+    p.add_argument('--video_feature', type=str, default=None, help='video feature name')
+    p.add_argument('--feat4_feature', type=str, default=None, help='4th feature name')
+    p.add_argument('--debug', action='store_true', default=False, help='whether use debug to limit samples')
+    p.add_argument('--test_sets', type=str, default='test1,test2', help='process on which test sets')
+    p.add_argument('--save_root', type=str, default='./saved', help='save prediction results and models')
+    p.add_argument('--savewhole', action='store_true', default=False, help='whether save latent embeddings')
+    p.add_argument('--feat_type', type=str, default='frm_unalign', help='feature type [utt, frm_align, frm_unalign]')
+    p.add_argument('--feat_scale', type=int, default=1, help='pre-compress input')
+    p.add_argument('--model', type=str, default='wengnet', help='model name for training')
+    p.add_argument('--layers', type=str, default='256,128', help='hidden size in model training')
+    p.add_argument('--n_classes', type=int, default=-1)
+    p.add_argument('--num_folder', type=int, default=-1)
+    p.add_argument('--model_type', type=str, default='mlp')
+    p.add_argument('--full_mse_loss_w', type=float, default=0.5)
+    p.add_argument('--missing_mse_loss_w', type=float, default=0.5)
+    p.add_argument('--text_feat_loss_w', type=float, default=0.1)
+    p.add_argument('--text_query_feat_loss_w', type=float, default=0.7)
+    p.add_argument('--features_loss_w', type=float, default=0.1)
+    p.add_argument('--rnc_loss_w', type=float, default=0.8)
+    p.add_argument('--lr', type=float, default=0.0001, metavar='LR')
+    p.add_argument('--l2', type=float, default=0.00001, metavar='L2')
+    p.add_argument('--dropout', type=float, default=0.5, metavar='dropout')
+    p.add_argument('--batch_size', type=int, default=32, metavar='BS')
+    p.add_argument('--num_workers', type=int, default=0, metavar='nw')
+    p.add_argument('--epochs', type=int, default=100, metavar='E')
+    p.add_argument('--seed', type=int, default=100)
+    p.add_argument('--gpu', default=0, type=int)
+    p.add_argument('--local_rank', default=0, type=int)
+    # ---- additive flags ----
+    p.add_argument('--feat_root', type=str, default=None, help='root of <feature_name>/<utt>.npy (config.PATH_TO_FEATURES)')
+    p.add_argument('--label_path', type=str, default=None, help='label .npz (config.PATH_TO_LABEL)')
+    p.add_argument('--exclude_names', type=str, default=None,
+                   help='text file of train utterances to drop (the reference drops 51 over-long ones, cmumosei.py:10-62)')
+    p.add_argument('--synthetic', type=int, default=0, help='N synthetic S0-shaped utterances per split instead of files')
+    p.add_argument('--synthetic_ragged', action='store_true', help='ragged synthetic lengths (padding semantics)')
+    p.add_argument('--folds', type=int, default=1, help='K-fold cross-validation over the train split (reference: 1)')
+    p.add_argument('--checkpoint', type=str, default=None,
+                   help='checkpoint with ["state_dict"] (inference; the reference hard-codes its path, ..._inference.py:341)')
+    p.add_argument('--save_checkpoints', action='store_true', help='torch.save the best epochs (commented out in the reference :375)')
+    return p
+
+
+def _dist():
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 and not dist.is_initialized():
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank = int(os.environ.get("RANK", "0"))
+    return world, rank, (dist.group.WORLD if world > 1 else None)
+
+
+def load_splits(args):
+    from .dataset import Store4F, read_names_labels
+    if args.synthetic:
+        dims, frames = (1024, 4096, 1024, 4096), (384, 64, 256, 64)
+        mk = lambda n, seed: Store4F.synthetic(n, dims, frames, seed=seed, ragged=args.synthetic_ragged)  # noqa: E731
+        return mk(args.synthetic, 1234), mk(max(args.batch_size, args.synthetic // 8), 4321), \
+            mk(max(args.batch_size, args.synthetic // 8), 9876)
+    if not (args.feat_root and args.label_path):
+        raise SystemExit("give --feat_root and --label_path (reference on-disk layout) or --synthetic N")
+    names_feats = (args.audio_feature, args.text_feature, args.video_feature, args.feat4_feature)
+    ex = [l.strip() for l in open(args.exclude_names)] if args.exclude_names else []
+    stores = []
+    for split in ("train", "val", "test"):
+        names, vals = read_names_labels(args.label_path, split, args.debug, ex if split == "train" else ())
+        print(f'{split}: sample number {len(names)}')
+        stores.append(Store4F.from_disk(args.feat_root, names_feats, names, vals))
+    return tuple(stores)
+
+
+def run_split(tr, store, batch_size, train: bool, rank, world):
+    """train_or_eval_model (main…:74-178): one pass over a split.  Returns the reference's result dict."""
+    preds_full, preds_missing, labels, names = [], [], [], []
+    for batch, vals, nm in store.batches(batch_size, rank, world, lockstep=train):
+        tr.load_batch(batch["audio"], batch["text"], batch["video"], batch["feat4"], vals)
+        if train:
+            tr.train_step()
+            pf, pm = tr.predictions()
+        else:
+            out = tr.score()
+            pf, pm = out["val_preds_full"], out["val_preds_missing"]
+        preds_full.append(pf.float().cpu().numpy())           # the reference syncs per step too (:156-158)
+        preds_missing.append(pm.float().cpu().numpy())
+        labels.append(vals.numpy())
+        names += nm
+    pf, pm, y = np.concatenate(preds_full), np.concatenate(preds_missing), np.concatenate(labels)
+    return {"val_mse_full": float(np.mean((pf.reshape(-1) - y) ** 2)),
+            "val_mse_missing": float(np.mean((pm.reshape(-1) - y) ** 2)),
+            "val_preds_full": pf, "val_preds_missing": pm, "val_labels": y, "names": names}
+
+
+def make_trainer(args, stores, device, pg, state_dict=None):
+    """One trainer serves every split: its static buffers are sized for the longest utterances of all of them."""
+    from .trainer import Trainer
+    store = stores[0]
+    max_frames = tuple(max(s.max_frames[i] for s in stores) for i in range(4))
+    w = (args.full_mse_loss_w, args.missing_mse_loss_w, args.text_feat_loss_w, args.text_query_feat_loss_w,
+         args.features_loss_w, args.rnc_loss_w)
+    cap = max(args.batch_size + 1, 2)                         # +1: a trailing single sample joins the last batch
+    return Trainer(store.dims, cap, max_frames, device, lr=args.lr, weight_decay=args.l2, loss_w=w,
+                   seed=args.seed, process_group=pg, state_dict=state_dict, use_graph=True)
+
+
+def main_train(argv=None):
+    from metric import eval_mosei_metric
+    from .trainer import lr_lambda
+    args = build_parser(False).parse_args(argv)
+    args.n_classes, args.num_folder = 6, 5                    # reference :255-256
+    args.test_sets = args.test_sets.split(',')
+    world, rank, pg = _dist()
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        print(args)
+        print('====== Reading Data =======')
+    train, val, test = load_splits(args)
+    args.input_dims = train.dims
+    if rank == 0:
+        print('====== Training and Evaluation =======')
+    best_valid = {'mae': 1.0, 'f1': 0}
+    best_full, best_missing = {'mae': 1.0, 'f1': 0}, {'mae': 1.0, 'f1': 0}
+    for ii in range(args.folds):
+        if rank == 0:
+            print(f'>>>>> Cross-validation: training on the {ii+1} folder >>>>>')
+            print('Step1: build model (each folder has its own model)')
+        start = time.time()
+        torch.manual_seed(args.seed + ii)
+        tr = make_trainer(args, (train, val, test), device, pg)
+        if rank == 0:
+            print('Step2: training (multiple epoches)')
+        for epoch in range(args.epochs):
+            tr.set_lr(args.lr * lr_lambda(epoch))             # LambdaLR, stepped once per epoch (:318-321,:342)
+            t0 = time.time()
+            tres = run_split(tr, train, args.batch_size, True, rank, world)
+            if rank == 0:
+                print('used: {} s'.format(time.time() - t0))
+            run_split(tr, val, args.batch_size, False, 0, 1)
+            if rank == 0:
+                print('epoch:%d; train_val_mse_full:%.4f; train_val_mse_missing:%.4f' %
+                      (epoch + 1, tres['val_mse_full'], tres['val_mse_missing']))
+            te = run_split(tr, test, args.batch_size, False, 0, 1)
+            r_full = eval_mosei_metric(te['val_preds_full'], te['val_labels'], te['names'])
+            r_miss = eval_mosei_metric(te['val_preds_missing'], te['val_labels'], te['names'])
+            if r_full['mae'] <= best_full['mae']:
+                best_full = dict(r_full, epoch=epoch)
+                if rank == 0:
+                    print("***************better full**********************")
+                    if args.save_checkpoints:
+                        torch.save({'epoch': epoch + 1, 'state_dict': tr.state_dict()},
+                                   f'mosei_mult-view_kd_full_{best_full["mae"]}_{epoch+1}.pt')
+            if r_miss['mae'] <= best_missing['mae']:
+                best_missing = dict(r_miss, epoch=epoch)
+                if rank == 0:
+                    print("===============better missing===================")
+                    if args.save_checkpoints:
+                        torch.save({'epoch': epoch + 1, 'state_dict': tr.state_dict()},
+                                   f'mosei_mult-view_kd_missing_{best_missing["mae"]}_{epoch+1}.pt')
+            if rank == 0:
+                print("test full:")
+                print(r_full)
+                print("test missing:")
+                print(r_miss)
+                print("-" * 50)
+        if rank == 0:
+            print(f'>>>>> Finish: training on the {ii+1} data, duration: {time.time() - start} >>>>>')
+    if rank == 0:
+        print('====== Gain predition on test data =======')
+        print("best_valid:")
+        print(best_valid)
+        print("best_test_full:")
+        print(best_full)
+        print("best_test_missing:")
+        print(best_missing)
+        with open('features_ablation_study.txt', mode='a') as f:   # reference :411-416
+            f.write(f'--full_mse_loss_w={args.full_mse_loss_w} --missing_mse_loss_w={args.missing_mse_loss_w} '
+                    f'--text_feat_loss_w={args.text_feat_loss_w} --text_query_feat_loss_w={args.text_query_feat_loss_w} '
+                    f'--features_loss_w={args.features_loss_w} --rnc_loss_w={args.rnc_loss_w}\n')
+            f.write(str(best_full) + '\n' + str(best_missing) + '\n')
+        print(f'{args.audio_feature}+{args.text_feature}+{args.video_feature}')
+
+
+def main_inference(argv=None):
+    args = build_parser(True).parse_args(argv)
+    args.test_sets = args.test_sets.split(',')
+    world, rank, pg = _dist()
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    train, val, test = load_splits(args)
+    sd = None
+    if args.checkpoint:
+        ck = torch.load(args.checkpoint, map_location="cpu")
+        sd = {k.replace('module.', ''): v for k, v in ck['state_dict'].items()}   # ..._inference.py:341 (strict=False)
+    torch.manual_seed(args.seed)
+    tr = make_trainer(args, (train, val, test), device, None, state_dict=sd)
+    keys = ("val_preds_full", "val_preds_missing", "full_rep", "missing_rep", "full_rnc", "missing_rnc",
+            "text_rep_query_full", "text_rep_query_missing", "text_rep_full", "text_rep_missing")
+    results = {}
+    for split_name, store in (("train", train), ("val", val), ("test", test)):
+        acc = {k: [] for k in keys}
+        labels, names = [], []
+        t0 = time.time()
+        for batch, vals, nm in store.batches(args.batch_size, rank, world):    # whole reference batches per rank
+            tr.load_batch(batch["audio"], batch["text"], batch["video"], batch["feat4"], vals)
+            out = tr.score()
+            for k in keys:
+                acc[k].append(out[k].float().cpu().numpy())
+            labels.append(vals.numpy())
+            names += nm
+        res = {k: np.concatenate(v) for k, v in acc.items()}
+        res["val_labels"], res["names"] = np.concatenate(labels), names
+        res["val_mse_full"] = float(np.mean((res["val_preds_full"].reshape(-1) - res["val_labels"]) ** 2))
+        res["val_mse_missing"] = float(np.mean((res["val_preds_missing"].reshape(-1) - res["val_labels"]) ** 2))
+        results[split_name] = res
+        print(f'[rank {rank}] {split_name}: {len(names)} utterances in {time.time() - t0:.2f} s; '
+              f'val_mse_full:{res["val_mse_full"]:.4f}; val_mse_missing:{res["val_mse_missing"]:.4f}')
+    if args.savewhole:
+        os.makedirs(args.save_root, exist_ok=True)
+        np.savez(os.path.join(args.save_root, f'inference_rank{rank}.npz'),
+                 **{f"{s}/{k}": v for s, r in results.items() for k, v in r.items() if k != "names"})
+    return results

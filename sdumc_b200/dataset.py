@@ -1,0 +1,117 @@
+"""Feature store + collate for the 4-feature SDUMC dataset.
+
+On-disk format of the reference (toolkit/utils/read_data.py:22-49, toolkit/data/feat_data.py:171-258,
+toolkit/dataloader/cmumosei.py:133-145):
+    <feat_root>/<feature_name>/<utterance>.npy        float array [T, D]  (or a directory of per-frame .npy)
+    label .npz with pickled dicts  train_corpus / val_corpus / test_corpus : {utterance: {'emo': ., 'val': .}}
+Utterances are kept as bf16 tensors in pinned host memory; a batch is right-zero-padded per modality to the
+batch maximum exactly like pad_to_maxlen_pre_modality_tensor_4 (read_data.py:223-248) — the model has no
+mask, so padded frames take part in both softmaxes and the padding rule is part of the semantics.
+"""
+from __future__ import annotations
+
+import os
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+STREAMS = ("audio", "text", "video", "feat4")
+
+
+def read_one_feature(feature_root: str, name: str) -> np.ndarray:
+    """[T, D] float array of one utterance (read_data.py:22-49)."""
+    path, dpath = os.path.join(feature_root, name + ".npy"), os.path.join(feature_root, name)
+    if os.path.exists(path):
+        feats = [np.load(path).squeeze()]
+    elif os.path.isdir(dpath):
+        feats = [np.load(os.path.join(dpath, f)) for f in sorted(os.listdir(dpath))]
+    else:
+        raise FileNotFoundError(f"feature path or dir do not exist: {path}")
+    x = np.array(feats).squeeze()
+    if x.ndim == 1:
+        x = x[np.newaxis, :]
+    return x
+
+
+def read_names_labels(label_path: str, split: str, debug: bool = False, exclude: Sequence[str] = ()):
+    """(names, vals) of a split ('train' | 'val' | 'test') of the label .npz (cmumosei.py:133-145)."""
+    corpus = np.load(label_path, allow_pickle=True)[f"{split}_corpus"].tolist()
+    ex = set(exclude)
+    names = [n for n in corpus if n not in ex]
+    if debug:
+        names = names[:100]
+    return names, [float(corpus[n]["val"]) for n in names]
+
+
+class Store4F:
+    """Four per-utterance feature lists resident in pinned host memory (bf16) + labels."""
+
+    def __init__(self, feats: Dict[str, List[torch.Tensor]], vals: Sequence[float], names: Sequence[str]):
+        self.feats, self.vals, self.names = feats, torch.tensor(list(vals), dtype=torch.float32), list(names)
+        n = len(self.names)
+        assert all(len(feats[s]) == n for s in STREAMS) and len(self.vals) == n
+        self.dims = tuple(int(feats[s][0].shape[1]) for s in STREAMS)
+        self.max_frames = tuple(max(int(x.shape[0]) for x in feats[s]) for s in STREAMS)
+
+    def __len__(self):
+        return len(self.names)
+
+    @classmethod
+    def from_disk(cls, feat_root: str, feature_names: Sequence[str], names: Sequence[str], vals: Sequence[float]):
+        feats = {}
+        for s, fname in zip(STREAMS, feature_names):
+            root = os.path.join(feat_root, fname)
+            feats[s] = [torch.from_numpy(np.ascontiguousarray(read_one_feature(root, n), dtype=np.float32)).bfloat16()
+                        for n in names]
+        return cls(feats, vals, names)
+
+    @classmethod
+    def synthetic(cls, n: int, dims=(1024, 4096, 1024, 4096), frames=(384, 64, 256, 64), seed: int = 1234,
+                  ragged: bool = False, chunk: int = 256):
+        """S0-like utterances (sdumc_b200.data.synth_batch); ragged=True draws lengths in [L/4, L]."""
+        from .data import synth_batch
+        dev = "cuda" if torch.cuda.is_available() else "cpu"
+        feats = {s: [] for s in STREAMS}
+        vals: List[float] = []
+        g = torch.Generator().manual_seed(seed)
+        for start in range(0, n, chunk):
+            b = min(chunk, n - start)
+            batch = synth_batch(b, dims, frames, seed=seed + start, device=dev)
+            for s in STREAMS:
+                x = batch[s].cpu()
+                for i in range(b):
+                    L = int(torch.randint(max(1, frames[STREAMS.index(s)] // 4), frames[STREAMS.index(s)] + 1, (1,),
+                                          generator=g)) if ragged else x.shape[1]
+                    feats[s].append(x[i, :L].clone())
+            vals += batch["vals"].cpu().tolist()
+        return cls(feats, vals, [f"synthetic_{i:06d}" for i in range(n)])
+
+    def collate(self, idx: Sequence[int]) -> Tuple[Dict[str, torch.Tensor], torch.Tensor, List[str]]:
+        """Right-zero-pad each modality to the batch maximum and stack (read_data.py:223-248)."""
+        out = {}
+        for s in STREAMS:
+            xs = [self.feats[s][i] for i in idx]
+            L = max(int(x.shape[0]) for x in xs)
+            buf = torch.zeros(len(xs), L, xs[0].shape[1], dtype=torch.bfloat16).pin_memory() \
+                if torch.cuda.is_available() else torch.zeros(len(xs), L, xs[0].shape[1], dtype=torch.bfloat16)
+            for j, x in enumerate(xs):
+                buf[j, : x.shape[0]] = x
+            out[s] = buf
+        return out, self.vals[list(idx)], [self.names[i] for i in idx]
+
+    def batches(self, batch_size: int, rank: int = 0, world: int = 1, lockstep: bool = False) -> Iterator:
+        """Reference batches [i*bs, (i+1)*bs) in order (the reference train loader does not shuffle,
+        cmumosei.py:104-110), dealt round-robin to the ranks at whole-batch granularity (a sample's output
+        depends on its batch's padding), never leaving a trailing batch of size 1."""
+        n = len(self)
+        bounds = list(range(0, n, batch_size))
+        chunks = [list(range(b, min(n, b + batch_size))) for b in bounds]
+        if len(chunks) > 1 and len(chunks[-1]) == 1:        # the reference model crashes on B == 1
+            chunks[-2] += chunks[-1]
+            chunks.pop()
+        if world > 1 and lockstep:
+            chunks = chunks[: len(chunks) // world * world]  # every rank takes the same number of (collective) steps
+        for i, c in enumerate(chunks):
+            if i % world == rank:
+                yield self.collate(c)

@@ -72,9 +72,12 @@ class Trainer:
         self.load_state_dict(state_dict)
         Da, Dt, Dv = self.dims[:3]
         fr = self.frames
-        bf = lambda *s: torch.zeros(*s, dtype=torch.bfloat16, device=dev)  # noqa: E731
-        self.inputs = {"a": bf(B, fr["a"], Da), "t0": bf(B, fr["t0"], Dt), "v": bf(B, fr["v"], Dv),
-                       "t1": bf(B, fr["t1"], Dt)}
+        # static input buffers sized for the largest batch (B utterances x `frames`); a batch padded to fewer
+        # frames (the reference pads to the batch maximum, read_data.py:223-248) uses a prefix of each buffer
+        self.in_dims = {"a": Da, "t0": Dt, "v": Dv, "t1": Dt}
+        self.in_flat = {k: torch.zeros(B * fr[k] * self.in_dims[k], dtype=torch.bfloat16, device=dev) for k in fr}
+        self.cur_frames = dict(fr)
+        self.inputs = {k: self.in_flat[k].view(B, fr[k], self.in_dims[k]) for k in fr}
         self.labels = z(B)
         # device-resident scalars (CUDA-graph replay)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # optimisation step, 1-based after the bump
@@ -88,6 +91,7 @@ class Trainer:
         self.y2 = z(R)
         n_g = 2 * B * self.world
         self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64), dtype=torch.uint8, device=dev)
+        self.cur_B = self.B
         self.train_dropout = True      # tests switch dropout off to compare against a deterministic reference
         self.n_steps = 0
         self._graph = None
@@ -112,36 +116,52 @@ class Trainer:
     def load_batch(self, audio, text, video, feat4, vals):
         """Copies a batch into the static device buffers (H2D when given pinned host tensors).  bf16 tensors
         are copied as they are; fp32 tensors are converted on the device."""
+        b = audio.shape[0]
+        if b > self.B:
+            raise ValueError(f"batch of {b} exceeds the trainer's capacity {self.B}")
+        self.cur_B = b                      # a batch smaller than B (end of an epoch) runs eagerly
         for key, src in (("a", audio), ("t0", text), ("v", video), ("t1", feat4)):
-            dst = self.inputs[key]
+            L, D = int(src.shape[1]), int(src.shape[2])
+            if src.shape[0] != b or D != self.in_dims[key] or L > self.frames[key] or L < 1:
+                raise ValueError(f"stream {key}: got {tuple(src.shape)}, capacity [{self.B},{self.frames[key]},"
+                                 f"{self.in_dims[key]}]")
+            self.cur_frames[key] = L
+            dst = self.in_flat[key][:b * L * D].view(b, L, D)
+            self.inputs[key] = dst
             if src.dtype == torch.bfloat16:
-                dst.copy_(src.view(dst.shape), non_blocking=True)
+                dst.copy_(src, non_blocking=True)
             else:
                 tmp = src.to(self.device, non_blocking=True).float().contiguous()
                 ops.cast_bf16(tmp.view(-1), dst.view(-1))
-        self.labels.copy_(vals.view(-1), non_blocking=True)
+        self.labels[:b].copy_(vals.reshape(-1), non_blocking=True)
 
     # ---- the step --------------------------------------------------------------------------
     def _forward(self, dropout: bool, need_grad: bool):
-        cfg = Cfg(B=self.B, n_pass=2, frames=self.frames, dropout=dropout, need_grad=need_grad, seed=self.seed, step=0,
-                  step_dev=self.step_dev)
+        b = self.cur_B
+        cfg = Cfg(B=b, n_pass=2, frames=dict(self.cur_frames), dropout=dropout, need_grad=need_grad, seed=self.seed,
+                  step=0, step_dev=self.step_dev)
         return self.engine.forward(self.W, self.inputs, cfg)
 
     def _loss_and_seeds(self, st):
         """6-term loss (:134-148) -> self.terms, gradient seeds -> self.d_*."""
-        B, W_, rank = self.B, self.world, self.rank
+        B, W_, rank = self.cur_B, self.world, self.rank
         vals, f, rnc, th, ct = Engine.outputs(st)
         th = th.contiguous()                                      # [2,B,256] out of the strided Q buffer
-        y = self.labels
+        y = self.labels[:B]
+        R = 2 * B
+        d_vals, d_f, d_rnc, d_th, d_ct, y2 = (self.d_vals[:R], self.d_f[:R], self.d_rnc[:R], self.d_th[:R],
+                                              self.d_ct[:R], self.y2[:R])
+        d_th.zero_()
+        d_ct.zero_()
         self.sums.zero_()
         ops.loss_sums(vals[0], vals[1], y, th[0], th[1], ct[0], ct[1], f[0], f[1], B=B, sums=self.sums)
         self.rnc_val.zero_()
-        self.d_rnc.zero_()
+        d_rnc.zero_()
         w6 = self.loss_w[5]
         if W_ == 1:
-            self.y2[:B].copy_(y)
-            self.y2[B:].copy_(y)
-            ops.rnc(st.t["rnc"], self.y2, loss=self.rnc_val, dfeats=self.d_rnc, grad_scale=w6, workspace=self.rnc_ws)
+            y2[:B].copy_(y)
+            y2[B:].copy_(y)
+            ops.rnc(st.t["rnc"], y2, loss=self.rnc_val, dfeats=d_rnc, grad_scale=w6, workspace=self.rnc_ws)
         else:
             from . import dp
             dp.reduce_sums(self.sums, self.pg)
@@ -151,19 +171,18 @@ class Trainer:
                         workspace=self.rnc_ws)
             loss_g, d_local = dp.rnc_global(rnc.contiguous(), y.contiguous(), self.pg, rnc_fn)
             self.rnc_val.copy_(loss_g)
-            self.d_rnc.view(2, B, 64).copy_(d_local)
+            d_rnc.view(2, B, 64).copy_(d_local)
         ops.loss_finish(vals[0], vals[1], y, th[0], th[1], ct[0], ct[1], f[0], f[1], B=B, sums=self.sums,
                         rnc=self.rnc_val, B_global=B * W_, w=self.loss_w, terms=self.terms,
-                        d_v0=self.d_vals[:B], d_v1=self.d_vals[B:], d_th1=self.d_th[B:], d_ct1=self.d_ct[B:],
-                        d_f0=self.d_f[:B], d_f1=self.d_f[B:])
+                        d_v0=d_vals[:B], d_v1=d_vals[B:], d_th1=d_th[B:], d_ct1=d_ct[B:], d_f0=d_f[:B], d_f1=d_f[B:])
+        return d_vals, d_f, d_rnc, d_th, d_ct
 
     def _step_body(self):
         self.step_dev.add_(1)
         st = self._forward(dropout=self.train_dropout, need_grad=True)
-        self._loss_and_seeds(st)
+        d_vals, d_f, d_rnc, d_th, d_ct = self._loss_and_seeds(st)
         self.grads.zero_()
-        self.engine.backward(self.W, st, d_vals=self.d_vals, d_fused=self.d_f, d_rnc=self.d_rnc, d_th=self.d_th,
-                             d_ct=self.d_ct)
+        self.engine.backward(self.W, st, d_vals=d_vals, d_fused=d_f, d_rnc=d_rnc, d_th=d_th, d_ct=d_ct)
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.grads[:self.layout.n_live], group=self.pg)
@@ -175,8 +194,9 @@ class Trainer:
     def train_step(self):
         """One optimisation step on the batch currently in the static buffers.  Returns nothing; read
         `terms` (device tensor: 6 loss terms + total) and `predictions()` when needed."""
-        if not self.use_graph or self.n_steps == 0:
-            self._step_body()          # first step eager: one-time kernel attribute setup, allocator warm-up
+        full = self.cur_B == self.B and self.cur_frames == self.frames
+        if not self.use_graph or self.n_steps == 0 or not full:
+            self._step_body()          # first step (one-time kernel attribute setup) and smaller batches run eagerly
         elif self._graph is None:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()

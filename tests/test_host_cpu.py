@@ -1,0 +1,85 @@
+"""CPU tests of the host-side layers around the hot path: CLI surface, metric, dataset reader + the
+reference's padding / batching rules."""
+import numpy as np
+import torch
+
+REFERENCE_FLAGS = [  # add_argument flags of the reference parsers (main_frame_val_text_missing.py:213-252)
+    '--dataset', '--train_dataset', '--valid_dataset', '--test_dataset', '--audio_feature', '--text_feature',
+    '--video_feature', '--feat4_feature', '--debug', '--test_sets', '--save_root', '--savewhole', '--feat_type',
+    '--feat_scale', '--model', '--layers', '--n_classes', '--num_folder', '--model_type', '--full_mse_loss_w',
+    '--missing_mse_loss_w', '--text_feat_loss_w', '--text_query_feat_loss_w', '--features_loss_w', '--rnc_loss_w',
+    '--lr', '--l2', '--dropout', '--batch_size', '--num_workers', '--epochs', '--seed', '--gpu', '--local_rank']
+
+
+def test_cli_keeps_every_reference_flag_and_default():
+    from sdumc_b200.cli import build_parser
+    for inference in (False, True):
+        p = build_parser(inference)
+        ours = {a.option_strings[0]: a for a in p._actions if a.option_strings}
+        assert set(REFERENCE_FLAGS) <= set(ours)
+        a = p.parse_args([])
+        assert (a.full_mse_loss_w, a.missing_mse_loss_w, a.text_feat_loss_w, a.text_query_feat_loss_w,
+                a.features_loss_w, a.rnc_loss_w) == (0.5, 0.5, 0.1, 0.7, 0.1, 0.8)
+        assert (a.lr, a.l2, a.batch_size, a.epochs, a.seed, a.layers) == (1e-4, 1e-5, 32, 100, 100, '256,128')
+    # the canonical invocation of shell/main_text_missing_icassp.sh parses
+    build_parser(False).parse_args(
+        "--dataset=CMU-MOSEI --valid_dataset=CMU-MOSEI_valid --test_dataset=CMU-MOSEI_test "
+        "--model=wengnet_mosei_mult_views_text_missing --test_sets=test3 --num_workers=4 --audio_feature=a "
+        "--text_feature=t --video_feature=v --feat4_feature=f --batch_size=96 --lr=1e-4 --epochs=25 --gpu=0 "
+        "--full_mse_loss_w=0.5 --missing_mse_loss_w=0.5 --text_feat_loss_w=0 --text_query_feat_loss_w=0 "
+        "--features_loss_w=0.13 --rnc_loss_w=0.5".split())
+
+
+def test_lr_schedule_matches_reference_lambda():
+    from sdumc_b200.trainer import lr_lambda
+    ref = lambda epoch: (epoch + 1) / 5 if epoch < 5 else 0.9 ** ((epoch + 1 - 5) // 10)  # noqa: E731  (main…:319-320)
+    assert all(abs(lr_lambda(e) - ref(e)) < 1e-15 for e in range(60))
+
+
+def test_metric_keys_and_values():
+    from metric import eval_mosei_metric
+    r = eval_mosei_metric([0.5, -1.0, 2.0, 0.1], [1.0, -2.0, 1.5, 0.0])
+    assert set(r) >= {"mae", "f1"} and abs(r["mae"] - 0.525) < 1e-12 and r["acc2"] == 1.0
+
+
+def test_reader_and_collate_follow_reference_padding(tmp_path):
+    from sdumc_b200.dataset import Store4F, read_names_labels, read_one_feature
+    rng = np.random.default_rng(0)
+    names = [f"utt{i}" for i in range(7)]
+    feats = ("wav", "txt", "vis", "f4")
+    dims = (16, 24, 8, 24)
+    lens = {}
+    for f, d in zip(feats, dims):
+        (tmp_path / f).mkdir()
+        for n in names:
+            L = int(rng.integers(1, 9))
+            lens[(f, n)] = L
+            np.save(tmp_path / f / f"{n}.npy", rng.standard_normal((L, d)).astype(np.float32))
+    # a visual feature stored as a directory of per-frame vectors (read_data.py:33-37)
+    (tmp_path / "vis" / "dirutt").mkdir()
+    for k in range(3):
+        np.save(tmp_path / "vis" / "dirutt" / f"{k:03d}.npy", np.full((8,), float(k), dtype=np.float32))
+    assert read_one_feature(str(tmp_path / "vis"), "dirutt").shape == (3, 8)
+    corpus = {n: {"emo": 0, "val": float(i) / 3 - 1} for i, n in enumerate(names)}
+    np.savez(tmp_path / "label.npz", train_corpus=corpus, val_corpus=corpus, test_corpus=corpus)
+    nm, vals = read_names_labels(str(tmp_path / "label.npz"), "train", exclude=["utt3"])
+    assert nm == [n for n in names if n != "utt3"] and len(vals) == 6
+    st = Store4F.from_disk(str(tmp_path), feats, nm, vals)
+    assert st.dims == dims
+    batches = list(st.batches(4))
+    assert [len(b[2]) for b in batches] == [4, 2]
+    b0, v0, n0 = batches[0]
+    for key, f in zip(("audio", "text", "video", "feat4"), feats):
+        Lmax = max(lens[(f, n)] for n in n0)
+        assert b0[key].shape[1] == Lmax                                   # padded to the BATCH maximum
+        for j, n in enumerate(n0):
+            L = lens[(f, n)]
+            ref = torch.from_numpy(np.load(tmp_path / f / f"{n}.npy")).bfloat16()
+            assert torch.equal(b0[key][j, :L], ref) and float(b0[key][j, L:].abs().sum()) == 0.0   # right zero-pad
+    # a trailing batch of one sample is merged (the reference model crashes on B == 1)
+    st5 = Store4F.from_disk(str(tmp_path), feats, nm[:5], vals[:5])
+    assert [len(b[2]) for b in st5.batches(4)] == [5]
+    # whole batches are dealt to ranks; lock-step training drops the remainder
+    st6 = Store4F.from_disk(str(tmp_path), feats, nm, vals)
+    assert [len(b[2]) for b in st6.batches(2, rank=1, world=2)] == [2]
+    assert [len(b[2]) for b in st6.batches(2, rank=0, world=2, lockstep=True)] == [2]
