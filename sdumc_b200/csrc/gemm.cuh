@@ -80,21 +80,24 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
 }
 
 // Coalesced store of a 32-row x 32-column bf16 block owned row-per-lane (w = this lane's 32 values,
-// packed) through the warp's padded staging buffer: 4 conflict-free 128-bit smem writes per lane,
+// packed) through the warp's swizzled staging buffer: 4 conflict-free 128-bit smem writes per lane,
 // then each instruction stores eight full 64-byte row segments.  `dst` points at (row0, n0).
 template <int kRowWords>
 __device__ __forceinline__ void store_block_bf16(uint32_t* stg, const uint32_t (&w)[16], __nv_bfloat16* dst, long ld,
                                                  int rows_valid, int lane, bool accumulate) {
+  // chunk c of row r lives at 16-byte slot c ^ ((r >> 1) & 3): a quarter-warp (8 rows writing the same chunk,
+  // or 2 rows x 4 chunks when reading) always touches 8 distinct 4-bank groups
   uint4* mine = reinterpret_cast<uint4*>(stg + lane * kRowWords);
-  mine[0] = make_uint4(w[0], w[1], w[2], w[3]);
-  mine[1] = make_uint4(w[4], w[5], w[6], w[7]);
-  mine[2] = make_uint4(w[8], w[9], w[10], w[11]);
-  mine[3] = make_uint4(w[12], w[13], w[14], w[15]);
+  const int sw = (lane >> 1) & 3;
+  mine[0 ^ sw] = make_uint4(w[0], w[1], w[2], w[3]);
+  mine[1 ^ sw] = make_uint4(w[4], w[5], w[6], w[7]);
+  mine[2 ^ sw] = make_uint4(w[8], w[9], w[10], w[11]);
+  mine[3 ^ sw] = make_uint4(w[12], w[13], w[14], w[15]);
   __syncwarp();
 #pragma unroll
   for (int it = 0; it < 4; ++it) {
     const int rr = it * 8 + (lane >> 2), q = lane & 3;
-    uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kRowWords + q * 4);
+    uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kRowWords + ((q ^ ((rr >> 1) & 3)) * 4));
     if (rr < rows_valid) {
       uint4* g = reinterpret_cast<uint4*>(dst + (long)rr * ld + q * 8);
       if (accumulate) {
@@ -120,7 +123,7 @@ struct GemmCfg {
   static constexpr int kStages = (kBlockN == 256) ? 4 : (kBlockN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * kBlockN < 32) ? 32 : 2 * kBlockN;
   static constexpr int kEpiWarps = 8;                        // two groups of 4, alternating tiles
-  static constexpr int kStageRowWords = 20;                  // 16 payload words + pad: conflict-free 128-bit access
+  static constexpr int kStageRowWords = 16;                  // 64-byte rows, 16-byte chunks XOR-swizzled by (row >> 1) & 3
   static constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowWords * 4;
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kThreads = 384;

@@ -162,7 +162,18 @@ def run_case(name: str) -> dict:
     elif kind == "timeepi":
         # timeepi:inproj:<ntgt>:<K>  |  timeepi:keyproj:<nq>:<store_k>
         sub = rest[0]
-        if sub == "inproj":
+        if sub == "rmw":
+            # dH += (dZ W_in) * mask : M=196608, N=K=256, B MN-major, bf16 read-modify-write epilogue
+            masked = int(rest[1])
+            M, N, K = 196608, 256, 256
+            A, B = mk((M, K), torch.bfloat16), mk((K, N), torch.bfloat16)
+            H = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+
+            def go():
+                ops.gemm(A, B, M=M, N=N, K=K, b_mn=True, fmask_site=7 if masked else 0, out_bf16=H,
+                         bf16_mode=ops.OUT_ADD, seed=5, step=1)
+            nbytes = A.numel() * 2 + 2 * M * N * 2
+        elif sub == "inproj":
             ntgt, K = int(rest[1]), int(rest[2])
             M, N = 196608, 256
             A, B = mk((M, K), torch.bfloat16), mk((N, K), torch.bfloat16)
@@ -236,6 +247,8 @@ CASES = [
     "time:32768:256:4096:00:1",
     "time:256:1024:196608:11:37",
     "time:196608:256:256:00:1",
+    "timeepi:rmw:1",
+    "timeepi:rmw:0",
     "timeepi:inproj:0:1024",
     "timeepi:inproj:4:1024",
     "timeepi:inproj:0:4096",
