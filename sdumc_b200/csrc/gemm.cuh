@@ -84,7 +84,7 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
 // then each instruction stores eight full 64-byte row segments.  `dst` points at (row0, n0).
 template <int kRowWords>
 __device__ __forceinline__ void store_block_bf16(uint32_t* stg, const uint32_t (&w)[16], __nv_bfloat16* dst, long ld,
-                                                 int rows_valid, int lane, bool accumulate) {
+                                                 int rows_valid, int lane, const uint4* oldv /*prefetched or null*/) {
   // chunk c of row r lives at 16-byte slot c ^ ((r >> 1) & 3): a quarter-warp (8 rows writing the same chunk,
   // or 2 rows x 4 chunks when reading) always touches 8 distinct 4-bank groups
   uint4* mine = reinterpret_cast<uint4*>(stg + lane * kRowWords);
@@ -100,8 +100,8 @@ __device__ __forceinline__ void store_block_bf16(uint32_t* stg, const uint32_t (
     uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kRowWords + ((q ^ ((rr >> 1) & 3)) * 4));
     if (rr < rows_valid) {
       uint4* g = reinterpret_cast<uint4*>(dst + (long)rr * ld + q * 8);
-      if (accumulate) {
-        const uint4 old = *g;
+      if (oldv) {
+        const uint4 old = oldv[it];
         val.x = add_bf16x2(val.x, old.x);
         val.y = add_bf16x2(val.y, old.y);
         val.z = add_bf16x2(val.z, old.z);
@@ -111,6 +111,15 @@ __device__ __forceinline__ void store_block_bf16(uint32_t* stg, const uint32_t (
     }
   }
   __syncwarp();
+}
+
+template <int kRegs>
+__device__ __forceinline__ void reg_alloc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kRegs));
+}
+template <int kRegs>
+__device__ __forceinline__ void reg_dealloc() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kRegs));
 }
 
 template <int kBlockN>
@@ -125,7 +134,8 @@ struct GemmCfg {
   static constexpr int kEpiWarps = 8;                        // two groups of 4, alternating tiles
   static constexpr int kStageRowWords = 16;                  // 64-byte rows, 16-byte chunks XOR-swizzled by (row >> 1) & 3
   static constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowWords * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kVecBytes = 2 /*groups*/ * 2 /*bias, ctx*/ * kBlockN * 4;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kThreads = 384;
 };
 
@@ -145,7 +155,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
   uint32_t* staging = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  float* vec_s = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + Cfg::kVecBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
@@ -181,6 +192,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) reg_dealloc<40>();   // warpgroup 0 (producer, MMA issuer, TMEM allocator, spare) keeps 40 registers
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -261,19 +273,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
   } else if (warp >= 4) {
     // ===================== epilogue: two groups of 4 warps, alternating tiles =====================
+    reg_alloc<224>();                 // registers released by the producer / MMA warpgroup
     const int ew = warp & 3;          // TMEM lane quarter this warp may touch
     const int grp = (warp - 4) >> 2;  // group g drains accumulator stage g (tiles with local index % 2 == g)
+    const int gtid = threadIdx.x - 128 - grp * 128;
     uint32_t* stg = staging + (warp - 4) * 32 * Cfg::kStageRowWords;
+    float* bias_s = vec_s + grp * 2 * kBlockN;       // this tile's bias slice
+    float* ctx_s = bias_s + kBlockN;                 // shared query vector (key-projection, nq == 1)
     uint32_t acc_phase = 0;
     const uint32_t drop_thr = drop_threshold(ep.drop_p);
     const float drop_scale = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
     const DropKey key = resolve_key(ep.key);
+    const bool rmw = ep.kind == EPI_GENERIC && ep.out_bf16 && ep.bf16_mode == OUT_ADD;
+    const bool ctx_shared = ep.kind == EPI_KEYPROJ && ep.q_stride == 0 && ep.nq == 1;
+    constexpr int NC = kBlockN / 32;
     int li = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++li) {
       if ((li & 1) != grp) continue;
       const int acc = grp;
       const int mn = t % (m_tiles * n_tiles);
       const int m_blk = mn / n_tiles, n_blk = mn - m_blk * n_tiles;
+      // stage the per-column vectors of this tile (group-local named barrier: 128 threads)
+      for (int j = gtid; j < kBlockN; j += 128) {
+        const int n = n_blk * kBlockN + j;
+        bias_s[j] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.f;
+        if (ctx_shared) ctx_s[j] = n < sh.N ? __ldg(ep.qv + n) : 0.f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int r0 = m_blk * 128 + ew * 32;  // first row of this warp's slab
@@ -287,34 +313,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       if (ep.kind == EPI_KEYPROJ && row_ok) qrow = ep.qv + (long)(r / ep.L) * ep.q_stride;
       U4 tw[4];
 
-#pragma unroll 1
-      for (int c = 0; c < kBlockN / 32; ++c) {
-        uint32_t acc_r[32];
-        tmem_ld32(taddr + (uint32_t)(c * 32), acc_r);
-        const int n0 = n_blk * kBlockN + c * 32;
-        const bool full = (n0 + 32 <= sh.N);
-        // the bias chunk is fetched while the TMEM load is in flight
-        float4 bia[8];
-        if (ep.bias && full) {
+      // issue the TMEM load of chunk c (and, for read-modify-write outputs, the loads of the old values)
+      auto issue = [&](int c, uint32_t (&buf)[32], uint4 (&oldv)[4]) {
+        tmem_ld32(taddr + (uint32_t)(c * 32), buf);
+        if (rmw) {
+          const int n0 = n_blk * kBlockN + c * 32;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) bia[j] = __ldg(reinterpret_cast<const float4*>(ep.bias + n0) + j);
+          for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), q = lane & 3;
+            oldv[it] = (rr < rows_valid && n0 < sh.N)
+                           ? *reinterpret_cast<const uint4*>(ep.out_bf16 + (long)(r0 + rr) * ep.ld_bf16 + n0 + q * 8)
+                           : make_uint4(0, 0, 0, 0);
+          }
         }
-        tmem_ld_wait();
-        if (n0 >= sh.N) continue;  // warp-uniform
+      };
+
+      auto process = [&](int c, const uint32_t (&acc_r)[32], const uint4 (&oldv)[4]) {
+        const int n0 = n_blk * kBlockN + c * 32;
+        if (n0 >= sh.N) return;  // warp-uniform
+        const bool full = (n0 + 32 <= sh.N);
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(acc_r[j]);
-        if (ep.bias) {
-          if (full) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              v[4 * j] += bia[j].x; v[4 * j + 1] += bia[j].y; v[4 * j + 2] += bia[j].z; v[4 * j + 3] += bia[j].w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + j < sh.N) v[j] += __ldg(ep.bias + n0 + j);
-          }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c * 32 + j);
+          v[j] = __uint_as_float(acc_r[j]) + b4.x;
+          v[j + 1] = __uint_as_float(acc_r[j + 1]) + b4.y;
+          v[j + 2] = __uint_as_float(acc_r[j + 2]) + b4.z;
+          v[j + 3] = __uint_as_float(acc_r[j + 3]) + b4.w;
         }
         if (ep.act == ACT_RELU) {
 #pragma unroll
@@ -330,7 +355,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
-                                                  rows_valid, lane, false);
+                                                  rows_valid, lane, nullptr);
           }
           // dropped copies: word (n0 >> 5) & 3 of Philox(row, n0 >> 7, site, step)
           if ((c & 3) == 0) {
@@ -348,9 +373,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               w[j] = pack_bf16x2(((bits >> (2 * j)) & 1u) ? 2.f * v[2 * j] : 0.f,
                                  ((bits >> (2 * j + 1)) & 1u) ? 2.f * v[2 * j + 1] : 0.f);
             store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.tgt[i] + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
-                                                  rows_valid, lane, false);
+                                                  rows_valid, lane, nullptr);
           }
-          continue;
+          return;
         }
 
         if (ep.kind == EPI_KEYPROJ) {
@@ -359,7 +384,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
             store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
-                                                  rows_valid, lane, false);
+                                                  rows_valid, lane, nullptr);
             // the backward pass reads the bf16 K; score with the same rounded values
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -367,8 +392,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               v[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
             }
           }
-          // column groups outer, queries inner: 7 independent accumulators, no serial FMA chain per query
-          if (ep.nq == 7) {
+          if (ctx_shared) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(ctx_s + c * 32 + j);
+              s0 = fmaf(v[j], w4.x, s0);
+              s1 = fmaf(v[j + 1], w4.y, s1);
+              s2 = fmaf(v[j + 2], w4.z, s2);
+              s3 = fmaf(v[j + 3], w4.w, s3);
+            }
+            sc[0] += (s0 + s1) + (s2 + s3);
+          } else if (ep.nq == 7) {
+            // column groups outer, queries inner: 7 independent accumulators, no serial FMA chain per query
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               float4 w4[7];
@@ -400,7 +436,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               sc[q] += (s0 + s1) + (s2 + s3);
             }
           }
-          continue;
+          return;
         }
 
         // ---- generic ----
@@ -467,8 +503,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
-                                                rows_valid, lane, ep.bf16_mode == OUT_ADD);
+                                                rows_valid, lane, rmw ? oldv : nullptr);
         }
+      };
+
+      // software pipeline over the 32-column chunks: the TMEM load (and RMW prefetch) of chunk c+1 is in
+      // flight while chunk c is processed
+      uint32_t bufA[32], bufB[32];
+      uint4 oldA[4], oldB[4];
+      issue(0, bufA, oldA);
+#pragma unroll 1
+      for (int c = 0; c < NC; c += 2) {
+        tmem_ld_wait();
+        issue(c + 1, bufB, oldB);
+        process(c, bufA, oldA);
+        tmem_ld_wait();
+        if (c + 2 < NC) issue(c + 2, bufA, oldA);
+        process(c + 1, bufB, oldB);
       }
       if (ep.kind == EPI_KEYPROJ && row_ok) {
         float* srow = ep.scores + (long)r * ep.nq;
