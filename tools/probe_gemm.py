@@ -133,6 +133,8 @@ def run_case(name: str) -> dict:
         M, N, K = map(int, rest[0:3])
         a_mn, b_mn = int(rest[3][0]), int(rest[3][1])
         ks = int(rest[4])
+        noout = len(rest) > 5 and rest[5] == "noout"
+        bn = int(rest[6]) if len(rest) > 6 else 0
         A = mk((K, M) if a_mn else (M, K), torch.bfloat16)
         B = mk((K, N) if b_mn else (N, K), torch.bfloat16)
         outb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16) if ks == 1 else None
@@ -140,7 +142,8 @@ def run_case(name: str) -> dict:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
         def go():
-            ops.gemm(A, B, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, k_splits=ks, out_bf16=outb, out_f32=outf,
+            ops.gemm(A, B, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, k_splits=ks, out_bf16=None if noout else outb,
+                     out_f32=None if noout else outf, block_n=bn,
                      f32_mode=ops.OUT_ATOMIC if ks > 1 else ops.OUT_STORE)
         for _ in range(3):
             go()
