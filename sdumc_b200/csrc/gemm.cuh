@@ -233,7 +233,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     // ===================== MMA issuer (one thread) =====================
     const uint32_t idesc = make_idesc(kFmt, (uint32_t)sh.a_mn, (uint32_t)sh.b_mn, (uint32_t)kBlockN);
     const uint32_t mn_lbo = sh.dbg_lbo ? sh.dbg_lbo : (uint32_t)(kBlockK * 128);
-    const uint32_t mn_sbo = sh.dbg_sbo ? sh.dbg_sbo : 1024u;
+    const uint32_t mn_sbo = (sh.dbg_sbo & 0xffffu) ? (sh.dbg_sbo & 0xffffu) : 1024u;
     const uint32_t a_lbo = sh.a_mn ? mn_lbo : 16u, a_sbo = sh.a_mn ? mn_sbo : 1024u;
     const uint32_t b_lbo = sh.b_mn ? mn_lbo : 16u, b_sbo = sh.b_mn ? mn_sbo : 1024u;
     // descriptor start-address advance per UMMA_K step, in 16-byte units
@@ -511,15 +511,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // flight while chunk c is processed
       uint32_t bufA[32], bufB[32];
       uint4 oldA[4], oldB[4];
-      issue(0, bufA, oldA);
+      const uint32_t dbg = sh.dbg_sbo >> 16;   // bring-up switches (tools/probe_gemm.py), 0 in production
+      if (dbg != 1) {
+        issue(0, bufA, oldA);
 #pragma unroll 1
-      for (int c = 0; c < NC; c += 2) {
-        tmem_ld_wait();
-        issue(c + 1, bufB, oldB);
-        process(c, bufA, oldA);
-        tmem_ld_wait();
-        if (c + 2 < NC) issue(c + 2, bufA, oldA);
-        process(c + 1, bufB, oldB);
+        for (int c = 0; c < NC; c += 2) {
+          tmem_ld_wait();
+          issue(c + 1, bufB, oldB);
+          if (dbg != 2) process(c, bufA, oldA);
+          tmem_ld_wait();
+          if (c + 2 < NC) issue(c + 2, bufA, oldA);
+          if (dbg != 2) process(c + 1, bufB, oldB);
+        }
       }
       if (ep.kind == EPI_KEYPROJ && row_ok) {
         float* srow = ep.scores + (long)r * ep.nq;

@@ -135,6 +135,7 @@ def run_case(name: str) -> dict:
         ks = int(rest[4])
         noout = len(rest) > 5 and rest[5] == "noout"
         bn = int(rest[6]) if len(rest) > 6 else 0
+        dbg = int(rest[7]) if len(rest) > 7 else 0
         A = mk((K, M) if a_mn else (M, K), torch.bfloat16)
         B = mk((K, N) if b_mn else (N, K), torch.bfloat16)
         outb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16) if ks == 1 else None
@@ -143,7 +144,7 @@ def run_case(name: str) -> dict:
 
         def go():
             ops.gemm(A, B, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, k_splits=ks, out_bf16=None if noout else outb,
-                     out_f32=None if noout else outf, block_n=bn,
+                     out_f32=None if noout else outf, block_n=bn, dbg_sbo=dbg << 16,
                      f32_mode=ops.OUT_ATOMIC if ks > 1 else ops.OUT_STORE)
         for _ in range(3):
             go()
