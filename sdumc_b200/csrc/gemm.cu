@@ -168,7 +168,9 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
   }
   if (epi.kind == EPI_INPROJ) {
     SDUMC_CHECK_ARG(sh.N % 32 == 0 && epi.n_tgt >= 0 && epi.n_tgt <= 4, "gemm: bad in-proj epilogue");
-    SDUMC_CHECK_ARG(epi.ld_bf16 % 8 == 0, "gemm: in-proj epilogue needs ld %% 8 == 0");
+    SDUMC_CHECK_ARG(epi.ld_bf16 % 16 == 0, "gemm: in-proj epilogue needs ld %% 16 == 0");
+    for (int i = 0; i < epi.n_tgt; ++i)
+      SDUMC_CHECK_ARG(epi.tgt[i] && (reinterpret_cast<uintptr_t>(epi.tgt[i]) & 31u) == 0, "gemm: in-proj target %d misaligned", i);
   }
   if (epi.kind == EPI_KEYPROJ && epi.out_bf16) SDUMC_CHECK_ARG(epi.ld_bf16 % 8 == 0, "gemm: key-proj K ld %% 8");
   if (epi.out_f32 && epi.f32_mode != OUT_ATOMIC)
@@ -176,8 +178,8 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
                     "gemm: fp32 output must be 16-byte aligned with ld %% 4 == 0");
   if (epi.drop_p > 0.f) SDUMC_CHECK_ARG(sh.N % 4 == 0, "gemm: element dropout needs N %% 4 == 0");
   if (epi.out_bf16)
-    SDUMC_CHECK_ARG(sh.N % 32 == 0 && epi.ld_bf16 % 8 == 0 && (reinterpret_cast<uintptr_t>(epi.out_bf16) & 15u) == 0,
-                    "gemm: bf16 output needs N %% 32 == 0, ld %% 8 == 0 and a 16-byte aligned base");
+    SDUMC_CHECK_ARG(sh.N % 32 == 0 && epi.ld_bf16 % 16 == 0 && (reinterpret_cast<uintptr_t>(epi.out_bf16) & 31u) == 0,
+                    "gemm: bf16 output needs N %% 32 == 0, ld %% 16 == 0 and a 32-byte aligned base");
   if (epi.bias) SDUMC_CHECK_ARG((reinterpret_cast<uintptr_t>(epi.bias) & 15u) == 0, "gemm: bias must be 16-byte aligned");
   if (epi.gate) SDUMC_CHECK_ARG(epi.ld_gate % 4 == 0 && (reinterpret_cast<uintptr_t>(epi.gate) & 15u) == 0,
                                 "gemm: gate must be 16-byte aligned with ld %% 4 == 0");

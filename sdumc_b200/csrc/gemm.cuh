@@ -8,14 +8,14 @@
 //   MN-major (reduction index strided: the dX = dY*W and dW = dY^T*X cases) — only the TMA box
 //   and the UMMA descriptor differ;
 // * persistent CTAs, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (one thread),
-//   warp 2 = TMEM allocator, warps 4..7 / 8..11 = two epilogue groups (TMEM -> registers -> smem
-//   staging -> coalesced 16-byte stores) that alternate tiles; accumulators double-buffered in
+//   warp 2 = TMEM allocator, warps 4..7 / 8..11 = two epilogue groups (TMEM -> registers -> 256-bit
+//   row stores, software-pipelined over 32-column chunks) that alternate tiles; accumulators double-buffered in
 //   TMEM (2 x kBlockN columns) so the epilogue of tile i overlaps the MMAs of tiles i+1, i+2;
 // * split-K over the reduction for the weight-gradient shapes (fp32 atomics into the grad buffer).
 //
 // Epilogues (fused, selected at run time):
 //   generic : bias, ReLU/tanh, ReLU+dropout backward gate, element dropout, frame-mask multiply,
-//             fp32 store / += / atomicAdd, bf16 store / +=
+//             fp32 store / += / atomicAdd, bf16 store / += (old values prefetched one chunk ahead)
 //   in-proj : bias, plain bf16 H plus up to 4 independently dropped copies (the X' of
 //             FRA2UTT_new / Cross_Attention of both passes; reference
 //             toolkit/models/wengnet_mosei_mult_views_text_missing.py:57,81)
@@ -79,38 +79,26 @@ __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
   return pack_bf16x2(lo, hi);
 }
 
-// Coalesced store of a 32-row x 32-column bf16 block owned row-per-lane (w = this lane's 32 values,
-// packed) through the warp's swizzled staging buffer: 4 conflict-free 128-bit smem writes per lane,
-// then each instruction stores eight full 64-byte row segments.  `dst` points at (row0, n0).
-template <int kRowWords>
-__device__ __forceinline__ void store_block_bf16(uint32_t* stg, const uint32_t (&w)[16], __nv_bfloat16* dst, long ld,
-                                                 int rows_valid, int lane, const uint4* oldv /*prefetched or null*/) {
-  // chunk c of row r lives at 16-byte slot c ^ ((r >> 1) & 3): a quarter-warp (8 rows writing the same chunk,
-  // or 2 rows x 4 chunks when reading) always touches 8 distinct 4-bank groups
-  uint4* mine = reinterpret_cast<uint4*>(stg + lane * kRowWords);
-  const int sw = (lane >> 1) & 3;
-  mine[0 ^ sw] = make_uint4(w[0], w[1], w[2], w[3]);
-  mine[1 ^ sw] = make_uint4(w[4], w[5], w[6], w[7]);
-  mine[2 ^ sw] = make_uint4(w[8], w[9], w[10], w[11]);
-  mine[3 ^ sw] = make_uint4(w[12], w[13], w[14], w[15]);
-  __syncwarp();
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a lane's 32 bf16 of one row chunk = two full 32-byte sectors
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* w) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+               "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+               : "memory");
+}
+__device__ __forceinline__ void ld_global_256(const void* p, uint32_t* w) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+               : "l"(p)
+               : "memory");
+}
+// store (or accumulate onto prefetched old values) this lane's 32 consecutive bf16 of its own row
+__device__ __forceinline__ void store_row_bf16(__nv_bfloat16* dst, uint32_t (&w)[16], const uint32_t* oldv) {
+  if (oldv) {
 #pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int rr = it * 8 + (lane >> 2), q = lane & 3;
-    uint4 val = *reinterpret_cast<const uint4*>(stg + rr * kRowWords + ((q ^ ((rr >> 1) & 3)) * 4));
-    if (rr < rows_valid) {
-      uint4* g = reinterpret_cast<uint4*>(dst + (long)rr * ld + q * 8);
-      if (oldv) {
-        const uint4 old = oldv[it];
-        val.x = add_bf16x2(val.x, old.x);
-        val.y = add_bf16x2(val.y, old.y);
-        val.z = add_bf16x2(val.z, old.z);
-        val.w = add_bf16x2(val.w, old.w);
-      }
-      *g = val;
-    }
+    for (int j = 0; j < 16; ++j) w[j] = add_bf16x2(w[j], oldv[j]);
   }
-  __syncwarp();
+  st_global_256(dst, &w[0]);
+  st_global_256(dst + 16, &w[8]);
 }
 
 template <int kRegs>
@@ -132,10 +120,8 @@ struct GemmCfg {
   static constexpr int kStages = (kBlockN == 256) ? 4 : (kBlockN == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * kBlockN < 32) ? 32 : 2 * kBlockN;
   static constexpr int kEpiWarps = 8;                        // two groups of 4, alternating tiles
-  static constexpr int kStageRowWords = 16;                  // 64-byte rows, 16-byte chunks XOR-swizzled by (row >> 1) & 3
-  static constexpr int kStagingBytes = kEpiWarps * 32 * kStageRowWords * 4;
   static constexpr int kVecBytes = 2 /*groups*/ * 2 /*bias, ctx*/ * kBlockN * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kThreads = 384;
 };
 
@@ -154,9 +140,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
-  uint32_t* staging = reinterpret_cast<uint32_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  float* vec_s = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kStagingBytes + Cfg::kVecBytes);
+  float* vec_s = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kVecBytes);
   uint64_t* full_bar = bars;                       // [kStages]
   uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
@@ -277,7 +262,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int ew = warp & 3;          // TMEM lane quarter this warp may touch
     const int grp = (warp - 4) >> 2;  // group g drains accumulator stage g (tiles with local index % 2 == g)
     const int gtid = threadIdx.x - 128 - grp * 128;
-    uint32_t* stg = staging + (warp - 4) * 32 * Cfg::kStageRowWords;
     float* bias_s = vec_s + grp * 2 * kBlockN;       // this tile's bias slice
     float* ctx_s = bias_s + kBlockN;                 // shared query vector (key-projection, nq == 1)
     uint32_t acc_phase = 0;
@@ -305,7 +289,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int r0 = m_blk * 128 + ew * 32;  // first row of this warp's slab
       const int r = r0 + lane;
       const bool row_ok = r < sh.M;
-      const int rows_valid = sh.M - r0;      // may be <= 0 or > 32
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN);
 
       float sc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -314,21 +297,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       U4 tw[4];
 
       // issue the TMEM load of chunk c (and, for read-modify-write outputs, the loads of the old values)
-      auto issue = [&](int c, uint32_t (&buf)[32], uint4 (&oldv)[4]) {
+      auto issue = [&](int c, uint32_t (&buf)[32], uint32_t (&oldv)[16]) {
         tmem_ld32(taddr + (uint32_t)(c * 32), buf);
         if (rmw) {
           const int n0 = n_blk * kBlockN + c * 32;
-#pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int rr = it * 8 + (lane >> 2), q = lane & 3;
-            oldv[it] = (rr < rows_valid && n0 < sh.N)
-                           ? *reinterpret_cast<const uint4*>(ep.out_bf16 + (long)(r0 + rr) * ep.ld_bf16 + n0 + q * 8)
-                           : make_uint4(0, 0, 0, 0);
+          if (row_ok && n0 < sh.N) {
+            const __nv_bfloat16* src = ep.out_bf16 + (long)r * ep.ld_bf16 + n0;
+            ld_global_256(src, &oldv[0]);
+            ld_global_256(src + 16, &oldv[8]);
           }
         }
       };
 
-      auto process = [&](int c, const uint32_t (&acc_r)[32], const uint4 (&oldv)[4]) {
+      auto process = [&](int c, const uint32_t (&acc_r)[32], const uint32_t (&oldv)[16]) {
         const int n0 = n_blk * kBlockN + c * 32;
         if (n0 >= sh.N) return;  // warp-uniform
         const bool full = (n0 + 32 <= sh.N);
@@ -354,8 +335,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (ep.out_bf16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
-                                                  rows_valid, lane, nullptr);
+            if (row_ok) store_row_bf16(ep.out_bf16 + (long)r * ep.ld_bf16 + n0, w, nullptr);
           }
           // dropped copies: word (n0 >> 5) & 3 of Philox(row, n0 >> 7, site, step)
           if ((c & 3) == 0) {
@@ -372,8 +352,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int j = 0; j < 16; ++j)
               w[j] = pack_bf16x2(((bits >> (2 * j)) & 1u) ? 2.f * v[2 * j] : 0.f,
                                  ((bits >> (2 * j + 1)) & 1u) ? 2.f * v[2 * j + 1] : 0.f);
-            store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.tgt[i] + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
-                                                  rows_valid, lane, nullptr);
+            if (row_ok) store_row_bf16(ep.tgt[i] + (long)r * ep.ld_bf16 + n0, w, nullptr);
           }
           return;
         }
@@ -383,8 +362,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             uint32_t w[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
-                                                  rows_valid, lane, nullptr);
+            if (row_ok) store_row_bf16(ep.out_bf16 + (long)r * ep.ld_bf16 + n0, w, nullptr);
             // the backward pass reads the bf16 K; score with the same rounded values
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -502,15 +480,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           uint32_t w[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          store_block_bf16<Cfg::kStageRowWords>(stg, w, ep.out_bf16 + (long)r0 * ep.ld_bf16 + n0, ep.ld_bf16,
-                                                rows_valid, lane, rmw ? oldv : nullptr);
+          if (row_ok) store_row_bf16(ep.out_bf16 + (long)r * ep.ld_bf16 + n0, w, rmw ? oldv : nullptr);
         }
       };
 
       // software pipeline over the 32-column chunks: the TMEM load (and RMW prefetch) of chunk c+1 is in
       // flight while chunk c is processed
       uint32_t bufA[32], bufB[32];
-      uint4 oldA[4], oldB[4];
+      uint32_t oldA[16], oldB[16];
       const uint32_t dbg = sh.dbg_sbo >> 16;   // bring-up switches (tools/probe_gemm.py), 0 in production
       if (dbg != 1) {
         issue(0, bufA, oldA);
