@@ -66,6 +66,7 @@ struct GemmShape {
   int k_splits;
   // debug overrides of the MN-major descriptor fields (0 = computed); see tests/test_gemm_gpu.py
   uint32_t dbg_lbo, dbg_sbo;
+  unsigned long long* dbg_clk;  // bring-up: per-CTA cycle counters of the pipeline phases (nullptr in production)
 };
 
 
@@ -190,7 +191,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
         const int kb1 = (int)(((long)(ks + 1) * nkb) / sh.k_splits);
         for (int kb = kb0; kb < kb1; ++kb) {
+          const long long tw0 = sh.dbg_clk ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (sh.dbg_clk) sh.dbg_clk[blockIdx.x * 16 + 0] += clock64() - tw0;   // producer: waiting for a free stage
           uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -232,11 +235,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ks = t / (m_tiles * n_tiles);
       const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
       const int kb1 = (int)(((long)(ks + 1) * nkb) / sh.k_splits);
+      long long tm0 = sh.dbg_clk ? clock64() : 0;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+      if (sh.dbg_clk && lane == 0) sh.dbg_clk[blockIdx.x * 16 + 1] += clock64() - tm0;   // MMA: waiting for a drained accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBlockN);
       for (int kb = kb0; kb < kb1; ++kb) {
+        tm0 = sh.dbg_clk ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
+        if (sh.dbg_clk && lane == 0) sh.dbg_clk[blockIdx.x * 16 + 2] += clock64() - tm0;  // MMA: waiting for TMA data
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
@@ -283,8 +290,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bias_s[j] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.f;
         if (ctx_shared) ctx_s[j] = n < sh.N ? __ldg(ep.qv + n) : 0.f;
       }
+      const bool clk = sh.dbg_clk && ew == 0 && lane == 0;
+      long long te0 = sh.dbg_clk ? clock64() : 0;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      if (clk) sh.dbg_clk[blockIdx.x * 16 + 4 + grp * 4] += clock64() - te0;   // epilogue: staging barrier
+      te0 = sh.dbg_clk ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
+      if (clk) sh.dbg_clk[blockIdx.x * 16 + 5 + grp * 4] += clock64() - te0;   // epilogue: waiting for the accumulator
+      te0 = sh.dbg_clk ? clock64() : 0;
       tc_fence_after();
       const int r0 = m_blk * 128 + ew * 32;  // first row of this warp's slab
       const int r = r0 + lane;
@@ -510,6 +523,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (clk) {
+        sh.dbg_clk[blockIdx.x * 16 + 6 + grp * 4] += clock64() - te0;          // epilogue: draining one tile
+        sh.dbg_clk[blockIdx.x * 16 + 7 + grp * 4] += 1;                         // tiles
+      }
       acc_phase ^= 1u;
     }
   }

@@ -142,9 +142,11 @@ def run_case(name: str) -> dict:
         outf = torch.zeros(M, N, device=dev) if ks > 1 else None
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-        def go():
+        clk = torch.zeros(148, 16, dtype=torch.int64, device=dev)
+
+        def go(c=None):
             ops.gemm(A, B, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, k_splits=ks, out_bf16=None if noout else outb,
-                     out_f32=None if noout else outf, block_n=bn, dbg_sbo=dbg << 16,
+                     out_f32=None if noout else outf, block_n=bn, dbg_sbo=dbg << 16, dbg_clk=c,
                      f32_mode=ops.OUT_ATOMIC if ks > 1 else ops.OUT_STORE)
         for _ in range(3):
             go()
@@ -162,6 +164,12 @@ def run_case(name: str) -> dict:
         res["ms"] = ms
         res["tflops"] = 2.0 * M * N * K / ms / 1e9
         res["gbs"] = (A.numel() * 2 + B.numel() * 2 + M * N * (2 if ks == 1 else 4)) / ms / 1e6
+        go(clk)
+        torch.cuda.synchronize()
+        cm = clk.float().mean(0).tolist()
+        res["clk"] = {"prod_wait_empty": cm[0], "mma_wait_tempty": cm[1], "mma_wait_full": cm[2],
+                      "epi0_bar": cm[4], "epi0_wait_tfull": cm[5], "epi0_drain": cm[6], "epi0_tiles": cm[7],
+                      "epi1_wait_tfull": cm[9], "epi1_drain": cm[10], "epi1_tiles": cm[11]}
         res["ok"] = True
     elif kind == "timeepi":
         # timeepi:inproj:<ntgt>:<K>  |  timeepi:keyproj:<nq>:<store_k>
