@@ -122,12 +122,12 @@ int num_sms() {
   return g_num_sms;
 }
 
-template <int kBlockN, bool kTF32>
+template <int kBlockN, bool kTF32, int kKind>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& sh, const GemmEpi& ep,
                        int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN>;
   static bool attr_done = false;
-  auto kern = gemm_tcgen05_kernel<kBlockN, kTF32>;
+  auto kern = gemm_tcgen05_kernel<kBlockN, kTF32, kKind>;
   if (!attr_done) {
     SDUMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
@@ -200,14 +200,23 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
 
   if (tf32) {
-    if (block_n == 256) return launch_inst<256, true>(ta, tb, sh, epi, grid, stream);
-    if (block_n == 128) return launch_inst<128, true>(ta, tb, sh, epi, grid, stream);
-    return launch_inst<64, true>(ta, tb, sh, epi, grid, stream);
-  } else {
-    if (block_n == 256) return launch_inst<256, false>(ta, tb, sh, epi, grid, stream);
-    if (block_n == 128) return launch_inst<128, false>(ta, tb, sh, epi, grid, stream);
-    return launch_inst<64, false>(ta, tb, sh, epi, grid, stream);
+    SDUMC_CHECK_ARG(epi.kind == EPI_GENERIC, "gemm: tf32 operands support the generic epilogue only");
+    if (block_n == 256) return launch_inst<256, true, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
+    if (block_n == 128) return launch_inst<128, true, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
+    return launch_inst<64, true, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
   }
+  if (epi.kind == EPI_INPROJ) {
+    SDUMC_CHECK_ARG(block_n == 256, "gemm: in-proj epilogue is instantiated for block_n 256 (N = 256)");
+    return launch_inst<256, false, KIND_INPROJ>(ta, tb, sh, epi, grid, stream);
+  }
+  if (epi.kind == EPI_KEYPROJ) return launch_inst<256, false, KIND_KEYPROJ>(ta, tb, sh, epi, grid, stream);
+  // 'bf16 += acc * frame mask' without any other option: the dH accumulation of the attention backward
+  const bool pure_rmw = block_n == 256 && epi.out_bf16 && epi.bf16_mode == OUT_ADD && !epi.out_f32 && !epi.bias &&
+                        epi.act == ACT_NONE && !epi.gate && epi.drop_p == 0.f;
+  if (pure_rmw) return launch_inst<256, false, KIND_RMW>(ta, tb, sh, epi, grid, stream);
+  if (block_n == 256) return launch_inst<256, false, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
+  if (block_n == 128) return launch_inst<128, false, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
+  return launch_inst<64, false, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
 }
 
 }  // namespace sdumc

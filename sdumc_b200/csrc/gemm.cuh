@@ -30,6 +30,9 @@ namespace sdumc {
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_TANH = 2 };
 enum : int { OUT_STORE = 0, OUT_ADD = 1, OUT_ATOMIC = 2 };
 enum : int { EPI_GENERIC = 0, EPI_INPROJ = 1, EPI_KEYPROJ = 2 };
+// compile-time specialisations of the epilogue (one compact chunk loop per kind: the all-in-one body thrashed
+// the instruction cache); KIND_RMW = generic restricted to 'bf16 += acc * frame_mask' (the dH accumulation)
+enum : int { KIND_GENERIC = 0, KIND_INPROJ = 1, KIND_KEYPROJ = 2, KIND_RMW = 3 };
 
 struct GemmEpi {
   int kind;  // EPI_*
@@ -126,7 +129,7 @@ struct GemmCfg {
   static constexpr int kThreads = 384;
 };
 
-template <int kBlockN, bool kTF32>
+template <int kBlockN, bool kTF32, int kKind>
 __global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmShape sh, const GemmEpi ep) {
@@ -275,8 +278,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const uint32_t drop_thr = drop_threshold(ep.drop_p);
     const float drop_scale = ep.drop_p > 0.f ? 1.f / (1.f - ep.drop_p) : 1.f;
     const DropKey key = resolve_key(ep.key);
-    const bool rmw = ep.kind == EPI_GENERIC && ep.out_bf16 && ep.bf16_mode == OUT_ADD;
-    const bool ctx_shared = ep.kind == EPI_KEYPROJ && ep.q_stride == 0 && ep.nq == 1;
+    const bool rmw = kKind == KIND_RMW || (kKind == KIND_GENERIC && ep.out_bf16 && ep.bf16_mode == OUT_ADD);
+    const bool ctx_shared = kKind == KIND_KEYPROJ && ep.q_stride == 0 && ep.nq == 1;
     constexpr int NC = kBlockN / 32;
     int li = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++li) {
@@ -306,7 +309,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
       float sc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       const float* qrow = ep.qv;
-      if (ep.kind == EPI_KEYPROJ && row_ok) qrow = ep.qv + (long)(r / ep.L) * ep.q_stride;
+      if (kKind == KIND_KEYPROJ && row_ok) qrow = ep.qv + (long)(r / ep.L) * ep.q_stride;
       U4 tw[4];
 
       // issue the TMEM load of chunk c (and, for read-modify-write outputs, the loads of the old values)
@@ -335,15 +338,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           v[j + 2] = __uint_as_float(acc_r[j + 2]) + b4.z;
           v[j + 3] = __uint_as_float(acc_r[j + 3]) + b4.w;
         }
-        if (ep.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        } else if (ep.act == ACT_TANH) {
+        if constexpr (kKind == KIND_KEYPROJ) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
+        } else if constexpr (kKind == KIND_GENERIC) {
+          if (ep.act == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+          } else if (ep.act == ACT_TANH) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = tanh_fast(v[j]);
+          }
         }
 
-        if (ep.kind == EPI_INPROJ) {
+        if constexpr (kKind == KIND_INPROJ) {
           uint32_t w[16];
           if (ep.out_bf16) {
 #pragma unroll
@@ -370,7 +378,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           return;
         }
 
-        if (ep.kind == EPI_KEYPROJ) {
+        if constexpr (kKind == KIND_KEYPROJ) {
           if (ep.out_bf16) {
             uint32_t w[16];
 #pragma unroll
@@ -430,7 +438,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           return;
         }
 
+        if constexpr (kKind == KIND_RMW) {   // dH += acc * frame mask
+          if (ep.fmask_site) {
+            const U4 w4 = frame_mask_words(key, ep.fmask_site, (uint32_t)r, (uint32_t)(n0 >> 7));
+            const int wsel = (n0 >> 5) & 3;
+            const uint32_t bits = wsel == 0 ? w4.x : (wsel == 1 ? w4.y : (wsel == 2 ? w4.z : w4.w));
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = ((bits >> j) & 1u) ? 2.f * v[j] : 0.f;
+          }
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          if (row_ok) store_row_bf16(ep.out_bf16 + (long)r * ep.ld_bf16 + n0, w, oldv);
+          return;
+        }
+
         // ---- generic ----
+        if constexpr (kKind == KIND_GENERIC) {
         if (ep.gate && row_ok) {
           const float* g = ep.gate + (long)r * ep.ld_gate + n0;
           if (full) {
@@ -495,6 +519,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           for (int j = 0; j < 16; ++j) w[j] = pack_bf16x2(v[2 * j], v[2 * j + 1]);
           if (row_ok) store_row_bf16(ep.out_bf16 + (long)r * ep.ld_bf16 + n0, w, rmw ? oldv : nullptr);
         }
+        }  // KIND_GENERIC
       };
 
       // software pipeline over the 32-column chunks: the TMEM load (and RMW prefetch) of chunk c+1 is in
@@ -514,7 +539,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (dbg != 2) process(c + 1, bufB, oldB);
         }
       }
-      if (ep.kind == EPI_KEYPROJ && row_ok) {
+      if (kKind == KIND_KEYPROJ && row_ok) {
         float* srow = ep.scores + (long)r * ep.nq;
 #pragma unroll
         for (int q = 0; q < 7; ++q)
