@@ -150,7 +150,7 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
   const int m_tiles = (sh.M + 127) / 128;
   const int sms = num_sms();
   if (block_n == 0) {
-    if (epi.kind == EPI_KEYPROJ) {
+    if (epi.kind == EPI_KEYPROJ || epi.kind == EPI_INPROJ) {   // specialised epilogues own a whole 256-wide row
       block_n = 256;
     } else {
       const long t256 = (long)m_tiles * ((sh.N + 255) / 256) * sh.k_splits;
