@@ -114,11 +114,34 @@ def _ksplits(rows_k: int, m_gemm: int, n_gemm: int) -> int:
 
 
 class Engine:
-    def __init__(self, layout: ParamLayout, device):
+    def __init__(self, layout: ParamLayout, device, multi_stream: bool = True):
         self.layout = layout
         self.device = device
+        self.multi_stream = multi_stream
+        self._streams: List[torch.cuda.Stream] = []
 
     # ------------------------------------------------------------------ helpers
+    def _parallel(self, n: int, fn):
+        """Run fn(0..n-1) on n side streams forked from the current stream, then join.  The branches of the
+        model that do not depend on each other (three modalities, seven query MLPs, ...) are small kernels
+        that each occupy a fraction of the SMs; running them side by side hides their launch / pipeline-fill
+        latency (and becomes parallel branches of the captured CUDA graph).  Tensors shared with the main
+        stream must be allocated before the fork."""
+        if not self.multi_stream or n <= 1:
+            for i in range(n):
+                fn(i)
+            return
+        main = torch.cuda.current_stream()
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=self.device))
+        for i in range(n):
+            side = self._streams[i]
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                fn(i)
+        for i in range(n):
+            main.wait_stream(self._streams[i])
+
     def _new(self, st: State, name: str, shape, dtype=torch.float32, zero=False):
         fn = torch.zeros if zero else torch.empty
         t = fn(shape, dtype=dtype, device=self.device)
@@ -202,27 +225,40 @@ class Engine:
         u_pool_b = [self._new(st, f"u_bf16.{m}", (R, G), torch.bfloat16) for m in range(3)]
         for (p, m) in units:
             L = cfg.frames[_unit_stream(p, m)]
+            self._new(st, f"Sf.{p}.{m}", (B * L, 1))
+            if keep:
+                self._new(st, f"Kf.{p}.{m}", (B * L, G), torch.bfloat16)
+            self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
+
+        def fra2utt_unit(i):
+            p, m = units[i]
+            L = cfg.frames[_unit_stream(p, m)]
             X = st.t[f"Xf.{p}.{m}"]
-            S = self._new(st, f"Sf.{p}.{m}", (B * L, 1))
-            Kt = self._new(st, f"Kf.{p}.{m}", (B * L, G), torch.bfloat16) if keep else None
+            S = st.t[f"Sf.{p}.{m}"]
+            Kt = st.t[f"Kf.{p}.{m}"] if keep else None
             pre = f"fra2utt_{m}"
             ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
                      act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt,
                      qv=W.f32(pre + ".attention_context_vector"), q_stride=0, nq=1, L=L, scores=S)
-            Opre = self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
-            ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=Opre, out=u_pool[m][p * B:(p + 1) * B], out_stride_b=G,
-                         out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
+            ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=st.t[f"Of_pre.{p}.{m}"], out=u_pool[m][p * B:(p + 1) * B],
+                         out_stride_b=G, out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
                          site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev)
+        self._parallel(len(units), fra2utt_unit)
 
         # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
         cat = self._new(st, "cat", (R, 3 * G))
         cat_b = self._new(st, "cat_bf16", (R, 3 * G), torch.bfloat16)
-        for m, name in enumerate(MODALITY_MLPS):
-            h1 = self._new(st, f"h1.{m}", (R, G))
-            h1b = self._new(st, f"h1_bf16.{m}", (R, G), torch.bfloat16)
+        for m in range(3):
+            self._new(st, f"h1.{m}", (R, G))
+            self._new(st, f"h1_bf16.{m}", (R, G), torch.bfloat16)
+
+        def modality_mlp(m):
+            name = MODALITY_MLPS[m]
+            h1, h1b = st.t[f"h1.{m}"], st.t[f"h1_bf16.{m}"]
             self._linear_fwd(W, st, name + ".0", u_pool[m], h1, relu=True, drop_site=site_id(name + ".0"), y_bf16=h1b)
             self._linear_fwd(W, st, name + ".3", h1, cat[:, m * G:(m + 1) * G], relu=True,
                              drop_site=site_id(name + ".1"), y_bf16=cat_b[:, m * G:(m + 1) * G])
+        self._parallel(3, modality_mlp)
         a1 = self._new(st, "a1", (R, G))
         a1b = self._new(st, "a1_bf16", (R, G), torch.bfloat16)
         a2 = self._new(st, "a2", (R, G))
@@ -236,40 +272,55 @@ class Engine:
             ops.cast_bf16(qin, qin_b)
         Q = self._new(st, "Q", (R, NQ * G))
         Q_b = self._new(st, "Q_bf16", (R, NQ * G), torch.bfloat16)
-        for i, name in enumerate(QUERY_MLPS):
+        def query_mlp(i):
+            name = QUERY_MLPS[i]
             x = qin[i] if i < 4 else cat[:, (i - 4) * G:(i - 3) * G]
             self._linear_fwd(W, st, name + ".0", x, Q[:, i * G:(i + 1) * G], relu=True, drop_site=site_id(name + ".0"),
                              y_bf16=Q_b[:, i * G:(i + 1) * G])
+        self._parallel(NQ, query_mlp)
         Qp = [self._new(st, f"Qp.{m}", (R * NQ, G)) for m in range(3)]
-        for m in range(3):
-            self._linear_fwd(W, st, f"cross_att_fra2utt_{m}.query_proj", Q.view(R * NQ, G), Qp[m], relu=False)
+        self._parallel(3, lambda m: self._linear_fwd(W, st, f"cross_att_fra2utt_{m}.query_proj", Q.view(R * NQ, G),
+                                                     Qp[m], relu=False))
 
         # 4. Cross_Attention per unit
         C = [self._new(st, f"C.{m}", (R * NQ, G)) for m in range(3)]
         C_b = [self._new(st, f"C_bf16.{m}", (R * NQ, G), torch.bfloat16) for m in range(3)]
         for (p, m) in units:
             L = cfg.frames[_unit_stream(p, m)]
+            self._new(st, f"Sc.{p}.{m}", (B * L, NQ))
+            if keep:
+                self._new(st, f"Kc.{p}.{m}", (B * L, G), torch.bfloat16)
+            self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
+
+        def cross_unit(i):
+            p, m = units[i]
+            L = cfg.frames[_unit_stream(p, m)]
             X = st.t[f"Xc.{p}.{m}"]
-            S = self._new(st, f"Sc.{p}.{m}", (B * L, NQ))
-            Kt = self._new(st, f"Kc.{p}.{m}", (B * L, G), torch.bfloat16) if keep else None
+            S = st.t[f"Sc.{p}.{m}"]
+            Kt = st.t[f"Kc.{p}.{m}"] if keep else None
             pre = f"cross_att_fra2utt_{m}"
             ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
                      act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=Qp[m][p * B * NQ:(p + 1) * B * NQ],
                      q_stride=NQ * G, nq=NQ, L=L, scores=S)
-            Opre = self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
-            ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=Opre, out=C[m][p * B * NQ:(p + 1) * B * NQ],
+            ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=st.t[f"Oc_pre.{p}.{m}"], out=C[m][p * B * NQ:(p + 1) * B * NQ],
                          out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
-                         drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev)
+                         drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step,
+                         step_dev=cfg.step_dev)
+        self._parallel(len(units), cross_unit)
 
         # 5. utterance chain B
         c = []
-        for m, name in enumerate(CROSS_MLPS):
-            c1 = self._new(st, f"c1.{m}", (R * NQ, 256))
-            c1b = self._new(st, f"c1_bf16.{m}", (R * NQ, 256), torch.bfloat16)
-            cm = self._new(st, f"c.{m}", (R * NQ, 128))
+        for m in range(3):
+            self._new(st, f"c1.{m}", (R * NQ, 256))
+            self._new(st, f"c1_bf16.{m}", (R * NQ, 256), torch.bfloat16)
+            c.append(self._new(st, f"c.{m}", (R * NQ, 128)))
+
+        def cross_mlp(m):
+            name = CROSS_MLPS[m]
+            c1, c1b = st.t[f"c1.{m}"], st.t[f"c1_bf16.{m}"]
             self._linear_fwd(W, st, name + ".0", C[m], c1, relu=True, drop_site=site_id(name + ".0"), y_bf16=c1b)
-            self._linear_fwd(W, st, name + ".3", c1, cm, relu=True, drop_site=site_id(name + ".1"))
-            c.append(cm)
+            self._linear_fwd(W, st, name + ".3", c1, c[m], relu=True, drop_site=site_id(name + ".1"))
+        self._parallel(3, cross_mlp)
         Wc = self._new(st, "Wc", (R, NQ * 128))
         ops.weight_fwd(c, g, R=R, W=Wc)
         Wc_b = self._new(st, "Wc_bf16", (R, NQ * 128), torch.bfloat16)
@@ -347,20 +398,29 @@ class Engine:
         extra = (None, d_ct.reshape(R * NQ, 128).contiguous() if d_ct is not None else None, None)
         ops.weight_bwd(dWc, [t[f"c.{m}"] for m in range(3)], t["g"], R=R, dc=dc, dg=dg_extra, dc_extra=extra)
         # B5. cross MLPs -> gradient of the (dropped) pooled cross-attention outputs
-        dC = []
-        for m, name in enumerate(CROSS_MLPS):
-            dc1 = e(R * NQ, 256)
-            self._linear_bwd(W, st, name + ".3", dc[m], t[f"c1_bf16.{m}"], Y=t[f"c.{m}"], dropped=True, dX=dc1)
-            dCm = e(R * NQ, G)
-            self._linear_bwd(W, st, name + ".0", dc1, t[f"C_bf16.{m}"], Y=t[f"c1.{m}"], dropped=True, dX=dCm)
-            dC.append(dCm)
+        dC = [e(R * NQ, G) for _ in range(3)]
+        dc1s = [e(R * NQ, 256) for _ in range(3)]
+
+        def cross_mlp_bwd(m):
+            name = CROSS_MLPS[m]
+            self._linear_bwd(W, st, name + ".3", dc[m], t[f"c1_bf16.{m}"], Y=t[f"c.{m}"], dropped=True, dX=dc1s[m])
+            self._linear_bwd(W, st, name + ".0", dc1s[m], t[f"C_bf16.{m}"], Y=t[f"c1.{m}"], dropped=True, dX=dC[m])
+        self._parallel(3, cross_mlp_bwd)
         # B6. Cross_Attention blocks
         dH: Dict[str, torch.Tensor] = {}
+        for (p, m) in units:                       # one dH per input stream, written first by the cross block
+            s_ = _unit_stream(p, m)
+            if s_ not in dH:
+                dH[s_] = torch.empty(B * cfg.frames[s_], G, dtype=torch.bfloat16, device=dev)
+        started: Dict[str, bool] = {}
         dQp = [e(R * NQ, G) for _ in range(3)]
-        for (p, m) in units:
-            self._attn_block_bwd(W, st, p, m, "cross_att_fra2utt", NQ, dOut=dC[m][p * B * NQ:(p + 1) * B * NQ],
-                                 Qp=t[f"Qp.{m}"][p * B * NQ:(p + 1) * B * NQ], qp_stride=NQ * G,
-                                 dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH)
+
+        def cross_attn_bwd(m):                     # passes of one modality accumulate into the same dH: in order
+            for p in range(NP):
+                self._attn_block_bwd(W, st, p, m, "cross_att_fra2utt", NQ, dOut=dC[m][p * B * NQ:(p + 1) * B * NQ],
+                                     Qp=t[f"Qp.{m}"][p * B * NQ:(p + 1) * B * NQ], qp_stride=NQ * G,
+                                     dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH, started=started)
+        self._parallel(3, cross_attn_bwd)
         # B7. query projections -> dQ
         dQ = e(R * NQ, G)
         for m in range(3):
@@ -372,11 +432,13 @@ class Engine:
         dcat = e(R, 3 * G)
         Qv = t["Q"]
         dth = d_th.reshape(R, G).contiguous() if d_th is not None else None
-        for i, name in enumerate(QUERY_MLPS):
+        def query_mlp_bwd(i):
+            name = QUERY_MLPS[i]
             xb = t["qin_bf16"][i] if i < 4 else t["cat_bf16"][:, (i - 4) * G:(i - 3) * G]
             dX = dqin[i] if i < 4 else dcat[:, (i - 4) * G:(i - 3) * G]
             self._linear_bwd(W, st, name + ".0", dQ[:, i * G:(i + 1) * G], xb, Y=Qv[:, i * G:(i + 1) * G],
                              dropped=True, dX=dX, dY2=dth if i == 5 else None)
+        self._parallel(NQ, query_mlp_bwd)
         # gate + partial fusions
         da2 = e(R, G)
         ops.gate_bwd(dqin, dg_extra, t["g"], t["cat"], t["a2"], W.f32("fc_att.weight"), R=R, dh=dcat, da2=da2,
@@ -386,31 +448,38 @@ class Engine:
         self._linear_bwd(W, st, "attention_mlp.0", da1, t["cat_bf16"], Y=t["a1"], dropped=True, dX=dcat,
                          dX_mode=ops.OUT_ADD)
         # B9. modality MLPs -> gradient of the (dropped) FRA2UTT outputs
-        du = []
-        for m, name in enumerate(MODALITY_MLPS):
-            dh1 = e(R, G)
+        du = [e(R, G) for _ in range(3)]
+        dh1s = [e(R, G) for _ in range(3)]
+
+        def modality_mlp_bwd(m):
+            name = MODALITY_MLPS[m]
             self._linear_bwd(W, st, name + ".3", dcat[:, m * G:(m + 1) * G], t[f"h1_bf16.{m}"],
-                             Y=t["cat"][:, m * G:(m + 1) * G], dropped=True, dX=dh1)
-            dum = e(R, G)
-            self._linear_bwd(W, st, name + ".0", dh1, t[f"u_bf16.{m}"], Y=t[f"h1.{m}"], dropped=True, dX=dum)
-            du.append(dum)
+                             Y=t["cat"][:, m * G:(m + 1) * G], dropped=True, dX=dh1s[m])
+            self._linear_bwd(W, st, name + ".0", dh1s[m], t[f"u_bf16.{m}"], Y=t[f"h1.{m}"], dropped=True, dX=du[m])
+        self._parallel(3, modality_mlp_bwd)
         # B10. FRA2UTT_new blocks
-        for (p, m) in units:
+        def fra2utt_bwd(m):
             pre = f"fra2utt_{m}"
-            self._attn_block_bwd(W, st, p, m, "fra2utt", 1, dOut=du[m][p * B:(p + 1) * B],
-                                 Qp=W.f32(pre + ".attention_context_vector"), qp_stride=0,
-                                 dQp=W.grad(pre + ".attention_context_vector"), dH=dH)
+            for p in range(NP):
+                self._attn_block_bwd(W, st, p, m, "fra2utt", 1, dOut=du[m][p * B:(p + 1) * B],
+                                     Qp=W.f32(pre + ".attention_context_vector"), qp_stride=0,
+                                     dQp=W.grad(pre + ".attention_context_vector"), dH=dH, started=started)
+        self._parallel(3, fra2utt_bwd)
         # B11. in-projection weight / bias gradients (inputs carry no gradient)
-        for s, dHs in dH.items():
+        items = list(dH.items())
+
+        def inproj_bwd(i):
+            s, dHs = items[i]
             wname = INPROJ[_stream_mod(s)]
             X = t[f"X.{s}"]
             rows, D = X.shape
             ops.gemm(dHs, X, M=G, N=D, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, G, D),
                      out_f32=W.grad(wname + ".weight"), f32_mode=ops.OUT_ATOMIC)
             ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
+        self._parallel(len(items), inproj_bwd)
 
     def _attn_block_bwd(self, W: Weights, st: State, p: int, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
-                        dH: Dict[str, torch.Tensor]):
+                        dH: Dict[str, torch.Tensor], started: Dict[str, bool]):
         cfg = st.cfg
         t = st.t
         B = cfg.B
@@ -423,9 +492,8 @@ class Engine:
         P = t[f"S{tag}.{p}.{m}"]
         Opre = t[f"O{tag}_pre.{p}.{m}"]
         dZ = torch.empty(B * L, G, dtype=torch.bfloat16, device=self.device)
-        first = s not in dH
-        if first:
-            dH[s] = torch.empty(B * L, G, dtype=torch.bfloat16, device=self.device)
+        first = not started.get(s, False)          # the first block of a stream stores, later ones accumulate
+        started[s] = True
         fmask = site_id(pre + ".in", p) if cfg.dropout else 0
         ops.attn_bwd(X, Kt, P, dOut, dout_stride_b=nq * G, O_pre=Opre, Qp=Qp, qp_stride_b=qp_stride, B=B, L=L, nq=nq,
                      out_drop_p=FRAME_P if cfg.dropout else 0.0, out_site=site_id(pre + ".out", p), dZ=dZ, dH=dH[s],
