@@ -152,9 +152,11 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
 // reduced with a halving butterfly (9 shuffles + NQ broadcasts instead of 5 * NQ).
 // ------------------------------------------------------------------------------------------
 template <int NQ>
-__global__ void __launch_bounds__(256, (NQ == 1) ? 3 : 1) attn_bwd_kernel(AttnBwdArgs a) {
+__global__ void __launch_bounds__(256, (NQ == 1) ? 2 : 1) attn_bwd_kernel(AttnBwdArgs a) {
+  constexpr int RB = 2;           // rows per warp iteration (independent dependency chains -> ILP)
   extern __shared__ float P_s[];  // [L][8] probabilities of this sample (padded to 8 per row)
   __shared__ float dO_s[NQ][G];
+  __shared__ float Qp_s[NQ][G];
   __shared__ float red_q[NQ][G];
   __shared__ float red_b[G];
   __shared__ float delta_s[8];
@@ -172,6 +174,7 @@ __global__ void __launch_bounds__(256, (NQ == 1) ? 3 : 1) attn_bwd_kernel(AttnBw
       g = elem_rand(key, a.out_site, e) >= thr ? g * oscale : 0.f;
     }
     (&dO_s[0][0])[i] = g;
+    (&Qp_s[0][0])[i] = __ldg(a.Qp + (long)b * a.qp_stride_b + i);
     (&red_q[0][0])[i] = 0.f;
   }
   for (int i = tid; i < L * 8; i += 256) {
@@ -190,123 +193,148 @@ __global__ void __launch_bounds__(256, (NQ == 1) ? 3 : 1) attn_bwd_kernel(AttnBw
   __syncthreads();
 
   const int g0 = lane * 8;
-  float dO[NQ][8], Qp[NQ][8], dq_acc[NQ][8], db_acc[8];
+  float dO[NQ][8], dq_acc[NQ][8], db_acc[8];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
     const float4 d0 = *reinterpret_cast<const float4*>(&dO_s[q][g0]);
     const float4 d1 = *reinterpret_cast<const float4*>(&dO_s[q][g0 + 4]);
-    const float* qp = a.Qp + (long)b * a.qp_stride_b + q * G + g0;
-    const float4 q0 = __ldg(reinterpret_cast<const float4*>(qp));
-    const float4 q1 = __ldg(reinterpret_cast<const float4*>(qp + 4));
     dO[q][0] = d0.x; dO[q][1] = d0.y; dO[q][2] = d0.z; dO[q][3] = d0.w;
     dO[q][4] = d1.x; dO[q][5] = d1.y; dO[q][6] = d1.z; dO[q][7] = d1.w;
-    Qp[q][0] = q0.x; Qp[q][1] = q0.y; Qp[q][2] = q0.z; Qp[q][3] = q0.w;
-    Qp[q][4] = q1.x; Qp[q][5] = q1.y; Qp[q][6] = q1.z; Qp[q][7] = q1.w;
 #pragma unroll
     for (int j = 0; j < 8; ++j) dq_acc[q][j] = 0.f;
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) db_acc[j] = 0.f;
-  // which of the (up to 8) per-row sums this lane ends up owning after the butterfly
+  // which of the (up to 8) per-row sums this lane owns after the butterfly
   const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const float my_delta = delta_s[own];
 
-  uint4 nx = make_uint4(0, 0, 0, 0), nk = nx, nh = nx;
-  if (warp < L) {
-    const long row0 = (long)b * L + warp;
-    nx = __ldg(reinterpret_cast<const uint4*>(a.X + row0 * a.ldx + g0));
-    nk = __ldg(reinterpret_cast<const uint4*>(a.Kt + row0 * a.ldk + g0));
-    if (a.dh_mode == 1) nh = *reinterpret_cast<const uint4*>(a.dH + row0 * a.lddh + g0);
+  // each warp owns rows {warp*RB + i*8*RB + r}; loads of the next pair are in flight while a pair computes
+  uint4 nx[RB], nk[RB], nh[RB];
+#pragma unroll
+  for (int r = 0; r < RB; ++r) {
+    nx[r] = make_uint4(0, 0, 0, 0); nk[r] = nx[r]; nh[r] = nx[r];
+    const int l = warp * RB + r;
+    if (l < L) {
+      const long row = (long)b * L + l;
+      nx[r] = __ldg(reinterpret_cast<const uint4*>(a.X + row * a.ldx + g0));
+      nk[r] = __ldg(reinterpret_cast<const uint4*>(a.Kt + row * a.ldk + g0));
+      if (a.dh_mode == 1) nh[r] = *reinterpret_cast<const uint4*>(a.dH + row * a.lddh + g0);
+    }
   }
-  for (int l = warp; l < L; l += 8) {
-    const long row = (long)b * L + l;
-    float x[8], k[8];
-    unpack8(nx, x);
-    unpack8(nk, k);
-    const uint4 oldh = nh;
-    if (l + 8 < L) {
-      const long rown = row + 8;
-      nx = __ldg(reinterpret_cast<const uint4*>(a.X + rown * a.ldx + g0));
-      nk = __ldg(reinterpret_cast<const uint4*>(a.Kt + rown * a.ldk + g0));
-      if (a.dh_mode == 1) nh = *reinterpret_cast<const uint4*>(a.dH + rown * a.lddh + g0);
+  for (int l0 = warp * RB; l0 < L; l0 += 8 * RB) {
+    float x[RB][8], k[RB][8];
+    uint4 oldh[RB];
+#pragma unroll
+    for (int r = 0; r < RB; ++r) {
+      unpack8(nx[r], x[r]);
+      unpack8(nk[r], k[r]);
+      oldh[r] = nh[r];
+      const int ln = l0 + 8 * RB + r;
+      if (ln < L) {
+        const long rown = (long)b * L + ln;
+        nx[r] = __ldg(reinterpret_cast<const uint4*>(a.X + rown * a.ldx + g0));
+        nk[r] = __ldg(reinterpret_cast<const uint4*>(a.Kt + rown * a.ldk + g0));
+        if (a.dh_mode == 1) nh[r] = *reinterpret_cast<const uint4*>(a.dH + rown * a.lddh + g0);
+      }
     }
-    const float4 p0 = *reinterpret_cast<const float4*>(&P_s[l * 8]);
-    const float4 p1 = *reinterpret_cast<const float4*>(&P_s[l * 8 + 4]);
-    const float Pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-
-    // partial dot products of this lane's 8 columns
-    float v[8];
+    // partial dot products of this lane's 8 columns, for both rows
+    float dS[RB][NQ];
+    float Pv[RB][8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      if (q < NQ) {
-        float s = x[0] * dO[q][0];
+    for (int r = 0; r < RB; ++r) {
+      const int l = min(l0 + r, L - 1);   // a missing second row recomputes the last row; its stores are skipped
+      const float4 p0 = *reinterpret_cast<const float4*>(&P_s[l * 8]);
+      const float4 p1 = *reinterpret_cast<const float4*>(&P_s[l * 8 + 4]);
+      Pv[r][0] = p0.x; Pv[r][1] = p0.y; Pv[r][2] = p0.z; Pv[r][3] = p0.w;
+      Pv[r][4] = p1.x; Pv[r][5] = p1.y; Pv[r][6] = p1.z; Pv[r][7] = p1.w;
+      float v[8];
 #pragma unroll
-        for (int j = 1; j < 8; ++j) s = fmaf(x[j], dO[q][j], s);
-        v[q] = s;
+      for (int q = 0; q < 8; ++q) {
+        if (q < NQ) {
+          float s = x[r][0] * dO[q][0];
+#pragma unroll
+          for (int j = 1; j < 8; ++j) s = fmaf(x[r][j], dO[q][j], s);
+          v[q] = s;
+        } else {
+          v[q] = 0.f;
+        }
+      }
+      if (NQ == 1) {
+        const float dP = warp_sum(v[0]);
+        dS[r][0] = a.alpha * Pv[r][0] * (dP - delta_s[0]);
       } else {
-        v[q] = 0.f;
+        // halving butterfly: after 4+2+1+2 shuffles lane `own` holds the full sum of index `own`
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        float w[4], u[2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float keep = b4 ? v[4 + i] : v[i], send = b4 ? v[i] : v[4 + i];
+          w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const float keep = b3 ? w[2 + i] : w[i], send = b3 ? w[i] : w[2 + i];
+          u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        float t = (b2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u[0] : u[1], 4);
+        t += __shfl_xor_sync(0xffffffffu, t, 2);
+        t += __shfl_xor_sync(0xffffffffu, t, 1);
+        const float mine = a.alpha * P_s[l * 8 + own] * (t - my_delta);
+#pragma unroll
+        for (int q = 0; q < NQ; ++q)
+          dS[r][q] = __shfl_sync(0xffffffffu, mine, ((q & 4) ? 16 : 0) + ((q & 2) ? 8 : 0) + ((q & 1) ? 4 : 0));
       }
     }
-    float dS[NQ];
-    if (NQ == 1) {
-      const float dP = warp_sum(v[0]);
-      dS[0] = a.alpha * Pv[0] * (dP - delta_s[0]);
-    } else {
-      // halving butterfly: after 4+2+1+2 shuffles lane `own` holds the full sum of index `own`
-      const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-      float w[4], u[2];
+    // dK, value path, dQp: the Qp slice comes from shared memory once per row pair
+    float dK[RB][8], dXv[RB][8];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float keep = b4 ? v[4 + i] : v[i], send = b4 ? v[i] : v[4 + i];
-        w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-      }
+    for (int r = 0; r < RB; ++r)
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const float keep = b3 ? w[2 + i] : w[i], send = b3 ? w[i] : w[2 + i];
-        u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-      float t = (b2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u[0] : u[1], 4);
-      t += __shfl_xor_sync(0xffffffffu, t, 2);
-      t += __shfl_xor_sync(0xffffffffu, t, 1);
-      const float mine = a.alpha * P_s[l * 8 + own] * (t - my_delta);
-#pragma unroll
-      for (int q = 0; q < NQ; ++q)
-        dS[q] = __shfl_sync(0xffffffffu, mine, ((q & 4) ? 16 : 0) + ((q & 2) ? 8 : 0) + ((q & 1) ? 4 : 0));
-    }
-    float dK[8], dXv[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { dK[j] = 0.f; dXv[j] = 0.f; }
+      for (int j = 0; j < 8; ++j) { dK[r][j] = 0.f; dXv[r][j] = 0.f; }
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
+      const float4 q0 = *reinterpret_cast<const float4*>(&Qp_s[q][g0]);
+      const float4 q1 = *reinterpret_cast<const float4*>(&Qp_s[q][g0 + 4]);
+      const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dK[j] = fmaf(dS[q], Qp[q][j], dK[j]);
-        dXv[j] = fmaf(Pv[q], dO[q][j], dXv[j]);
-        dq_acc[q][j] = fmaf(dS[q], k[j], dq_acc[q][j]);
+      for (int r = 0; r < RB; ++r) {
+        const bool live = (l0 + r) < L;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          dK[r][j] = fmaf(dS[r][q], qq[j], dK[r][j]);
+          dXv[r][j] = fmaf(Pv[r][q], dO[q][j], dXv[r][j]);
+          if (live) dq_acc[q][j] = fmaf(dS[r][q], k[r][j], dq_acc[q][j]);
+        }
       }
     }
-    float dZ[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      dZ[j] = dK[j] * (1.f - k[j] * k[j]);
-      db_acc[j] += dZ[j];
-    }
-    *reinterpret_cast<uint4*>(a.dZ + row * a.lddz + g0) = pack8(dZ);
-
-    if (a.fmask_site) {
-      const U4 wm = frame_mask_words(key, a.fmask_site, (uint32_t)row, (uint32_t)(g0 >> 7));
-      const int wsel = (g0 >> 5) & 3;
-      const uint32_t bits = (wsel == 0 ? wm.x : (wsel == 1 ? wm.y : (wsel == 2 ? wm.z : wm.w))) >> (g0 & 31);
+    for (int r = 0; r < RB; ++r) {
+      const int l = l0 + r;
+      if (l >= L) break;
+      const long row = (long)b * L + l;
+      float dZ[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dXv[j] = ((bits >> j) & 1u) ? 2.f * dXv[j] : 0.f;
-    }
-    if (a.dh_mode == 1) {
-      float old[8];
-      unpack8(oldh, old);
+      for (int j = 0; j < 8; ++j) {
+        dZ[j] = dK[r][j] * (1.f - k[r][j] * k[r][j]);
+        db_acc[j] += dZ[j];
+      }
+      *reinterpret_cast<uint4*>(a.dZ + row * a.lddz + g0) = pack8(dZ);
+      if (a.fmask_site) {
+        const U4 wm = frame_mask_words(key, a.fmask_site, (uint32_t)row, (uint32_t)(g0 >> 7));
+        const int wsel = (g0 >> 5) & 3;
+        const uint32_t bits = (wsel == 0 ? wm.x : (wsel == 1 ? wm.y : (wsel == 2 ? wm.z : wm.w))) >> (g0 & 31);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) dXv[j] += old[j];
+        for (int j = 0; j < 8; ++j) dXv[r][j] = ((bits >> j) & 1u) ? 2.f * dXv[r][j] : 0.f;
+      }
+      if (a.dh_mode == 1) {
+        float old[8];
+        unpack8(oldh[r], old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dXv[r][j] += old[j];
+      }
+      *reinterpret_cast<uint4*>(a.dH + row * a.lddh + g0) = pack8(dXv[r]);
     }
-    *reinterpret_cast<uint4*>(a.dH + row * a.lddh + g0) = pack8(dXv);
   }
 
 #pragma unroll
