@@ -151,21 +151,54 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
 // next row's X'/K/dH loads are in flight while a row computes, and the NQ per-row dot products are
 // reduced with a halving butterfly (9 shuffles + NQ broadcasts instead of 5 * NQ).
 // ------------------------------------------------------------------------------------------
+// One CTA per sample.  The sample's X', K (and dH when accumulating) rows are contiguous in memory, so they
+// are streamed through a kStages-deep shared-memory ring of 16-row stages filled by 1-D bulk copies
+// (cp.async.bulk + mbarrier): the bytes in flight (~100 KB per SM) no longer depend on registers.
+// A stage is consumed by all 8 warps, two rows each; a lane owns 8 of the 256 columns.
+constexpr int kBwdStages = 4;
+constexpr int kBwdRows = 16;                       // rows per stage
+constexpr int kBwdTile = kBwdRows * G * 2;         // bytes of one bf16 [16,256] tile
+
 template <int NQ>
-__global__ void __launch_bounds__(256, (NQ == 1) ? 2 : 1) attn_bwd_kernel(AttnBwdArgs a) {
-  constexpr int RB = 2;           // rows per warp iteration (independent dependency chains -> ILP)
-  extern __shared__ float P_s[];  // [L][8] probabilities of this sample (padded to 8 per row)
+__global__ void __launch_bounds__(256, 1) attn_bwd_kernel(AttnBwdArgs a) {
+  constexpr int RB = 2;  // rows per warp per stage (independent dependency chains -> ILP)
+  extern __shared__ __align__(128) unsigned char dyn[];
+  // layout: ring [kStages][3 tiles: X', K, dH_old] | P_s [L][8] | part [8 warps][NQ][G]
+  unsigned char* ring = dyn;
+  float* P_s = reinterpret_cast<float*>(dyn + kBwdStages * 3 * kBwdTile);
+  float* part = P_s + ((a.L * 8 + 3) & ~3);
   __shared__ float dO_s[NQ][G];
   __shared__ float Qp_s[NQ][G];
-  __shared__ float red_q[NQ][G];
-  __shared__ float red_b[G];
+  __shared__ float red_b[8][G];
   __shared__ float delta_s[8];
+  __shared__ __align__(8) uint64_t full_bar[kBwdStages];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int L = a.L;
+  const int n_iter = (L + kBwdRows - 1) / kBwdRows;
+  const bool rmw = a.dh_mode == 1;
   const uint32_t thr = drop_threshold(a.out_drop_p);
   const float oscale = a.out_drop_p > 0.f ? 1.f / (1.f - a.out_drop_p) : 1.f;
   const DropKey key = resolve_key(a.key);
+  const __nv_bfloat16* Xb = a.X + (long)b * L * G;    // host guarantees ldx == ldk == lddh == 256
+  const __nv_bfloat16* Kb = a.Kt + (long)b * L * G;
+  const __nv_bfloat16* Hb = a.dH + (long)b * L * G;
+
+  auto issue_stage = [&](int it) {                    // thread 0 only
+    const int slot = it % kBwdStages;
+    const int rows = min(kBwdRows, L - it * kBwdRows);
+    const uint32_t bytes = (uint32_t)rows * G * 2;
+    unsigned char* dst = ring + slot * 3 * kBwdTile;
+    mbar_expect_tx(&full_bar[slot], bytes * (rmw ? 3u : 2u));
+    bulk_load(dst, Xb + (long)it * kBwdRows * G, bytes, &full_bar[slot]);
+    bulk_load(dst + kBwdTile, Kb + (long)it * kBwdRows * G, bytes, &full_bar[slot]);
+    if (rmw) bulk_load(dst + 2 * kBwdTile, Hb + (long)it * kBwdRows * G, bytes, &full_bar[slot]);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < kBwdStages; ++i) mbar_init(&full_bar[i], 1);
+    fence_mbar_init();
+    for (int i = 0; i < kBwdStages && i < n_iter; ++i) issue_stage(i);
+  }
 
   for (int i = tid; i < NQ * G; i += 256) {
     float g = a.dOut[(long)b * a.dout_stride_b + i];
@@ -175,13 +208,11 @@ __global__ void __launch_bounds__(256, (NQ == 1) ? 2 : 1) attn_bwd_kernel(AttnBw
     }
     (&dO_s[0][0])[i] = g;
     (&Qp_s[0][0])[i] = __ldg(a.Qp + (long)b * a.qp_stride_b + i);
-    (&red_q[0][0])[i] = 0.f;
   }
   for (int i = tid; i < L * 8; i += 256) {
     const int l = i >> 3, q = i & 7;
     P_s[i] = q < NQ ? __ldg(a.P + ((long)b * L + l) * NQ + q) : 0.f;
   }
-  if (tid < G) red_b[tid] = 0.f;
   if (tid < 8) delta_s[tid] = 0.f;
   __syncthreads();
   for (int q = warp; q < NQ; q += 8) {
@@ -209,41 +240,26 @@ __global__ void __launch_bounds__(256, (NQ == 1) ? 2 : 1) attn_bwd_kernel(AttnBw
   const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
   const float my_delta = delta_s[own];
 
-  // each warp owns rows {warp*RB + i*8*RB + r}; loads of the next pair are in flight while a pair computes
-  uint4 nx[RB], nk[RB], nh[RB];
-#pragma unroll
-  for (int r = 0; r < RB; ++r) {
-    nx[r] = make_uint4(0, 0, 0, 0); nk[r] = nx[r]; nh[r] = nx[r];
-    const int l = warp * RB + r;
-    if (l < L) {
-      const long row = (long)b * L + l;
-      nx[r] = __ldg(reinterpret_cast<const uint4*>(a.X + row * a.ldx + g0));
-      nk[r] = __ldg(reinterpret_cast<const uint4*>(a.Kt + row * a.ldk + g0));
-      if (a.dh_mode == 1) nh[r] = *reinterpret_cast<const uint4*>(a.dH + row * a.lddh + g0);
-    }
-  }
-  for (int l0 = warp * RB; l0 < L; l0 += 8 * RB) {
+  for (int it = 0; it < n_iter; ++it) {
+    const int slot = it % kBwdStages;
+    mbar_wait(&full_bar[slot], (uint32_t)((it / kBwdStages) & 1));
+    const unsigned char* st = ring + slot * 3 * kBwdTile;
+    const int l0 = it * kBwdRows + warp * RB;
     float x[RB][8], k[RB][8];
     uint4 oldh[RB];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      unpack8(nx[r], x[r]);
-      unpack8(nk[r], k[r]);
-      oldh[r] = nh[r];
-      const int ln = l0 + 8 * RB + r;
-      if (ln < L) {
-        const long rown = (long)b * L + ln;
-        nx[r] = __ldg(reinterpret_cast<const uint4*>(a.X + rown * a.ldx + g0));
-        nk[r] = __ldg(reinterpret_cast<const uint4*>(a.Kt + rown * a.ldk + g0));
-        if (a.dh_mode == 1) nh[r] = *reinterpret_cast<const uint4*>(a.dH + rown * a.lddh + g0);
-      }
+      const int lr = warp * RB + r;   // row inside the stage (rows past L hold stale data; their stores are skipped)
+      unpack8(*reinterpret_cast<const uint4*>(st + (lr * G + g0) * 2), x[r]);
+      unpack8(*reinterpret_cast<const uint4*>(st + kBwdTile + (lr * G + g0) * 2), k[r]);
+      oldh[r] = *reinterpret_cast<const uint4*>(st + 2 * kBwdTile + (lr * G + g0) * 2);
     }
     // partial dot products of this lane's 8 columns, for both rows
     float dS[RB][NQ];
     float Pv[RB][8];
 #pragma unroll
     for (int r = 0; r < RB; ++r) {
-      const int l = min(l0 + r, L - 1);   // a missing second row recomputes the last row; its stores are skipped
+      const int l = min(l0 + r, L - 1);
       const float4 p0 = *reinterpret_cast<const float4*>(&P_s[l * 8]);
       const float4 p1 = *reinterpret_cast<const float4*>(&P_s[l * 8 + 4]);
       Pv[r][0] = p0.x; Pv[r][1] = p0.y; Pv[r][2] = p0.z; Pv[r][3] = p0.w;
@@ -319,7 +335,7 @@ __global__ void __launch_bounds__(256, (NQ == 1) ? 2 : 1) attn_bwd_kernel(AttnBw
         dZ[j] = dK[r][j] * (1.f - k[r][j] * k[r][j]);
         db_acc[j] += dZ[j];
       }
-      *reinterpret_cast<uint4*>(a.dZ + row * a.lddz + g0) = pack8(dZ);
+      *reinterpret_cast<uint4*>(a.dZ + row * G + g0) = pack8(dZ);
       if (a.fmask_site) {
         const U4 wm = frame_mask_words(key, a.fmask_site, (uint32_t)row, (uint32_t)(g0 >> 7));
         const int wsel = (g0 >> 5) & 3;
@@ -327,42 +343,62 @@ __global__ void __launch_bounds__(256, (NQ == 1) ? 2 : 1) attn_bwd_kernel(AttnBw
 #pragma unroll
         for (int j = 0; j < 8; ++j) dXv[r][j] = ((bits >> j) & 1u) ? 2.f * dXv[r][j] : 0.f;
       }
-      if (a.dh_mode == 1) {
+      if (rmw) {
         float old[8];
         unpack8(oldh[r], old);
 #pragma unroll
         for (int j = 0; j < 8; ++j) dXv[r][j] += old[j];
       }
-      *reinterpret_cast<uint4*>(a.dH + row * a.lddh + g0) = pack8(dXv[r]);
+      *reinterpret_cast<uint4*>(a.dH + row * G + g0) = pack8(dXv[r]);
     }
+    // every warp is done with this slot: refill it with the stage kStages ahead
+    __syncthreads();
+    if (tid == 0 && it + kBwdStages < n_iter) issue_stage(it + kBwdStages);
   }
 
+  // per-warp partials -> shared memory, summed without atomics
 #pragma unroll
-  for (int q = 0; q < NQ; ++q)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&red_q[q][g0 + j], dq_acc[q][j]);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&red_b[g0 + j], db_acc[j]);
+  for (int q = 0; q < NQ; ++q) {
+    float* dst = part + (warp * NQ + q) * G + g0;
+    *reinterpret_cast<float4*>(dst) = make_float4(dq_acc[q][0], dq_acc[q][1], dq_acc[q][2], dq_acc[q][3]);
+    *reinterpret_cast<float4*>(dst + 4) = make_float4(dq_acc[q][4], dq_acc[q][5], dq_acc[q][6], dq_acc[q][7]);
+  }
+  *reinterpret_cast<float4*>(&red_b[warp][g0]) = make_float4(db_acc[0], db_acc[1], db_acc[2], db_acc[3]);
+  *reinterpret_cast<float4*>(&red_b[warp][g0 + 4]) = make_float4(db_acc[4], db_acc[5], db_acc[6], db_acc[7]);
   __syncthreads();
   for (int i = tid; i < NQ * G; i += 256) {
-    const float val = (&red_q[0][0])[i];
+    float val = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) val += part[w * NQ * G + i];
     if (a.qp_stride_b == 0) atomicAdd(a.dQp + i, val);            // shared context vector: sum over the batch
     else a.dQp[(long)b * a.dqp_stride_b + i] = val;
   }
-  if (tid < G) atomicAdd(a.db + tid, red_b[tid]);
+  if (tid < G) {
+    float sdb = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sdb += red_b[w][tid];
+    atomicAdd(a.db + tid, sdb);
+  }
+}
+
+static size_t attn_bwd_smem(int L, int nq) {
+  return (size_t)kBwdStages * 3 * kBwdTile + (size_t)((L * 8 + 3) & ~3) * 4 + (size_t)8 * nq * G * 4;
 }
 
 int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.X && a.Kt && a.P && a.dOut && a.O_pre && a.Qp && a.dZ && a.dH && a.dQp && a.db,
                   "attn_bwd: null pointer");
   SDUMC_CHECK_ARG(a.B > 0 && a.L > 0 && (a.nq == 1 || a.nq == 7), "attn_bwd: bad shape");
-  SDUMC_CHECK_ARG(a.ldx % 8 == 0 && a.ldk % 8 == 0 && a.lddz % 8 == 0 && a.lddh % 8 == 0, "attn_bwd: ld %% 8");
-  const size_t smem = (size_t)a.L * 8 * sizeof(float);
-  SDUMC_CHECK_ARG(smem <= 160 * 1024, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
+  SDUMC_CHECK_ARG(a.ldx == G && a.ldk == G && a.lddz == G && a.lddh == G,
+                  "attn_bwd: frame tensors must be dense [B*L,256] (bulk-copy staging)");
+  SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.X) | reinterpret_cast<uintptr_t>(a.Kt) | reinterpret_cast<uintptr_t>(a.dH) |
+                    reinterpret_cast<uintptr_t>(a.dZ)) & 15u) == 0, "attn_bwd: frame tensors must be 16-byte aligned");
+  const size_t smem = attn_bwd_smem(a.L, a.nq);
+  SDUMC_CHECK_ARG(smem <= 220 * 1024, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
   static bool attr_done = false;
   if (!attr_done) {
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_done = true;
   }
   if (a.nq == 1) attn_bwd_kernel<1><<<a.B, 256, smem, stream>>>(a);
