@@ -394,11 +394,13 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.X) | reinterpret_cast<uintptr_t>(a.Kt) | reinterpret_cast<uintptr_t>(a.dH) |
                     reinterpret_cast<uintptr_t>(a.dZ)) & 15u) == 0, "attn_bwd: frame tensors must be 16-byte aligned");
   const size_t smem = attn_bwd_smem(a.L, a.nq);
-  SDUMC_CHECK_ARG(smem <= 220 * 1024, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
+  // dynamic + static shared memory must stay under 227 KB (static: 10 KB for nq = 1, 23 KB for nq = 7)
+  constexpr size_t kMaxDyn = 200 * 1024;
+  SDUMC_CHECK_ARG(smem <= kMaxDyn, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
   static bool attr_done = false;
   if (!attr_done) {
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
     attr_done = true;
   }
   if (a.nq == 1) attn_bwd_kernel<1><<<a.B, 256, smem, stream>>>(a);
