@@ -146,243 +146,308 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
 //   dZ_l = (sum_q dS_lq Qp_q) * (1 - K_l^2)          -> bf16, feeds the two tcgen05 GEMMs
 //   dQp_q = sum_l dS_lq K_l;  db_in = sum_l dZ_l
 //   dH_l (+)= (sum_q P_lq dO_q) * M_in                (value path; the GEMM adds dZ W_in)
-// One CTA per sample, one warp per frame row, a lane owns 8 of the 256 columns.  dO and Qp slices live in
-// registers (no shared-memory traffic in the row loop), the sample's probabilities in shared memory, the
-// next row's X'/K/dH loads are in flight while a row computes, and the NQ per-row dot products are
-// reduced with a halving butterfly (9 shuffles + NQ broadcasts instead of 5 * NQ).
-// ------------------------------------------------------------------------------------------
-// One CTA per sample.  The sample's X', K (and dH when accumulating) rows are contiguous in memory, so they
-// are streamed through a kStages-deep shared-memory ring of 16-row stages filled by 1-D bulk copies
-// (cp.async.bulk + mbarrier): the bytes in flight (~100 KB per SM) no longer depend on registers.
-// A stage is consumed by all 8 warps, two rows each; a lane owns 8 of the 256 columns.
-constexpr int kBwdStages = 4;
-constexpr int kBwdRows = 16;                       // rows per stage
-constexpr int kBwdTile = kBwdRows * G * 2;         // bytes of one bf16 [16,256] tile
+// The four products with the NQ (<= 8) queries are skinny matrix products (one side 8 wide), ~7K MACs per
+// frame row: far too many for fp32 SIMT at HBM speed and >90% padding for a tcgen05 tile, so they run on
+// the warp-level tensor-core path (mma.sync m16n8k16 / m16n8k8, bf16 in, fp32 accumulate) with the
+// queries padded to 8:
+//   dP  [16 rows x 8 q]    = X'[16 x 256] * dO^T          A: ldmatrix from the X' tile
+//   dQp^T [256 x 8 q]     += K^T[256 x 16 rows] * dS      A: ldmatrix.trans from the K tile, B: movmatrix(dS)
+//   dK  [16 x 256]         = dS[16 x 8] * Qp              A: the dP accumulator fragment, reused as operand
+//   dXv [16 x 256]         = P [16 x 8] * dO
+// One CTA (8 warps) per sample; a stage is 64 frame rows of X' and K, brought into a 2-deep shared-memory
+// ring by per-row bulk copies (rows padded to 528 B so ldmatrix is conflict-free).  Warp w works on rows
+// 16*(w&3).. of the stage and on column half (w>>2) of every product; the only exchange inside a warp
+// pair is the 16x8 partial dP (each half reduces over its own 128 columns).
+// dZ and the value-path gradient are written back into the tiles in place and leave through bulk
+// stores; the "+= old dH" of the accumulate mode is a bulk reduce-add performed at L2, so the old
+// gradient is never read by the SM.
+constexpr int kBwdStages = 2;
+constexpr int kBwdRows = 64;                       // rows per stage (16 per warp)
+constexpr int kBwdPitch = G + 8;                   // bf16 elements per padded shared-memory row (528 B)
+constexpr int kBwdTile = kBwdRows * kBwdPitch * 2; // bytes of one padded bf16 [64,256] tile
+constexpr int kBwdThreads = 256;
 
 template <int NQ>
-__global__ void __launch_bounds__(256, 1) attn_bwd_kernel(AttnBwdArgs a) {
-  constexpr int RB = 2;  // rows per warp per stage (independent dependency chains -> ILP)
+__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a) {
   extern __shared__ __align__(128) unsigned char dyn[];
-  // layout: ring [kStages][3 tiles: X', K, dH_old] | P_s [L][8] | part [8 warps][NQ][G]
+  // layout: ring [2 stages][X' tile, K tile] | dO_b [8][264] | dOT [256][8] | QpT [256][8] | dqp_s [8][256] f32 | P_s [L][8] f32
   unsigned char* ring = dyn;
-  float* P_s = reinterpret_cast<float*>(dyn + kBwdStages * 3 * kBwdTile);
-  float* part = P_s + ((a.L * 8 + 3) & ~3);
-  __shared__ float dO_s[NQ][G];
-  __shared__ float Qp_s[NQ][G];
-  __shared__ float red_b[8][G];
+  __nv_bfloat16* dO_b = reinterpret_cast<__nv_bfloat16*>(dyn + kBwdStages * 2 * kBwdTile);
+  __nv_bfloat16* dOT = dO_b + 8 * kBwdPitch;
+  __nv_bfloat16* QpT = dOT + G * 8;
+  float* dqp_s = reinterpret_cast<float*>(QpT + G * 8);
+  float* P_s = dqp_s + 8 * G;
   __shared__ float delta_s[8];
   __shared__ __align__(8) uint64_t full_bar[kBwdStages];
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int gid = lane >> 2, tq = lane & 3;           // fragment coordinates: row group / column pair
+  const int rw = warp & 3, hc = (warp >> 2) * (G / 2); // row slab of the stage / first column of this warp's half
+  __shared__ float4 dp_x[kBwdThreads];                // partial dP exchange inside a warp pair
   const int L = a.L;
   const int n_iter = (L + kBwdRows - 1) / kBwdRows;
   const bool rmw = a.dh_mode == 1;
   const uint32_t thr = drop_threshold(a.out_drop_p);
   const float oscale = a.out_drop_p > 0.f ? 1.f / (1.f - a.out_drop_p) : 1.f;
   const DropKey key = resolve_key(a.key);
-  const __nv_bfloat16* Xb = a.X + (long)b * L * G;    // host guarantees ldx == ldk == lddh == 256
+  const __nv_bfloat16* Xb = a.X + (long)b * L * G;    // host guarantees ldx == ldk == lddz == lddh == 256
   const __nv_bfloat16* Kb = a.Kt + (long)b * L * G;
-  const __nv_bfloat16* Hb = a.dH + (long)b * L * G;
+  __nv_bfloat16* Zb = a.dZ + (long)b * L * G;
+  __nv_bfloat16* Hb = a.dH + (long)b * L * G;
 
-  auto issue_stage = [&](int it) {                    // thread 0 only
+  auto issue_stage = [&](int it) {                    // threads 0..63: one row of X' and of K each
     const int slot = it % kBwdStages;
     const int rows = min(kBwdRows, L - it * kBwdRows);
-    const uint32_t bytes = (uint32_t)rows * G * 2;
-    unsigned char* dst = ring + slot * 3 * kBwdTile;
-    mbar_expect_tx(&full_bar[slot], bytes * (rmw ? 3u : 2u));
-    bulk_load(dst, Xb + (long)it * kBwdRows * G, bytes, &full_bar[slot]);
-    bulk_load(dst + kBwdTile, Kb + (long)it * kBwdRows * G, bytes, &full_bar[slot]);
-    if (rmw) bulk_load(dst + 2 * kBwdTile, Hb + (long)it * kBwdRows * G, bytes, &full_bar[slot]);
+    unsigned char* dst = ring + slot * 2 * kBwdTile;
+    if (tid == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2 * 2);
+    if (tid < rows) {
+      const long src = ((long)it * kBwdRows + tid) * G;
+      bulk_load(dst + tid * kBwdPitch * 2, Xb + src, G * 2, &full_bar[slot]);
+      bulk_load(dst + kBwdTile + tid * kBwdPitch * 2, Kb + src, G * 2, &full_bar[slot]);
+    }
   };
   if (tid == 0) {
     for (int i = 0; i < kBwdStages; ++i) mbar_init(&full_bar[i], 1);
     fence_mbar_init();
-    for (int i = 0; i < kBwdStages && i < n_iter; ++i) issue_stage(i);
   }
+  __syncthreads();
+  for (int i = 0; i < kBwdStages && i < n_iter; ++i) issue_stage(i);
 
-  for (int i = tid; i < NQ * G; i += 256) {
-    float g = a.dOut[(long)b * a.dout_stride_b + i];
-    if (a.out_drop_p > 0.f) {
-      const uint32_t e = (uint32_t)b * (uint32_t)(NQ * G) + (uint32_t)i;
-      g = elem_rand(key, a.out_site, e) >= thr ? g * oscale : 0.f;
+  // per-sample constants: masked dO (bf16, both layouts), Qp^T (bf16), probabilities, delta.
+  // All global loads of a batch are issued before the first use: with one CTA per SM this prologue is pure
+  // latency, and a load-use-load-use loop costs one DRAM round trip per iteration.
+  constexpr int kV4 = NQ * G / 4;                     // float4 groups of dO / Qp / O_pre
+  constexpr int kPer = (kV4 + kBwdThreads - 1) / kBwdThreads;
+  float dpart[kPer];                                  // this thread's partial <O_pre, dO> per group (one query each)
+  {
+    const float4* dOg = reinterpret_cast<const float4*>(a.dOut + (long)b * a.dout_stride_b);
+    const float4* Qg = reinterpret_cast<const float4*>(a.Qp + (long)b * a.qp_stride_b);
+    const float4* Og = reinterpret_cast<const float4*>(a.O_pre + (long)b * NQ * G);
+    float4 dv[kPer], qv[kPer], ov[kPer];
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = tid + j * kBwdThreads;
+      if (i < kV4) { dv[j] = __ldg(dOg + i); qv[j] = __ldg(Qg + i); ov[j] = __ldg(Og + i); }
+      else { dv[j] = qv[j] = ov[j] = make_float4(0.f, 0.f, 0.f, 0.f); }
     }
-    (&dO_s[0][0])[i] = g;
-    (&Qp_s[0][0])[i] = __ldg(a.Qp + (long)b * a.qp_stride_b + i);
+    // probabilities: [L, NQ] contiguous per sample -> P_s [L][8]
+    const float* Pg = a.P + (long)b * L * NQ;
+    for (int i0 = 0; i0 < L * NQ; i0 += 8 * kBwdThreads) {
+      float pv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const int i = i0 + j * kBwdThreads + tid; pv[j] = i < L * NQ ? __ldg(Pg + i) : 0.f; }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * kBwdThreads + tid;
+        if (i < L * NQ) P_s[(i / NQ) * 8 + (i % NQ)] = pv[j];
+      }
+    }
+    if (NQ < 8) for (int i = tid; i < L * (8 - NQ); i += kBwdThreads) P_s[(i / (8 - NQ)) * 8 + NQ + i % (8 - NQ)] = 0.f;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) {
+      const int i = tid + j * kBwdThreads;
+      dpart[j] = 0.f;
+      if (i < kV4) {
+        const int q = (i * 4) >> 8, g = (i * 4) & (G - 1);
+        float d[4] = {dv[j].x, dv[j].y, dv[j].z, dv[j].w};
+        if (a.out_drop_p > 0.f) {
+          // four consecutive elements share one Philox counter (elem_rand: counter e >> 2, word e & 3)
+          const uint32_t e = (uint32_t)b * (uint32_t)(NQ * G) + (uint32_t)(i * 4);
+          const U4 r = philox4x32_10(e >> 2, 0x5D0Cu, a.out_site, key.step, key.seed_lo, key.seed_hi);
+          d[0] = r.x >= thr ? d[0] * oscale : 0.f; d[1] = r.y >= thr ? d[1] * oscale : 0.f;
+          d[2] = r.z >= thr ? d[2] * oscale : 0.f; d[3] = r.w >= thr ? d[3] * oscale : 0.f;
+        }
+        const float qq[4] = {qv[j].x, qv[j].y, qv[j].z, qv[j].w};
+        const float oo[4] = {ov[j].x, ov[j].y, ov[j].z, ov[j].w};
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const __nv_bfloat16 dvb = __float2bfloat16(d[c]);
+          dO_b[q * kBwdPitch + g + c] = dvb;
+          dOT[(g + c) * 8 + q] = dvb;
+          QpT[(g + c) * 8 + q] = __float2bfloat16(qq[c]);
+          // delta uses the same bf16-rounded dO as the dP product, so sum_l P_l (dP_l - delta) = 0 holds exactly
+          dpart[j] = fmaf(oo[c], __bfloat162float(dvb), dpart[j]);
+        }
+      }
+    }
   }
-  for (int i = tid; i < L * 8; i += 256) {
-    const int l = i >> 3, q = i & 7;
-    P_s[i] = q < NQ ? __ldg(a.P + ((long)b * L + l) * NQ + q) : 0.f;
+  // zero the padding queries and the dQp staging buffer
+  for (int i = tid; i < (8 - NQ) * G; i += kBwdThreads) {
+    const int q = NQ + i / G, g = i % G;
+    dO_b[q * kBwdPitch + g] = __float2bfloat16(0.f);
+    dOT[g * 8 + q] = __float2bfloat16(0.f);
+    QpT[g * 8 + q] = __float2bfloat16(0.f);
   }
+  for (int i = tid; i < 8 * G; i += kBwdThreads) dqp_s[i] = 0.f;
   if (tid < 8) delta_s[tid] = 0.f;
   __syncthreads();
-  for (int q = warp; q < NQ; q += 8) {
-    float s = 0.f;
-    for (int g = lane; g < G; g += 32) s = fmaf(a.O_pre[(long)b * NQ * G + q * G + g], dO_s[q][g], s);
-    s = warp_sum(s);
-    if (lane == 0) delta_s[q] = s;
+  // a float4 group lies inside one query row (64 groups per query): warp-reduce, then one atomic per warp and query
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = tid + j * kBwdThreads;           // warp-uniform q: 32 consecutive groups never straddle a row of 64
+    const float s = warp_sum(dpart[j]);
+    if (lane == 0 && i < kV4) atomicAdd(&delta_s[(i * 4) >> 8], s);
   }
   __syncthreads();
+  const float dl0 = delta_s[2 * tq], dl1 = delta_s[2 * tq + 1];
 
-  const int g0 = lane * 8;
-  float dO[NQ][8], dq_acc[NQ][8], db_acc[8];
+  float dq_acc[8][4];    // dQp^T fragments: [m-tile of 16 columns][(col gid, q 2tq) (col gid, q 2tq+1) (col gid+8, ...)]
+  float db_acc[16][2];   // column sums of dZ over this thread's rows, per 8-column tile
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    const float4 d0 = *reinterpret_cast<const float4*>(&dO_s[q][g0]);
-    const float4 d1 = *reinterpret_cast<const float4*>(&dO_s[q][g0 + 4]);
-    dO[q][0] = d0.x; dO[q][1] = d0.y; dO[q][2] = d0.z; dO[q][3] = d0.w;
-    dO[q][4] = d1.x; dO[q][5] = d1.y; dO[q][6] = d1.z; dO[q][7] = d1.w;
+  for (int i = 0; i < 8; ++i) { dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f; }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dq_acc[q][j] = 0.f;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) db_acc[j] = 0.f;
-  // which of the (up to 8) per-row sums this lane owns after the butterfly
-  const int own = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-  const float my_delta = delta_s[own];
+  for (int i = 0; i < 16; ++i) { db_acc[i][0] = db_acc[i][1] = 0.f; }
 
   for (int it = 0; it < n_iter; ++it) {
     const int slot = it % kBwdStages;
     mbar_wait(&full_bar[slot], (uint32_t)((it / kBwdStages) & 1));
-    const unsigned char* st = ring + slot * 3 * kBwdTile;
-    const int l0 = it * kBwdRows + warp * RB;
-    float x[RB][8], k[RB][8];
-    uint4 oldh[RB];
-#pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const int lr = warp * RB + r;   // row inside the stage (rows past L hold stale data; their stores are skipped)
-      unpack8(*reinterpret_cast<const uint4*>(st + (lr * G + g0) * 2), x[r]);
-      unpack8(*reinterpret_cast<const uint4*>(st + kBwdTile + (lr * G + g0) * 2), k[r]);
-      oldh[r] = *reinterpret_cast<const uint4*>(st + 2 * kBwdTile + (lr * G + g0) * 2);
+    unsigned char* st = ring + slot * 2 * kBwdTile;
+    __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(st) + rw * 16 * kBwdPitch + hc;            // this warp's 16 rows x 128 columns
+    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(st + kBwdTile) + rw * 16 * kBwdPitch + hc;
+    const int l0 = it * kBwdRows + rw * 16;           // first frame of this warp's slab
+    const int valid = min(16, L - l0);                // may be <= 0 for a trailing warp
+    if (valid < 16) {                                 // rows past L: zero so they add nothing to dQp / db
+      for (int i = lane; i < 16 * (G / 16); i += 32) {
+        const int r = i / (G / 16), c = (i % (G / 16)) * 8;
+        if (r >= valid) {
+          *reinterpret_cast<uint4*>(Xs + r * kBwdPitch + c) = make_uint4(0, 0, 0, 0);
+          *reinterpret_cast<uint4*>(Ks + r * kBwdPitch + c) = make_uint4(0, 0, 0, 0);
+        }
+      }
+      __syncwarp();
     }
-    // partial dot products of this lane's 8 columns, for both rows
-    float dS[RB][NQ];
-    float Pv[RB][8];
+    if (valid > 0) {
+      // (1) dP = X' * dO^T: this warp's 128 columns, then add the partner warp's partial
+      float dP[4] = {0.f, 0.f, 0.f, 0.f};
+      {
+        const __nv_bfloat16* arow = Xs + ((lane & 7) + ((lane >> 3) & 1) * 8) * kBwdPitch + (lane >> 4) * 8;
+        const __nv_bfloat16* brow = dO_b + gid * kBwdPitch + hc + 2 * tq;
 #pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const int l = min(l0 + r, L - 1);
-      const float4 p0 = *reinterpret_cast<const float4*>(&P_s[l * 8]);
-      const float4 p1 = *reinterpret_cast<const float4*>(&P_s[l * 8 + 4]);
-      Pv[r][0] = p0.x; Pv[r][1] = p0.y; Pv[r][2] = p0.z; Pv[r][3] = p0.w;
-      Pv[r][4] = p1.x; Pv[r][5] = p1.y; Pv[r][6] = p1.z; Pv[r][7] = p1.w;
-      float v[8];
+        for (int kk = 0; kk < G / 32; ++kk) {
+          uint32_t af[4];
+          ldsm_x4(af, arow + kk * 16);
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + kk * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + kk * 16 + 8);
+          mma_16816(dP, af, b0, b1);
+        }
+        dp_x[tid] = make_float4(dP[0], dP[1], dP[2], dP[3]);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + rw) : "memory");
+        const float4 o = dp_x[tid ^ 128];
+        dP[0] += o.x; dP[1] += o.y; dP[2] += o.z; dP[3] += o.w;
+      }
+      // (2) dS = alpha * P * (dP - delta) on the accumulator layout: rows gid / gid+8, queries 2tq / 2tq+1
+      const bool v0 = gid < valid, v1 = gid + 8 < valid;
+      const float2 p0 = v0 ? *reinterpret_cast<const float2*>(&P_s[(l0 + gid) * 8 + 2 * tq]) : make_float2(0.f, 0.f);
+      const float2 p1 = v1 ? *reinterpret_cast<const float2*>(&P_s[(l0 + gid + 8) * 8 + 2 * tq]) : make_float2(0.f, 0.f);
+      const uint32_t dS_lo = pack2(v0 ? a.alpha * p0.x * (dP[0] - dl0) : 0.f, v0 ? a.alpha * p0.y * (dP[1] - dl1) : 0.f);
+      const uint32_t dS_hi = pack2(v1 ? a.alpha * p1.x * (dP[2] - dl0) : 0.f, v1 ? a.alpha * p1.y * (dP[3] - dl1) : 0.f);
+      const uint32_t P_lo = pack2(p0.x, p0.y), P_hi = pack2(p1.x, p1.y);
+      // (4) dQp^T += K^T * dS  (before the K tile is overwritten by dZ)
+      {
+        const uint32_t bt0 = movmatrix_trans(dS_lo), bt1 = movmatrix_trans(dS_hi);
+        const __nv_bfloat16* arow = Ks + ((lane & 7) + (lane >> 4) * 8) * kBwdPitch + ((lane >> 3) & 1) * 8;
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        if (q < NQ) {
-          float s = x[r][0] * dO[q][0];
-#pragma unroll
-          for (int j = 1; j < 8; ++j) s = fmaf(x[r][j], dO[q][j], s);
-          v[q] = s;
-        } else {
-          v[q] = 0.f;
+        for (int mt = 0; mt < 8; ++mt) {
+          uint32_t af[4];
+          ldsm_x4_trans(af, arow + mt * 16);
+          mma_16816(dq_acc[mt], af, bt0, bt1);
         }
       }
-      if (NQ == 1) {
-        const float dP = warp_sum(v[0]);
-        dS[r][0] = a.alpha * Pv[r][0] * (dP - delta_s[0]);
-      } else {
-        // halving butterfly: after 4+2+1+2 shuffles lane `own` holds the full sum of index `own`
-        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
-        float w[4], u[2];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float keep = b4 ? v[4 + i] : v[i], send = b4 ? v[i] : v[4 + i];
-          w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          const float keep = b3 ? w[2 + i] : w[i], send = b3 ? w[i] : w[2 + i];
-          u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-        float t = (b2 ? u[1] : u[0]) + __shfl_xor_sync(0xffffffffu, b2 ? u[0] : u[1], 4);
-        t += __shfl_xor_sync(0xffffffffu, t, 2);
-        t += __shfl_xor_sync(0xffffffffu, t, 1);
-        const float mine = a.alpha * P_s[l * 8 + own] * (t - my_delta);
-#pragma unroll
-        for (int q = 0; q < NQ; ++q)
-          dS[r][q] = __shfl_sync(0xffffffffu, mine, ((q & 4) ? 16 : 0) + ((q & 2) ? 8 : 0) + ((q & 1) ? 4 : 0));
-      }
-    }
-    // dK, value path, dQp: the Qp slice comes from shared memory once per row pair
-    float dK[RB][8], dXv[RB][8];
-#pragma unroll
-    for (int r = 0; r < RB; ++r)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { dK[r][j] = 0.f; dXv[r][j] = 0.f; }
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float4 q0 = *reinterpret_cast<const float4*>(&Qp_s[q][g0]);
-      const float4 q1 = *reinterpret_cast<const float4*>(&Qp_s[q][g0 + 4]);
-      const float qq[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-      for (int r = 0; r < RB; ++r) {
-        const bool live = (l0 + r) < L;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          dK[r][j] = fmaf(dS[r][q], qq[j], dK[r][j]);
-          dXv[r][j] = fmaf(Pv[r][q], dO[q][j], dXv[r][j]);
-          if (live) dq_acc[q][j] = fmaf(dS[r][q], k[r][j], dq_acc[q][j]);
-        }
-      }
-    }
-#pragma unroll
-    for (int r = 0; r < RB; ++r) {
-      const int l = l0 + r;
-      if (l >= L) break;
-      const long row = (long)b * L + l;
-      float dZ[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dZ[j] = dK[r][j] * (1.f - k[r][j] * k[r][j]);
-        db_acc[j] += dZ[j];
-      }
-      *reinterpret_cast<uint4*>(a.dZ + row * G + g0) = pack8(dZ);
+      // frame-mask words of this thread's two rows (this warp's 128-column half)
+      U4 ma, mb;
       if (a.fmask_site) {
-        const U4 wm = frame_mask_words(key, a.fmask_site, (uint32_t)row, (uint32_t)(g0 >> 7));
-        const int wsel = (g0 >> 5) & 3;
-        const uint32_t bits = (wsel == 0 ? wm.x : (wsel == 1 ? wm.y : (wsel == 2 ? wm.z : wm.w))) >> (g0 & 31);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dXv[r][j] = ((bits >> j) & 1u) ? 2.f * dXv[r][j] : 0.f;
+        const uint32_t r0 = (uint32_t)((long)b * L + l0 + gid);
+        ma = frame_mask_words(key, a.fmask_site, r0, (uint32_t)(warp >> 2));
+        mb = frame_mask_words(key, a.fmask_site, r0 + 8, (uint32_t)(warp >> 2));
       }
-      if (rmw) {
-        float old[8];
-        unpack8(oldh[r], old);
+      // (3) dK = dS * Qp, dXv = P * dO, eight columns at a time; dZ and the masked dXv replace K and X' in place
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dXv[r][j] += old[j];
+      for (int nt = 0; nt < 16; ++nt) {
+        const int col = nt * 8 + 2 * tq;               // relative to this warp's half
+        const uint32_t bq = *reinterpret_cast<const uint32_t*>(QpT + (hc + nt * 8 + gid) * 8 + 2 * tq);
+        const uint32_t bo = *reinterpret_cast<const uint32_t*>(dOT + (hc + nt * 8 + gid) * 8 + 2 * tq);
+        float dK[4], dX[4];
+        mma_1688(dK, dS_lo, dS_hi, bq);
+        mma_1688(dX, P_lo, P_hi, bo);
+        uint32_t* k0p = reinterpret_cast<uint32_t*>(Ks + gid * kBwdPitch + col);
+        uint32_t* k1p = reinterpret_cast<uint32_t*>(Ks + (gid + 8) * kBwdPitch + col);
+        const uint32_t kv0 = *k0p, kv1 = *k1p;
+        const float k00 = __uint_as_float(kv0 << 16), k01 = __uint_as_float(kv0 & 0xffff0000u);
+        const float k10 = __uint_as_float(kv1 << 16), k11 = __uint_as_float(kv1 & 0xffff0000u);
+        const float z00 = dK[0] * (1.f - k00 * k00), z01 = dK[1] * (1.f - k01 * k01);
+        const float z10 = dK[2] * (1.f - k10 * k10), z11 = dK[3] * (1.f - k11 * k11);
+        db_acc[nt][0] += z00 + z10;
+        db_acc[nt][1] += z01 + z11;
+        *k0p = pack2(z00, z01);
+        *k1p = pack2(z10, z11);
+        if (a.fmask_site) {
+          const int w = (nt >> 2) & 3;
+          const uint32_t wa = (w == 0 ? ma.x : (w == 1 ? ma.y : (w == 2 ? ma.z : ma.w))) >> ((nt & 3) * 8 + 2 * tq);
+          const uint32_t wb = (w == 0 ? mb.x : (w == 1 ? mb.y : (w == 2 ? mb.z : mb.w))) >> ((nt & 3) * 8 + 2 * tq);
+          dX[0] = (wa & 1u) ? 2.f * dX[0] : 0.f; dX[1] = (wa & 2u) ? 2.f * dX[1] : 0.f;
+          dX[2] = (wb & 1u) ? 2.f * dX[2] : 0.f; dX[3] = (wb & 2u) ? 2.f * dX[3] : 0.f;
+        }
+        *reinterpret_cast<uint32_t*>(Xs + gid * kBwdPitch + col) = pack2(dX[0], dX[1]);
+        *reinterpret_cast<uint32_t*>(Xs + (gid + 8) * kBwdPitch + col) = pack2(dX[2], dX[3]);
       }
-      *reinterpret_cast<uint4*>(a.dH + row * G + g0) = pack8(dXv[r]);
+      // tiles -> global: one bulk store per row and tensor, issued by the lane that owns the row
+      fence_proxy_async();
+      __syncwarp();
+      if (lane < valid) {
+        const long dst = (long)(l0 + lane) * G + hc;
+        bulk_store(Zb + dst, Ks + lane * kBwdPitch, G);
+        if (rmw) bulk_reduce_add_bf16(Hb + dst, Xs + lane * kBwdPitch, G);
+        else     bulk_store(Hb + dst, Xs + lane * kBwdPitch, G);
+      }
+      bulk_commit();
+      bulk_wait_read();
     }
-    // every warp is done with this slot: refill it with the stage kStages ahead
+    // every warp's stores have read this slot: refill it with the stage two ahead
     __syncthreads();
-    if (tid == 0 && it + kBwdStages < n_iter) issue_stage(it + kBwdStages);
+    if (it + kBwdStages < n_iter) issue_stage(it + kBwdStages);
   }
 
-  // per-warp partials -> shared memory, summed without atomics
+  // dQp: fragments of the four warps -> shared memory -> global
 #pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    float* dst = part + (warp * NQ + q) * G + g0;
-    *reinterpret_cast<float4*>(dst) = make_float4(dq_acc[q][0], dq_acc[q][1], dq_acc[q][2], dq_acc[q][3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(dq_acc[q][4], dq_acc[q][5], dq_acc[q][6], dq_acc[q][7]);
+  for (int mt = 0; mt < 8; ++mt) {
+    const int c = hc + mt * 16 + gid, q = 2 * tq;
+    if (q < NQ)     { atomicAdd(&dqp_s[q * G + c], dq_acc[mt][0]);       atomicAdd(&dqp_s[q * G + c + 8], dq_acc[mt][2]); }
+    if (q + 1 < NQ) { atomicAdd(&dqp_s[(q + 1) * G + c], dq_acc[mt][1]); atomicAdd(&dqp_s[(q + 1) * G + c + 8], dq_acc[mt][3]); }
   }
-  *reinterpret_cast<float4*>(&red_b[warp][g0]) = make_float4(db_acc[0], db_acc[1], db_acc[2], db_acc[3]);
-  *reinterpret_cast<float4*>(&red_b[warp][g0 + 4]) = make_float4(db_acc[4], db_acc[5], db_acc[6], db_acc[7]);
+  // db: reduce over the 8 row groups of the warp, then over the warps through shared memory
+#pragma unroll
+  for (int nt = 0; nt < 16; ++nt) {
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float v = db_acc[nt][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      db_acc[nt][j] = v;
+    }
+  }
+  __shared__ float db_s[G];
+  for (int i = tid; i < G; i += kBwdThreads) db_s[i] = 0.f;
   __syncthreads();
-  for (int i = tid; i < NQ * G; i += 256) {
-    float val = 0.f;
+  if (gid == 0) {
 #pragma unroll
-    for (int w = 0; w < 8; ++w) val += part[w * NQ * G + i];
-    if (a.qp_stride_b == 0) atomicAdd(a.dQp + i, val);            // shared context vector: sum over the batch
-    else a.dQp[(long)b * a.dqp_stride_b + i] = val;
+    for (int nt = 0; nt < 16; ++nt) {
+      atomicAdd(&db_s[hc + nt * 8 + 2 * tq], db_acc[nt][0]);
+      atomicAdd(&db_s[hc + nt * 8 + 2 * tq + 1], db_acc[nt][1]);
+    }
   }
-  if (tid < G) {
-    float sdb = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) sdb += red_b[w][tid];
-    atomicAdd(a.db + tid, sdb);
+  __syncthreads();
+  for (int i = tid; i < NQ * G; i += kBwdThreads) {
+    if (a.qp_stride_b == 0) atomicAdd(a.dQp + i, dqp_s[i]);            // shared context vector: sum over the batch
+    else a.dQp[(long)b * a.dqp_stride_b + i] = dqp_s[i];
   }
+  for (int i = tid; i < G; i += kBwdThreads) atomicAdd(a.db + i, db_s[i]);
+  bulk_wait_all();
 }
 
-static size_t attn_bwd_smem(int L, int nq) {
-  return (size_t)kBwdStages * 3 * kBwdTile + (size_t)((L * 8 + 3) & ~3) * 4 + (size_t)8 * nq * G * 4;
+static size_t attn_bwd_smem(int L) {
+  return (size_t)kBwdStages * 2 * kBwdTile + (size_t)8 * kBwdPitch * 2 + (size_t)2 * G * 8 * 2 + (size_t)8 * G * 4 +
+         (size_t)L * 8 * 4;
 }
 
 int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
@@ -393,9 +458,11 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
                   "attn_bwd: frame tensors must be dense [B*L,256] (bulk-copy staging)");
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.X) | reinterpret_cast<uintptr_t>(a.Kt) | reinterpret_cast<uintptr_t>(a.dH) |
                     reinterpret_cast<uintptr_t>(a.dZ)) & 15u) == 0, "attn_bwd: frame tensors must be 16-byte aligned");
-  const size_t smem = attn_bwd_smem(a.L, a.nq);
-  // dynamic + static shared memory must stay under 227 KB (static: 10 KB for nq = 1, 23 KB for nq = 7)
-  constexpr size_t kMaxDyn = 200 * 1024;
+  SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.dOut) | reinterpret_cast<uintptr_t>(a.Qp) | reinterpret_cast<uintptr_t>(a.O_pre)) & 15u) == 0 &&
+                  a.dout_stride_b % 4 == 0 && a.qp_stride_b % 4 == 0,
+                  "attn_bwd: dOut / Qp / O_pre must be 16-byte aligned with strides that are multiples of 4");
+  const size_t smem = attn_bwd_smem(a.L);
+  constexpr size_t kMaxDyn = 220 * 1024;   // + ~1.1 KB static stays under the 227 KB per-CTA limit
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
   static bool attr_done = false;
   if (!attr_done) {
@@ -403,8 +470,8 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
     SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
     attr_done = true;
   }
-  if (a.nq == 1) attn_bwd_kernel<1><<<a.B, 256, smem, stream>>>(a);
-  else           attn_bwd_kernel<7><<<a.B, 256, smem, stream>>>(a);
+  if (a.nq == 1) attn_bwd_kernel<1><<<a.B, kBwdThreads, smem, stream>>>(a);
+  else           attn_bwd_kernel<7><<<a.B, kBwdThreads, smem, stream>>>(a);
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
