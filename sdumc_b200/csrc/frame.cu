@@ -180,7 +180,10 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   __shared__ float delta_s[8];
   __shared__ __align__(8) uint64_t full_bar[kBwdStages];
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // the broadcast makes the warp index provably warp-uniform, so bulk-copy addresses derived from it live in
+  // uniform registers (no per-lane serialisation loop around UBLKCP)
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int gid = lane >> 2, tq = lane & 3;           // fragment coordinates: row group / column pair
   const int rw = warp & 3, hc = (warp >> 2) * (G / 2); // row slab of the stage / first column of this warp's half
   __shared__ float4 dp_x[kBwdThreads];                // partial dP exchange inside a warp pair
@@ -195,15 +198,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   __nv_bfloat16* Zb = a.dZ + (long)b * L * G;
   __nv_bfloat16* Hb = a.dH + (long)b * L * G;
 
-  auto issue_stage = [&](int it) {                    // threads 0..63: one row of X' and of K each
+  auto issue_stage = [&](int it) {                    // lane 0 of warp w: rows 8w..8w+7 of X' and of K
     const int slot = it % kBwdStages;
     const int rows = min(kBwdRows, L - it * kBwdRows);
     unsigned char* dst = ring + slot * 2 * kBwdTile;
-    if (tid == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2 * 2);
-    if (tid < rows) {
-      const long src = ((long)it * kBwdRows + tid) * G;
-      bulk_load(dst + tid * kBwdPitch * 2, Xb + src, G * 2, &full_bar[slot]);
-      bulk_load(dst + kBwdTile + tid * kBwdPitch * 2, Kb + src, G * 2, &full_bar[slot]);
+    if (lane == 0) {
+      if (warp == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2 * 2);
+      const int r1 = min(rows, warp * 8 + 8);
+      for (int r = warp * 8; r < r1; ++r) {
+        const long src = ((long)it * kBwdRows + r) * G;
+        bulk_load(dst + r * kBwdPitch * 2, Xb + src, G * 2, &full_bar[slot]);
+        bulk_load(dst + kBwdTile + r * kBwdPitch * 2, Kb + src, G * 2, &full_bar[slot]);
+      }
     }
   };
   if (tid == 0) {
@@ -393,11 +399,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       // tiles -> global: one bulk store per row and tensor, issued by the lane that owns the row
       fence_proxy_async();
       __syncwarp();
-      if (lane < valid) {
-        const long dst = (long)(l0 + lane) * G + hc;
-        bulk_store(Zb + dst, Ks + lane * kBwdPitch, G);
-        if (rmw) bulk_reduce_add_bf16(Hb + dst, Xs + lane * kBwdPitch, G);
-        else     bulk_store(Hb + dst, Xs + lane * kBwdPitch, G);
+      if (lane == 0) {
+        for (int r = 0; r < valid; ++r) {
+          const long dst = (long)(l0 + r) * G + hc;
+          bulk_store(Zb + dst, Ks + r * kBwdPitch, G);
+          if (rmw) bulk_reduce_add_bf16(Hb + dst, Xs + r * kBwdPitch, G);
+          else     bulk_store(Hb + dst, Xs + r * kBwdPitch, G);
+        }
       }
       bulk_commit();
       bulk_wait_read();
