@@ -305,6 +305,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int r0 = m_blk * 128 + ew * 32;  // first row of this warp's slab
       const int r = r0 + lane;
       const bool row_ok = r < sh.M;
+      const bool f32_vec = ((reinterpret_cast<uintptr_t>(ep.out_f32) | (uintptr_t)(ep.ld_f32 * 4)) & 15u) == 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * kBlockN);
 
       float sc[7] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -494,9 +495,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (ep.out_f32 && row_ok) {
           float* dst = ep.out_f32 + (long)r * ep.ld_f32 + n0;
           if (ep.f32_mode == OUT_ATOMIC) {
+            if (full && f32_vec) {
+              // split-K reduction: 16-byte vector reds (REDG.F32x4), a quarter of the L2 atomic operations
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (full || n0 + j < sh.N) atomicAdd(dst + j, v[j]);
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(v[j]), "f"(v[j + 1]),
+                             "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (full || n0 + j < sh.N) atomicAdd(dst + j, v[j]);
+            }
           } else if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
