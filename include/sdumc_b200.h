@@ -111,7 +111,7 @@ int sdumc_elem_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t n, floa
 typedef struct sdumc_pool_fwd_args {
   const SDUMC_BF16* X; /* X' [B*L,256] dropped frames, row pitch ldx */
   int64_t ldx;
-  float* S;            /* [B*L,nq] in: scores, out: attention probabilities */
+  float* S;            /* [B*L,nq] in: scores (unless Kt is set), out: attention probabilities */
   int32_t B, L, nq;
   float alpha;         /* softmax_scale = 0.3 */
   float* O_pre;        /* [B,nq,256] pooled output before the output dropout */
@@ -121,6 +121,10 @@ typedef struct sdumc_pool_fwd_args {
   float drop_p;
   uint32_t site;
   sdumc_dropkey key;
+  const SDUMC_BF16* Kt; /* optional tanh keys [B*L,256]: when set, the scores S = Kt Qp^T are computed here */
+  int64_t ldk;
+  const float* Qp;      /* with Kt: projected queries [B,nq,256] (qp_stride_b = nq*256) or shared context (0) */
+  int64_t qp_stride_b;
 } sdumc_pool_fwd_args;
 int sdumc_pool_fwd(const sdumc_pool_fwd_args* a, void* stream);
 

@@ -29,86 +29,200 @@ __device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
 }
 
 // ------------------------------------------------------------------------------------------
-// forward: P = softmax_L(alpha * S);  O = P^T X';  out = dropout(O)
+// forward: S = K Qp^T (optional);  P = softmax_L(alpha * S);  O = P^T X';  out = dropout(O)
+//
+// One CTA (8 warps) per sample.  The sample's K rows (when the scores are computed here) and then its X'
+// rows stream through a 2-deep ring of 64-row stages (per-row bulk copies into 528-byte padded rows).
+// Both products have one side only NQ (<= 8) wide, so they run on the warp-level tensor-core path with
+// the queries padded to 8 - the same fragments as attn_bwd:
+//   S   [16 rows x 8 q]   = K[16 x 256] * Qp^T         (per warp: its 128-column half, summed in the pair)
+//   O^T [256 x 8 q]      += X'^T[256 x 16 rows] * P    A: ldmatrix.trans of the X' tile, B: movmatrix(P)
+// When Kt is NULL the scores are taken from S (written by the key-projection GEMM epilogue, the
+// inference path that never materialises K).  P is written back to S for the backward pass.
 // ------------------------------------------------------------------------------------------
+constexpr int kFwdStages = 2;
+constexpr int kFwdRows = 64;
+constexpr int kFwdPitch = G + 8;
+constexpr int kFwdTile = kFwdRows * kFwdPitch * 2;
+constexpr int kFwdThreads = 256;
+
 template <int NQ>
-__global__ void __launch_bounds__(256) pool_fwd_kernel(PoolFwdArgs a) {
-  extern __shared__ float sm[];
-  float* Ps = sm;                                   // [L][NQ]
-  float* red = sm + ((a.L * NQ + 3) & ~3);          // [8 warps][NQ][G], 16-byte aligned
+__global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a) {
+  extern __shared__ __align__(128) unsigned char dyn[];
+  // layout: ring [2][tile] | QpB hi, lo [2][8][264] bf16 | o_s [8][256] f32 | S_s [L][8] f32
+  // (queries and probabilities enter the tensor-core products as bf16 hi + lo pairs: ~16 mantissa bits for
+  //  twice the - negligible - mma work; the frame operands K and X' are bf16 in memory anyway)
+  unsigned char* ring = dyn;
+  __nv_bfloat16* QpB = reinterpret_cast<__nv_bfloat16*>(dyn + kFwdStages * kFwdTile);
+  __nv_bfloat16* QpL = QpB + 8 * kFwdPitch;
+  float* o_s = reinterpret_cast<float*>(QpL + 8 * kFwdPitch);
+  float* S_s = o_s + 8 * G;
+  __shared__ float4 sp_x[kFwdThreads];
+  __shared__ __align__(8) uint64_t full_bar[kFwdStages];
   const int b = blockIdx.x;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (uniform-register bulk copies)
+  const int gid = lane >> 2, tq = lane & 3;
+  const int rw = warp & 3, hc = (warp >> 2) * (G / 2);
   const int L = a.L;
+  const int n_iter = (L + kFwdRows - 1) / kFwdRows;
+  const bool has_k = a.Kt != nullptr;
+  const int n_total = has_k ? 2 * n_iter : n_iter;
   const DropKey key = resolve_key(a.key);
+  const __nv_bfloat16* Xb = a.X + (long)b * L * G;          // host guarantees dense [B*L,256]
+  const __nv_bfloat16* Kb = has_k ? a.Kt + (long)b * L * G : nullptr;
   float* Sg = a.S + (long)b * L * NQ;
 
-  for (int i = tid; i < L * NQ; i += 256) Ps[i] = Sg[i];
-  __syncthreads();
-  for (int q = warp; q < NQ; q += 8) {
-    float m = -INFINITY;
-    for (int l = lane; l < L; l += 32) m = fmaxf(m, Ps[l * NQ + q]);
-    m = warp_max(m);
-    float s = 0.f;
-    for (int l = lane; l < L; l += 32) {
-      const float e = __expf(a.alpha * (Ps[l * NQ + q] - m));
-      Ps[l * NQ + q] = e;
-      s += e;
+  auto issue_stage = [&](int j) {                           // lane 0 of warp w: rows 8w..8w+7
+    const int slot = j % kFwdStages;
+    const bool kphase = has_k && j < n_iter;
+    const int it = kphase ? j : j - (has_k ? n_iter : 0);
+    const int rows = min(kFwdRows, L - it * kFwdRows);
+    const __nv_bfloat16* src = (kphase ? Kb : Xb) + (long)it * kFwdRows * G;
+    unsigned char* dst = ring + slot * kFwdTile;
+    if (lane == 0) {
+      if (warp == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2);
+      const int r1 = min(rows, warp * 8 + 8);
+      for (int r = warp * 8; r < r1; ++r) bulk_load(dst + r * kFwdPitch * 2, src + (long)r * G, G * 2, &full_bar[slot]);
     }
-    s = warp_sum(s);
-    const float inv = 1.f / s;
-    for (int l = lane; l < L; l += 32) Ps[l * NQ + q] *= inv;
+  };
+  if (tid == 0) {
+    for (int i = 0; i < kFwdStages; ++i) mbar_init(&full_bar[i], 1);
+    fence_mbar_init();
   }
   __syncthreads();
-  for (int i = tid; i < L * NQ; i += 256) Sg[i] = Ps[i];
+  for (int i = 0; i < kFwdStages && i < n_total; ++i) issue_stage(i);
 
-  float acc[NQ][8];
+  // prologue: queries -> bf16 [8][264] (padding queries zero), output staging buffer, and - when the scores
+  // are an input - the scores themselves
+  if (has_k) {
+    constexpr int kV4 = NQ * G / 4;
+    const float4* Qg = reinterpret_cast<const float4*>(a.Qp + (long)b * a.qp_stride_b);
+    for (int i = tid; i < 8 * G / 4; i += kFwdThreads) {
+      const float4 v = i < kV4 ? __ldg(Qg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int q = (i * 4) >> 8, g = (i * 4) & (G - 1);
+      const uint32_t h0 = pack2(v.x, v.y), h1 = pack2(v.z, v.w);
+      *reinterpret_cast<uint2*>(QpB + q * kFwdPitch + g) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(QpL + q * kFwdPitch + g) =
+          make_uint2(pack2(v.x - __uint_as_float(h0 << 16), v.y - __uint_as_float(h0 & 0xffff0000u)),
+                     pack2(v.z - __uint_as_float(h1 << 16), v.w - __uint_as_float(h1 & 0xffff0000u)));
+    }
+  } else {
+    for (int i0 = 0; i0 < L * NQ; i0 += 8 * kFwdThreads) {
+      float sv[8];
 #pragma unroll
-  for (int q = 0; q < NQ; ++q)
+      for (int j = 0; j < 8; ++j) { const int i = i0 + j * kFwdThreads + tid; sv[j] = i < L * NQ ? Sg[i] : 0.f; }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
-  const __nv_bfloat16* Xb = a.X + (long)b * L * a.ldx + lane * 8;
-  int l = warp;
-  for (; l + 24 < L; l += 32) {  // 4 rows in flight per warp
-    uint4 v[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(Xb + (long)(l + 8 * u) * a.ldx));
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      float x[8];
-      unpack8(v[u], x);
-#pragma unroll
-      for (int q = 0; q < NQ; ++q) {
-        const float p = Ps[(l + 8 * u) * NQ + q];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(p, x[j], acc[q][j]);
+      for (int j = 0; j < 8; ++j) {
+        const int i = i0 + j * kFwdThreads + tid;
+        if (i < L * NQ) S_s[(i / NQ) * 8 + (i % NQ)] = sv[j];
       }
     }
   }
-  for (; l < L; l += 8) {
-    float x[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(Xb + (long)l * a.ldx)), x);
-#pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-      const float p = Ps[l * NQ + q];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(p, x[j], acc[q][j]);
-    }
-  }
-  // per-warp partials -> shared memory [8][NQ][G], summed by the writer loop below (no atomics)
-#pragma unroll
-  for (int q = 0; q < NQ; ++q) {
-    float* dst = red + (warp * NQ + q) * G + lane * 8;
-    *reinterpret_cast<float4*>(dst) = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[q][4], acc[q][5], acc[q][6], acc[q][7]);
-  }
+  for (int i = tid; i < 8 * G; i += kFwdThreads) o_s[i] = 0.f;
   __syncthreads();
 
+  float acc[8][4];       // O^T fragments: [m-tile of 16 columns][(col gid, q 2tq) (col gid, q 2tq+1) (col gid+8, ...)]
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f; }
+
+  for (int j = 0; j < n_total; ++j) {
+    const int slot = j % kFwdStages;
+    const bool kphase = has_k && j < n_iter;
+    const int it = kphase ? j : j - (has_k ? n_iter : 0);
+    if (!kphase && it == 0) {
+      // ---- softmax over the L frames, one warp per query; P -> S_s (padding queries: 0) and -> global ----
+      // (every score of the sample is in S_s: the K phase ended with a __syncthreads, or the prologue did)
+      for (int q = warp; q < 8; q += kFwdThreads / 32) {
+        if (q < NQ) {
+          float m = -INFINITY;
+          for (int l = lane; l < L; l += 32) m = fmaxf(m, S_s[l * 8 + q]);
+          m = warp_max(m);
+          float ssum = 0.f;
+          for (int l = lane; l < L; l += 32) {
+            const float e = __expf(a.alpha * (S_s[l * 8 + q] - m));
+            S_s[l * 8 + q] = e;
+            ssum += e;
+          }
+          ssum = warp_sum(ssum);
+          const float inv = 1.f / ssum;
+          for (int l = lane; l < L; l += 32) S_s[l * 8 + q] *= inv;
+        } else {
+          for (int l = lane; l < L; l += 32) S_s[l * 8 + q] = 0.f;
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < L * NQ; i += kFwdThreads) Sg[i] = S_s[(i / NQ) * 8 + (i % NQ)];
+    }
+    mbar_wait(&full_bar[slot], (uint32_t)((j / kFwdStages) & 1));
+    __nv_bfloat16* Ts = reinterpret_cast<__nv_bfloat16*>(ring + slot * kFwdTile) + rw * 16 * kFwdPitch + hc;
+    const int l0 = it * kFwdRows + rw * 16;
+    const int valid = min(16, L - l0);
+    if (valid > 0) {
+      if (kphase) {
+        // scores of this warp's 16 rows: partial over its 128 columns, then add the partner warp's half
+        float sc[4] = {0.f, 0.f, 0.f, 0.f};
+        const __nv_bfloat16* arow = Ts + ((lane & 7) + ((lane >> 3) & 1) * 8) * kFwdPitch + (lane >> 4) * 8;
+        const __nv_bfloat16* brow = QpB + gid * kFwdPitch + hc + 2 * tq;
+#pragma unroll
+        for (int kk = 0; kk < G / 32; ++kk) {
+          uint32_t af[4];
+          ldsm_x4(af, arow + kk * 16);
+          const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + kk * 16);
+          const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + kk * 16 + 8);
+          mma_16816(sc, af, b0, b1);
+          const uint32_t c0 = *reinterpret_cast<const uint32_t*>(brow + 8 * kFwdPitch + kk * 16);
+          const uint32_t c1 = *reinterpret_cast<const uint32_t*>(brow + 8 * kFwdPitch + kk * 16 + 8);
+          mma_16816(sc, af, c0, c1);
+        }
+        sp_x[tid] = make_float4(sc[0], sc[1], sc[2], sc[3]);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + rw) : "memory");
+        const float4 o = sp_x[tid ^ 128];
+        // the lower-half warp writes rows gid, its partner rows gid+8 (rows past L hold garbage: skipped)
+        if (hc == 0) { if (gid < valid) *reinterpret_cast<float2*>(&S_s[(l0 + gid) * 8 + 2 * tq]) = make_float2(sc[0] + o.x, sc[1] + o.y); }
+        else if (gid + 8 < valid) *reinterpret_cast<float2*>(&S_s[(l0 + gid + 8) * 8 + 2 * tq]) = make_float2(sc[2] + o.z, sc[3] + o.w);
+      } else {
+        if (valid < 16) {                             // rows past L: zero so 0 * garbage cannot produce NaN
+          for (int i = lane; i < 16 * (G / 16); i += 32) {
+            const int r = i / (G / 16), c = (i % (G / 16)) * 8;
+            if (r >= valid) *reinterpret_cast<uint4*>(Ts + r * kFwdPitch + c) = make_uint4(0, 0, 0, 0);
+          }
+          __syncwarp();
+        }
+        const bool v0 = gid < valid, v1 = gid + 8 < valid;
+        const float2 p0 = v0 ? *reinterpret_cast<const float2*>(&S_s[(l0 + gid) * 8 + 2 * tq]) : make_float2(0.f, 0.f);
+        const float2 p1 = v1 ? *reinterpret_cast<const float2*>(&S_s[(l0 + gid + 8) * 8 + 2 * tq]) : make_float2(0.f, 0.f);
+        const uint32_t h0 = pack2(p0.x, p0.y), h1 = pack2(p1.x, p1.y);
+        const uint32_t l0p = pack2(p0.x - __uint_as_float(h0 << 16), p0.y - __uint_as_float(h0 & 0xffff0000u));
+        const uint32_t l1p = pack2(p1.x - __uint_as_float(h1 << 16), p1.y - __uint_as_float(h1 & 0xffff0000u));
+        const uint32_t bt0 = movmatrix_trans(h0), bt1 = movmatrix_trans(h1);
+        const uint32_t bl0 = movmatrix_trans(l0p), bl1 = movmatrix_trans(l1p);
+        const __nv_bfloat16* arow = Ts + ((lane & 7) + (lane >> 4) * 8) * kFwdPitch + ((lane >> 3) & 1) * 8;
+#pragma unroll
+        for (int mt = 0; mt < 8; ++mt) {
+          uint32_t af[4];
+          ldsm_x4_trans(af, arow + mt * 16);
+          mma_16816(acc[mt], af, bt0, bt1);
+          mma_16816(acc[mt], af, bl0, bl1);
+        }
+      }
+    }
+    __syncthreads();                                  // slot consumed by every warp (and S_s complete after the K phase)
+    if (j + kFwdStages < n_total) issue_stage(j + kFwdStages);
+  }
+
+  // O: fragments of the four row-slab warps -> shared memory -> global (+ output dropout)
+#pragma unroll
+  for (int mt = 0; mt < 8; ++mt) {
+    const int c = hc + mt * 16 + gid, q = 2 * tq;
+    if (q < NQ)     { atomicAdd(&o_s[q * G + c], acc[mt][0]);       atomicAdd(&o_s[q * G + c + 8], acc[mt][2]); }
+    if (q + 1 < NQ) { atomicAdd(&o_s[(q + 1) * G + c], acc[mt][1]); atomicAdd(&o_s[(q + 1) * G + c + 8], acc[mt][3]); }
+  }
+  __syncthreads();
   const uint32_t thr = drop_threshold(a.drop_p);
   const float scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
-  for (int i = tid; i < NQ * G; i += 256) {
-    float o = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) o += red[w * NQ * G + i];
+  for (int i = tid; i < NQ * G; i += kFwdThreads) {
+    const float o = o_s[i];
     a.O_pre[(long)b * NQ * G + i] = o;
     float y = o;
     if (a.drop_p > 0.f) {
@@ -123,18 +237,25 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolFwdArgs a) {
 int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.X && a.S && a.O_pre && a.out, "pool_fwd: null pointer");
   SDUMC_CHECK_ARG(a.B > 0 && a.L > 0 && (a.nq == 1 || a.nq == 7), "pool_fwd: bad shape B=%d L=%d nq=%d", a.B, a.L, a.nq);
-  SDUMC_CHECK_ARG(a.ldx % 8 == 0 && (reinterpret_cast<uintptr_t>(a.X) & 15u) == 0, "pool_fwd: X must be 16-byte aligned");
-  const size_t smem = (size_t)(((a.L * a.nq + 3) & ~3) + 8 * a.nq * G) * sizeof(float);
-  SDUMC_CHECK_ARG(smem <= 200 * 1024, "pool_fwd: L=%d too long for the shared-memory softmax", a.L);
-  if (a.nq == 1) {
-    static bool done1 = false;
-    if (!done1) { SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done1 = true; }
-    pool_fwd_kernel<1><<<a.B, 256, smem, stream>>>(a);
-  } else {
-    static bool done7 = false;
-    if (!done7) { SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); done7 = true; }
-    pool_fwd_kernel<7><<<a.B, 256, smem, stream>>>(a);
+  SDUMC_CHECK_ARG(a.ldx == G && (reinterpret_cast<uintptr_t>(a.X) & 15u) == 0,
+                  "pool_fwd: X must be dense [B*L,256] and 16-byte aligned (bulk-copy staging)");
+  if (a.Kt) {
+    SDUMC_CHECK_ARG(a.ldk == G && (reinterpret_cast<uintptr_t>(a.Kt) & 15u) == 0,
+                    "pool_fwd: Kt must be dense [B*L,256] and 16-byte aligned");
+    SDUMC_CHECK_ARG(a.Qp && (reinterpret_cast<uintptr_t>(a.Qp) & 15u) == 0 && a.qp_stride_b % 4 == 0,
+                    "pool_fwd: Qp is required with Kt (16-byte aligned, stride a multiple of 4)");
   }
+  const size_t smem = (size_t)kFwdStages * kFwdTile + (size_t)2 * 8 * kFwdPitch * 2 + (size_t)8 * G * 4 + (size_t)a.L * 8 * 4;
+  constexpr size_t kMaxDyn = 216 * 1024;
+  SDUMC_CHECK_ARG(smem <= kMaxDyn, "pool_fwd: L=%d too long for the shared-memory softmax", a.L);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    attr_done = true;
+  }
+  if (a.nq == 1) pool_fwd_kernel<1><<<a.B, kFwdThreads, smem, stream>>>(a);
+  else           pool_fwd_kernel<7><<<a.B, kFwdThreads, smem, stream>>>(a);
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

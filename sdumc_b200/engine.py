@@ -237,12 +237,17 @@ class Engine:
             S = st.t[f"Sf.{p}.{m}"]
             Kt = st.t[f"Kf.{p}.{m}"] if keep else None
             pre = f"fra2utt_{m}"
-            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                     act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt,
-                     qv=W.f32(pre + ".attention_context_vector"), q_stride=0, nq=1, L=L, scores=S)
+            ctx = W.f32(pre + ".attention_context_vector")
+            if keep:   # training: K is materialised for the backward pass, the scores come from the pooling kernel
+                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                         act=ops.ACT_TANH, out_bf16=Kt)
+            else:      # scoring: K never leaves the GEMM epilogue
+                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                         act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, qv=ctx, q_stride=0, nq=1, L=L, scores=S)
             ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=st.t[f"Of_pre.{p}.{m}"], out=u_pool[m][p * B:(p + 1) * B],
                          out_stride_b=G, out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
-                         site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev)
+                         site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev,
+                         Kt=Kt, Qp=ctx if keep else None, qp_stride_b=0)
         self._parallel(len(units), fra2utt_unit)
 
         # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
@@ -299,13 +304,17 @@ class Engine:
             S = st.t[f"Sc.{p}.{m}"]
             Kt = st.t[f"Kc.{p}.{m}"] if keep else None
             pre = f"cross_att_fra2utt_{m}"
-            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                     act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=Qp[m][p * B * NQ:(p + 1) * B * NQ],
-                     q_stride=NQ * G, nq=NQ, L=L, scores=S)
+            qp = Qp[m][p * B * NQ:(p + 1) * B * NQ]
+            if keep:
+                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                         act=ops.ACT_TANH, out_bf16=Kt)
+            else:
+                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                         act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, qv=qp, q_stride=NQ * G, nq=NQ, L=L, scores=S)
             ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=st.t[f"Oc_pre.{p}.{m}"], out=C[m][p * B * NQ:(p + 1) * B * NQ],
                          out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
                          drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step,
-                         step_dev=cfg.step_dev)
+                         step_dev=cfg.step_dev, Kt=Kt, Qp=qp if keep else None, qp_stride_b=NQ * G)
         self._parallel(len(units), cross_unit)
 
         # 5. utterance chain B

@@ -81,9 +81,12 @@ def colsum_bf16(X: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def pool_fwd(X, S, *, B, L, nq, O_pre, out, out_stride_b, out_bf16=None, drop_p=0.0, site=0, seed=0, step=0,
-             step_dev=None, alpha=0.3) -> None:
+             step_dev=None, alpha=0.3, Kt=None, Qp=None, qp_stride_b=0) -> None:
+    """softmax over frames + pooling; with Kt/Qp the scores are computed in the kernel (S is output only)."""
     a = STRUCTS["sdumc_pool_fwd_args"]()
     a.X, a.ldx, a.S = ptr(X), _ld(X), ptr(S)
+    a.Kt, a.ldk = ptr(Kt), (_ld(Kt) if Kt is not None else 0)
+    a.Qp, a.qp_stride_b = ptr(Qp), qp_stride_b
     a.B, a.L, a.nq, a.alpha = B, L, nq, alpha
     a.O_pre, a.out, a.out_stride_b, a.out_bf16 = ptr(O_pre), ptr(out), out_stride_b, ptr(out_bf16)
     a.drop_p, a.site, a.key = drop_p, site, dropkey(seed, step, step_dev)

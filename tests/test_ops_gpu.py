@@ -20,7 +20,16 @@ def _run(fn, *a, **kw):
 @pytest.mark.parametrize("nq,train,B,L", [(1, False, 5, 70), (7, False, 5, 70), (1, True, 5, 70), (7, True, 5, 70),
                                           (7, True, 3, 300), (7, False, 130, 2), (1, True, 2, 1000)])
 def test_pooling_attention_block_forward_backward(nq, train, B, L):
+    """training path: K from the tanh GEMM, scores + softmax + pooling in pool_fwd, tensor-core backward"""
     res = _run(lambda p: p.attention_block(nq, train, B=B, L=L))
+    (d,) = res.values()
+    assert all(v < BF16_TOL for v in d.values()), d
+
+
+@pytest.mark.parametrize("nq,B,L", [(1, 5, 70), (7, 5, 70), (7, 3, 300), (7, 130, 2), (1, 2, 1000)])
+def test_pooling_attention_block_scoring_path(nq, B, L):
+    """scoring path: the scores come from the key-projection GEMM epilogue (K is never re-read)"""
+    res = _run(lambda p: p.attention_block(nq, False, B=B, L=L, fused_scores=False))
     (d,) = res.values()
     assert all(v < BF16_TOL for v in d.values()), d
 

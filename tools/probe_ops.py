@@ -28,7 +28,9 @@ def report(tag, d):
     print(f"== {tag}: " + "  ".join(f"{k}={v:.2e}" for k, v in d.items()), flush=True)
 
 
-def attention_block(nq, train, B=5, L=70):
+def attention_block(nq, train, B=5, L=70, fused_scores=True):
+    """fused_scores: training path (K from a plain GEMM, scores inside pool_fwd); otherwise the scoring path
+    (scores from the key-projection GEMM epilogue)."""
     torch.manual_seed(1)
     seed, step, site_in, site_out = 77, 3, 11, 12
     H = (torch.randn(B * L, G, device=dev) * 1.5).bfloat16()
@@ -50,12 +52,17 @@ def attention_block(nq, train, B=5, L=70):
         X = H
     S = torch.zeros(B * L, nq, device=dev)
     Kt = torch.zeros(B * L, G, device=dev, dtype=torch.bfloat16)
-    ops.gemm(X, W, M=B * L, N=G, K=G, bias=b, act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=Qp,
-             q_stride=qstride, nq=nq, L=L, scores=S)
     Opre = torch.zeros(B, nq, G, device=dev)
     out = torch.zeros(B, nq, G, device=dev)
-    ops.pool_fwd(X, S, B=B, L=L, nq=nq, O_pre=Opre, out=out, out_stride_b=nq * G, drop_p=0.5 if train else 0.0,
-                 site=site_out, seed=seed, step=step)
+    if fused_scores:
+        ops.gemm(X, W, M=B * L, N=G, K=G, bias=b, act=ops.ACT_TANH, out_bf16=Kt)
+        ops.pool_fwd(X, S, B=B, L=L, nq=nq, O_pre=Opre, out=out, out_stride_b=nq * G, drop_p=0.5 if train else 0.0,
+                     site=site_out, seed=seed, step=step, Kt=Kt, Qp=Qp, qp_stride_b=qstride)
+    else:
+        ops.gemm(X, W, M=B * L, N=G, K=G, bias=b, act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=Qp,
+                 q_stride=qstride, nq=nq, L=L, scores=S)
+        ops.pool_fwd(X, S, B=B, L=L, nq=nq, O_pre=Opre, out=out, out_stride_b=nq * G, drop_p=0.5 if train else 0.0,
+                     site=site_out, seed=seed, step=step)
     Mout = ops.elem_mask(seed, step, site_out, B * nq * G, 0.5).view(B, nq, G) if train else torch.ones_like(out)
     # backward (kernels)
     dZ = torch.zeros(B * L, G, device=dev, dtype=torch.bfloat16)
@@ -82,7 +89,7 @@ def attention_block(nq, train, B=5, L=70):
     Or = Pr.transpose(1, 2) @ Xr
     outr = Or * Mout
     (outr * dOut).sum().backward()
-    report(f"attn nq={nq} train={train}", dict(
+    report(f"attn nq={nq} train={train} fused={fused_scores}", dict(
         K=nerr(Kt.view(B, L, G), Kr), P=nerr(S.view(B, L, nq), Pr), Opre=nerr(Opre, Or), out=nerr(out, outr),
         dH=nerr(dH.view(B, L, G), Hr.grad), dW=nerr(dW, Wr.grad), db=nerr(db, br.grad),
         dQp=nerr(dQp, Qr.grad)))
