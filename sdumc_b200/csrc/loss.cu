@@ -217,7 +217,53 @@ __device__ void block_scan_256(const float* src, double* dst, int n, double* wsu
   __syncthreads();
 }
 
-// One CTA per anchor row.  Shared memory: e[n] (float), aux[n] (float: logits, then 1/D), pre[n] (double).
+// Pairwise feature distances of the anchor rows against all n samples, dist[il*n + j] = |f_i - f_j|_2, as direct
+// differences (the features of the two passes are nearly equal at initialisation: the |a|^2+|b|^2-2ab form
+// would cancel).  64x64 output tile per CTA, 4x4 per thread, feature chunks of 64 through shared memory, so
+// the feature matrix is read n/64 times instead of once per anchor row.
+__global__ void __launch_bounds__(256) rnc_dist_kernel(RncArgs a, float* dist) {
+  __shared__ float Fi[64][65];
+  __shared__ float Fj[64][65];
+  const int n = a.n, D = a.D;
+  const int rows = a.row_end - a.row_begin;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int j0 = blockIdx.x * 64, il0 = blockIdx.y * 64;
+  float acc[4][4] = {};
+  for (int d0 = 0; d0 < D; d0 += 64) {
+    const int dw = min(64, D - d0);
+    for (int x = threadIdx.x; x < 64 * 64; x += 256) {
+      const int r = x >> 6, d = x & 63;
+      const int il = il0 + r, j = j0 + r;
+      Fi[r][d] = (il < rows && d < dw) ? a.feats[(long)(a.row_begin + il) * D + d0 + d] : 0.f;
+      Fj[r][d] = (j < n && d < dw) ? a.feats[(long)j * D + d0 + d] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int d = 0; d < 64; ++d) {
+      float fa[4], fb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { fa[u] = Fi[ty * 4 + u][d]; fb[u] = Fj[tx * 4 + u][d]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) { const float df = fa[u] - fb[v]; acc[u][v] = fmaf(df, df, acc[u][v]); }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int il = il0 + ty * 4 + u;
+    if (il >= rows) continue;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int j = j0 + tx * 4 + v;
+      if (j < n) dist[(long)il * n + j] = sqrtf(acc[u][v]);
+    }
+  }
+}
+
+// One CTA per anchor row.  Shared memory: pre[n] (double), e[n], aux[n] (logits, then 1/D), dist[n] (float).
+// Cmat holds the row's distances on entry (rnc_dist_kernel) and its gradient coefficients on exit.
 __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm, const float* ys, const int* pos,
                                                        float* Cmat) {
   extern __shared__ unsigned char smraw[];
@@ -225,7 +271,7 @@ __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm
   double* pre = reinterpret_cast<double*>(smraw);
   float* e = reinterpret_cast<float*>(pre + n);
   float* aux = e + n;
-  float* fi = aux + n;  // [D]
+  float* dist_s = aux + n;
   __shared__ float red[8];
   __shared__ double wsum[8];
   __shared__ float bcast;
@@ -235,24 +281,18 @@ __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm
   const int pi = pos[i];
   const float yi = a.labels[i];
   const float inv_t = 1.f / a.temperature;
-  for (int d = t; d < D; d += 256) fi[d] = a.feats[(long)i * D + d];
-  __syncthreads();
+  float* crow = Cmat + (long)blockIdx.x * n;
+  (void)D;
 
-  // 1. logits in sorted order, running max
+  // 1. logits in sorted order (the whole distance row moves to shared memory before crow is overwritten), running max
   float mx = -INFINITY;
   for (int s = t; s < n; s += 256) {
     const int j = perm[s];
+    const float ds = crow[j];
+    dist_s[s] = ds;
     float lg = -INFINITY;
     if (j != i) {
-      const float4* fj = reinterpret_cast<const float4*>(a.feats + (long)j * D);
-      float acc = 0.f;
-      for (int d4 = 0; d4 < D / 4; ++d4) {
-        const float4 v = __ldg(fj + d4);
-        const float d0 = fi[4 * d4] - v.x, d1 = fi[4 * d4 + 1] - v.y, d2 = fi[4 * d4 + 2] - v.z,
-                    d3 = fi[4 * d4 + 3] - v.w;
-        acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-      }
-      lg = -sqrtf(acc) * inv_t;
+      lg = -ds * inv_t;
       mx = fmaxf(mx, lg);
     }
     aux[s] = lg;
@@ -313,7 +353,6 @@ __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm
   __syncthreads();
   block_scan_256(aux, pre, n, wsum);  // pre = prefix sums of 1/D_k
   const float cscale = a.grad_scale / ((float)n * (float)(n - 1));
-  float* crow = Cmat + (long)blockIdx.x * n;
   for (int s = t; s < n; s += 256) {
     const int j = perm[s];
     float c = 0.f;
@@ -335,15 +374,7 @@ __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm
       const double Gj = (pre[pi] - (a0 > 0 ? pre[a0 - 1] : 0.0)) + (pre[b1 - 1] - pre[pi]);
       const float dl = cscale * (e[s] * (float)Gj - 1.f);  // d loss / d logit_ij
       // logit = -dist / t  ->  d loss / d dist = -dl / t ; direction (f_i - f_j) / dist
-      const float4* fj = reinterpret_cast<const float4*>(a.feats + (long)j * D);
-      float acc = 0.f;
-      for (int d4 = 0; d4 < D / 4; ++d4) {
-        const float4 v = __ldg(fj + d4);
-        const float d0 = fi[4 * d4] - v.x, d1 = fi[4 * d4 + 1] - v.y, d2 = fi[4 * d4 + 2] - v.z,
-                    d3 = fi[4 * d4 + 3] - v.w;
-        acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
-      }
-      const float dist = sqrtf(acc);
+      const float dist = dist_s[s];
       c = dist > 0.f ? -dl * inv_t / dist : 0.f;
     }
     crow[j] = c;  // coefficient of (f_i - f_j) in d loss/d f_i, and of -(f_i - f_j) in d loss/d f_j
@@ -440,12 +471,14 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
   if (!attr_done) {
     SDUMC_CUDA(cudaFuncSetAttribute(rnc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRncMaxN * 8));
     SDUMC_CUDA(cudaFuncSetAttribute(rnc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kRncMaxN * 16 + 256 * 4));
+                                    kRncMaxN * 20));
     attr_done = true;
   }
   rnc_sort_kernel<<<1, 1024, (size_t)n2 * 8, stream>>>(a.labels, a.n, n2, perm, ys, pos);
   SDUMC_CUDA(cudaGetLastError());
-  const size_t smem = (size_t)a.n * 16 + (size_t)a.D * 4;
+  rnc_dist_kernel<<<dim3((a.n + 63) / 64, (rows + 63) / 64), 256, 0, stream>>>(a, Cmat);
+  SDUMC_CUDA(cudaGetLastError());
+  const size_t smem = (size_t)a.n * 20;
   rnc_row_kernel<<<rows, 256, smem, stream>>>(a, perm, ys, pos, Cmat);
   SDUMC_CUDA(cudaGetLastError());
   if (a.dfeats) {

@@ -237,17 +237,14 @@ class Engine:
             S = st.t[f"Sf.{p}.{m}"]
             Kt = st.t[f"Kf.{p}.{m}"] if keep else None
             pre = f"fra2utt_{m}"
-            ctx = W.f32(pre + ".attention_context_vector")
-            if keep:   # training: K is materialised for the backward pass, the scores come from the pooling kernel
-                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                         act=ops.ACT_TANH, out_bf16=Kt)
-            else:      # scoring: K never leaves the GEMM epilogue
-                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                         act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, qv=ctx, q_stride=0, nq=1, L=L, scores=S)
+            # one query: the score is a single dot product per row, free in the GEMM epilogue (K is stored only
+            # when the backward pass needs it), and the pooling kernel reads X' alone
+            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                     act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt,
+                     qv=W.f32(pre + ".attention_context_vector"), q_stride=0, nq=1, L=L, scores=S)
             ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=st.t[f"Of_pre.{p}.{m}"], out=u_pool[m][p * B:(p + 1) * B],
                          out_stride_b=G, out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
-                         site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev,
-                         Kt=Kt, Qp=ctx if keep else None, qp_stride_b=0)
+                         site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev)
         self._parallel(len(units), fra2utt_unit)
 
         # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
@@ -305,7 +302,8 @@ class Engine:
             Kt = st.t[f"Kc.{p}.{m}"] if keep else None
             pre = f"cross_att_fra2utt_{m}"
             qp = Qp[m][p * B * NQ:(p + 1) * B * NQ]
-            if keep:
+            if keep:   # training: K is materialised for the backward pass; the 7 scores per row come from the
+                       # pooling kernel's tensor-core product instead of 7 x 256 SIMT FMAs in the GEMM epilogue
                 ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
                          act=ops.ACT_TANH, out_bf16=Kt)
             else:
