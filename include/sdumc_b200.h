@@ -149,7 +149,7 @@ typedef struct sdumc_attn_bwd_args {
   int64_t lddh;
   int32_t dh_mode;      /* 0 store, 1 accumulate */
   uint32_t fmask_site;  /* 0: no input dropout */
-  float* dQp;           /* [B,nq,256] stored, or [nq,256] atomicAdd when qp_stride_b == 0 */
+  float* dQp;           /* accumulated with atomicAdd (zero-fill first): [B,nq,256], or [nq,256] when qp_stride_b == 0 */
   int64_t dqp_stride_b;
   float* db;            /* [256] atomicAdd */
   sdumc_dropkey key;

@@ -7,6 +7,7 @@
 // Reference: FRA2UTT_new.forward / Cross_Attention.forward,
 //   toolkit/models/wengnet_mosei_mult_views_text_missing.py:56-68, :79-95 (forward);
 //   the backward formulas are autograd of those lines.
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -300,7 +301,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   float* P_s = dqp_s + 8 * G;
   __shared__ float delta_s[8];
   __shared__ __align__(8) uint64_t full_bar[kBwdStages];
-  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31;
   // the broadcast makes the warp index provably warp-uniform, so bulk-copy addresses derived from it live in
   // uniform registers (no per-lane serialisation loop around UBLKCP)
@@ -314,22 +314,25 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   const uint32_t thr = drop_threshold(a.out_drop_p);
   const float oscale = a.out_drop_p > 0.f ? 1.f / (1.f - a.out_drop_p) : 1.f;
   const DropKey key = resolve_key(a.key);
-  const __nv_bfloat16* Xb = a.X + (long)b * L * G;    // host guarantees ldx == ldk == lddz == lddh == 256
-  const __nv_bfloat16* Kb = a.Kt + (long)b * L * G;
-  __nv_bfloat16* Zb = a.dZ + (long)b * L * G;
-  __nv_bfloat16* Hb = a.dH + (long)b * L * G;
+  // persistent CTAs over (sample, 64-row stage) units: a contiguous, equal share per CTA, so neither the grid
+  // (waves of whole samples) nor the per-sample prologue quantises the work; the ring runs across samples
+  const int n_units = a.B * n_iter;
+  const int u_begin = (int)(((long)n_units * blockIdx.x) / gridDim.x);
+  const int my_units = (int)(((long)n_units * (blockIdx.x + 1)) / gridDim.x) - u_begin;
 
-  auto issue_stage = [&](int it) {                    // lane 0 of warp w: rows 8w..8w+7 of X' and of K
-    const int slot = it % kBwdStages;
+  auto issue_stage = [&](int k) {                     // lane 0 of warp w: rows 8w..8w+7 of X' and of K of unit k
+    const int u = u_begin + k;
+    const int ub = u / n_iter, it = u - ub * n_iter;
+    const int slot = k % kBwdStages;
     const int rows = min(kBwdRows, L - it * kBwdRows);
     unsigned char* dst = ring + slot * 2 * kBwdTile;
     if (lane == 0) {
       if (warp == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2 * 2);
       const int r1 = min(rows, warp * 8 + 8);
       for (int r = warp * 8; r < r1; ++r) {
-        const long src = ((long)it * kBwdRows + r) * G;
-        bulk_load(dst + r * kBwdPitch * 2, Xb + src, G * 2, &full_bar[slot]);
-        bulk_load(dst + kBwdTile + r * kBwdPitch * 2, Kb + src, G * 2, &full_bar[slot]);
+        const long src = (((long)ub * L + (long)it * kBwdRows) + r) * G;   // host guarantees dense [B*L,256] tensors
+        bulk_load(dst + r * kBwdPitch * 2, a.X + src, G * 2, &full_bar[slot]);
+        bulk_load(dst + kBwdTile + r * kBwdPitch * 2, a.Kt + src, G * 2, &full_bar[slot]);
       }
     }
   };
@@ -337,14 +340,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
     for (int i = 0; i < kBwdStages; ++i) mbar_init(&full_bar[i], 1);
     fence_mbar_init();
   }
+  for (int i = tid; i < 8 * G; i += kBwdThreads) dqp_s[i] = 0.f;
   __syncthreads();
-  for (int i = 0; i < kBwdStages && i < n_iter; ++i) issue_stage(i);
+  for (int i = 0; i < kBwdStages && i < my_units; ++i) issue_stage(i);
 
   // per-sample constants: masked dO (bf16, both layouts), Qp^T (bf16), probabilities, delta.
   // All global loads of a batch are issued before the first use: with one CTA per SM this prologue is pure
-  // latency, and a load-use-load-use loop costs one DRAM round trip per iteration.
+  // latency, and a load-use-load-use loop costs one DRAM round trip per iteration.  (The stage ring keeps
+  // loading meanwhile.)  Called by all threads after a __syncthreads.
   constexpr int kV4 = NQ * G / 4;                     // float4 groups of dO / Qp / O_pre
   constexpr int kPer = (kV4 + kBwdThreads - 1) / kBwdThreads;
+  float dl0 = 0.f, dl1 = 0.f;
+  auto load_sample = [&](int b) {
   float dpart[kPer];                                  // this thread's partial <O_pre, dO> per group (one query each)
   {
     const float4* dOg = reinterpret_cast<const float4*>(a.dOut + (long)b * a.dout_stride_b);
@@ -398,14 +405,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       }
     }
   }
-  // zero the padding queries and the dQp staging buffer
+  // zero the padding queries
   for (int i = tid; i < (8 - NQ) * G; i += kBwdThreads) {
     const int q = NQ + i / G, g = i % G;
     dO_b[q * kBwdPitch + g] = __float2bfloat16(0.f);
     dOT[g * 8 + q] = __float2bfloat16(0.f);
     QpT[g * 8 + q] = __float2bfloat16(0.f);
   }
-  for (int i = tid; i < 8 * G; i += kBwdThreads) dqp_s[i] = 0.f;
   if (tid < 8) delta_s[tid] = 0.f;
   __syncthreads();
   // a float4 group lies inside one query row (64 groups per query): warp-reduce, then one atomic per warp and query
@@ -416,7 +422,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
     if (lane == 0 && i < kV4) atomicAdd(&delta_s[(i * 4) >> 8], s);
   }
   __syncthreads();
-  const float dl0 = delta_s[2 * tq], dl1 = delta_s[2 * tq + 1];
+  dl0 = delta_s[2 * tq];
+  dl1 = delta_s[2 * tq + 1];
+  };
 
   float dq_acc[8][4];    // dQp^T fragments: [m-tile of 16 columns][(col gid, q 2tq) (col gid, q 2tq+1) (col gid+8, ...)]
   float db_acc[16][2];   // column sums of dZ over this thread's rows, per 8-column tile
@@ -425,9 +433,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
 #pragma unroll
   for (int i = 0; i < 16; ++i) { db_acc[i][0] = db_acc[i][1] = 0.f; }
 
-  for (int it = 0; it < n_iter; ++it) {
-    const int slot = it % kBwdStages;
-    mbar_wait(&full_bar[slot], (uint32_t)((it / kBwdStages) & 1));
+  // dQp of the finished sample: fragments of the four row-slab warps -> shared memory -> global atomics
+  // (a sample may be shared with the neighbouring CTAs; the host zero-fills dQp)
+  auto flush_dqp = [&](int b) {
+#pragma unroll
+    for (int mt = 0; mt < 8; ++mt) {
+      const int c = hc + mt * 16 + gid, q = 2 * tq;
+      if (q < NQ)     { atomicAdd(&dqp_s[q * G + c], dq_acc[mt][0]);       atomicAdd(&dqp_s[q * G + c + 8], dq_acc[mt][2]); }
+      if (q + 1 < NQ) { atomicAdd(&dqp_s[(q + 1) * G + c], dq_acc[mt][1]); atomicAdd(&dqp_s[(q + 1) * G + c + 8], dq_acc[mt][3]); }
+      dq_acc[mt][0] = dq_acc[mt][1] = dq_acc[mt][2] = dq_acc[mt][3] = 0.f;
+    }
+    __syncthreads();
+    float* dst = a.dQp + (a.qp_stride_b == 0 ? 0 : (long)b * a.dqp_stride_b);
+    for (int i = tid; i < NQ * G; i += kBwdThreads) {
+      atomicAdd(dst + i, dqp_s[i]);
+      dqp_s[i] = 0.f;
+    }
+    __syncthreads();
+  };
+
+  int b = -1;
+  for (int k = 0; k < my_units; ++k) {
+    const int u = u_begin + k;
+    const int ub = u / n_iter, it = u - ub * n_iter;
+    if (ub != b) {                                    // CTA-uniform; the previous unit ended with a __syncthreads
+      if (b >= 0) flush_dqp(b);
+      b = ub;
+      load_sample(b);
+    }
+    __nv_bfloat16* Zb = a.dZ + (long)b * L * G;
+    __nv_bfloat16* Hb = a.dH + (long)b * L * G;
+    const int slot = k % kBwdStages;
+    mbar_wait(&full_bar[slot], (uint32_t)((k / kBwdStages) & 1));
     unsigned char* st = ring + slot * 2 * kBwdTile;
     __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(st) + rw * 16 * kBwdPitch + hc;            // this warp's 16 rows x 128 columns
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(st + kBwdTile) + rw * 16 * kBwdPitch + hc;
@@ -531,18 +568,11 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       bulk_commit();
       bulk_wait_read();
     }
-    // every warp's stores have read this slot: refill it with the stage two ahead
+    // every warp's stores have read this slot: refill it with the unit two ahead
     __syncthreads();
-    if (it + kBwdStages < n_iter) issue_stage(it + kBwdStages);
+    if (k + kBwdStages < my_units) issue_stage(k + kBwdStages);
   }
-
-  // dQp: fragments of the four warps -> shared memory -> global
-#pragma unroll
-  for (int mt = 0; mt < 8; ++mt) {
-    const int c = hc + mt * 16 + gid, q = 2 * tq;
-    if (q < NQ)     { atomicAdd(&dqp_s[q * G + c], dq_acc[mt][0]);       atomicAdd(&dqp_s[q * G + c + 8], dq_acc[mt][2]); }
-    if (q + 1 < NQ) { atomicAdd(&dqp_s[(q + 1) * G + c], dq_acc[mt][1]); atomicAdd(&dqp_s[(q + 1) * G + c + 8], dq_acc[mt][3]); }
-  }
+  if (b >= 0) flush_dqp(b);
   // db: reduce over the 8 row groups of the warp, then over the warps through shared memory
 #pragma unroll
   for (int nt = 0; nt < 16; ++nt) {
@@ -566,10 +596,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
     }
   }
   __syncthreads();
-  for (int i = tid; i < NQ * G; i += kBwdThreads) {
-    if (a.qp_stride_b == 0) atomicAdd(a.dQp + i, dqp_s[i]);            // shared context vector: sum over the batch
-    else a.dQp[(long)b * a.dqp_stride_b + i] = dqp_s[i];
-  }
   for (int i = tid; i < G; i += kBwdThreads) atomicAdd(a.db + i, db_s[i]);
   bulk_wait_all();
 }
@@ -599,8 +625,16 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
     SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
     attr_done = true;
   }
-  if (a.nq == 1) attn_bwd_kernel<1><<<a.B, kBwdThreads, smem, stream>>>(a);
-  else           attn_bwd_kernel<7><<<a.B, kBwdThreads, smem, stream>>>(a);
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    SDUMC_CUDA(cudaGetDevice(&dev));
+    SDUMC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const long n_units = (long)a.B * ((a.L + kBwdRows - 1) / kBwdRows);
+  const int grid = (int)std::min<long>(n_units, num_sms);   // one resident CTA per SM (shared-memory bound)
+  if (a.nq == 1) attn_bwd_kernel<1><<<grid, kBwdThreads, smem, stream>>>(a);
+  else           attn_bwd_kernel<7><<<grid, kBwdThreads, smem, stream>>>(a);
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -420,7 +420,7 @@ class Engine:
             if s_ not in dH:
                 dH[s_] = torch.empty(B * cfg.frames[s_], G, dtype=torch.bfloat16, device=dev)
         started: Dict[str, bool] = {}
-        dQp = [e(R * NQ, G) for _ in range(3)]
+        dQp = [z(R * NQ, G) for _ in range(3)]     # attn_bwd accumulates (a sample may be split over CTAs)
 
         def cross_attn_bwd(m):                     # passes of one modality accumulate into the same dH: in order
             for p in range(NP):
