@@ -198,6 +198,10 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
   long tiles = (long)m_tiles * n_tiles * sh.k_splits;
   int grid = (int)(tiles < sms ? tiles : sms);
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  // resident B: one N tile whose whole K extent fits beside an A-only ring, and at least two tiles per CTA to
+  // amortise it (bit 18 of dbg_sbo disables it for A/B timing)
+  const int stages = block_n == 256 ? 4 : (block_n == 128 ? 6 : 8);
+  sh.b_res = (n_tiles == 1 && sh.k_splits == 1 && nkb <= stages && tiles >= 2L * grid && !((sh.dbg_sbo >> 16) & 4u)) ? 1 : 0;
 
   if (tf32) {
     SDUMC_CHECK_ARG(epi.kind == EPI_GENERIC, "gemm: tf32 operands support the generic epilogue only");

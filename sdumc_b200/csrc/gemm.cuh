@@ -67,6 +67,7 @@ struct GemmShape {
   int M, N, K;
   int a_mn, b_mn;  // 0 = K-major, 1 = MN-major
   int k_splits;
+  int b_res;       // 1: the whole B operand (one N tile, K <= kStages k-blocks) stays resident in shared memory
   // debug overrides of the MN-major descriptor fields (0 = computed); see tests/test_gemm_gpu.py
   uint32_t dbg_lbo, dbg_sbo;
   unsigned long long* dbg_clk;  // bring-up: per-CTA cycle counters of the pipeline phases (nullptr in production)
@@ -151,9 +152,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* bres_bar = tempty_bar + 3;             // resident-B mode: B loaded once per CTA
+  // resident-B mode (frame-level GEMMs with a 256x256 weight): B occupies the first nkb * kBBytes of the stage
+  // area, the ring behind it carries A only.  Without it every 128-row tile re-fetches the weight from L2
+  // (2x the A traffic) and the L2->SM fabric, not HBM, bounds the main loop.
+  const bool b_res = sh.b_res != 0;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (sh.dbg_clk && threadIdx.x == 0) {   // bring-up: CTA start / end wall clock (ns), slots 13 / 14
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    sh.dbg_clk[blockIdx.x * 16 + 13] = t;
+  }
 
   const int m_tiles = (sh.M + 127) / 128;
   const int n_tiles = (sh.N + kBlockN - 1) / kBlockN;
@@ -173,6 +184,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       mbar_init(&tfull_bar[i], 1);
       mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
     }
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
@@ -187,6 +199,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      uint8_t* ring_base = stage_base + (b_res ? nkb * Cfg::kBBytes : 0);
+      const int stage_stride = b_res ? Cfg::kABytes : Cfg::kStageBytes;
+      if (b_res && blockIdx.x < num_tiles) {
+        mbar_expect_tx(bres_bar, (uint32_t)(nkb * Cfg::kBBytes));
+        for (int kb = 0; kb < nkb; ++kb) {
+          uint8_t* sb = stage_base + kb * Cfg::kBBytes;
+          if (!sh.b_mn) {
+            tma_load_2d(sb, &tmB, kb * kBlockK, 0, bres_bar);
+          } else {
+#pragma unroll
+            for (int p = 0; p < kBlockN / kPanel; ++p)
+              tma_load_2d(sb + p * (kBlockK * 128), &tmB, p * kPanel, kb * kBlockK, bres_bar);
+          }
+        }
+      }
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
         const int ks = t / (m_tiles * n_tiles);
         const int mn = t - ks * (m_tiles * n_tiles);
@@ -197,9 +224,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const long long tw0 = sh.dbg_clk ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (sh.dbg_clk) sh.dbg_clk[blockIdx.x * 16 + 0] += clock64() - tw0;   // producer: waiting for a free stage
-          uint8_t* sa = stage_base + stage * Cfg::kStageBytes;
+          uint8_t* sa = ring_base + stage * stage_stride;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          mbar_expect_tx(&full_bar[stage], b_res ? Cfg::kABytes : Cfg::kStageBytes);
           if (!sh.a_mn) {
             tma_load_2d(sa, &tmA, kb * kBlockK, m_blk * 128, &full_bar[stage]);
           } else {
@@ -208,7 +235,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_2d(sa + p * (kBlockK * 128), &tmA, m_blk * 128 + p * kPanel, kb * kBlockK,
                           &full_bar[stage]);
           }
-          if (!sh.b_mn) {
+          if (b_res) {
+            // B is resident
+          } else if (!sh.b_mn) {
             tma_load_2d(sb, &tmB, kb * kBlockK, n_blk * kBlockN, &full_bar[stage]);
           } else {
 #pragma unroll
@@ -234,6 +263,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t ring_u32 = smem_u32(stage_base) + (b_res ? (uint32_t)(nkb * Cfg::kBBytes) : 0u);
+    const uint32_t stage_stride = b_res ? (uint32_t)Cfg::kABytes : (uint32_t)Cfg::kStageBytes;
+    if (b_res && blockIdx.x < num_tiles) mbar_wait(bres_bar, 0u);
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int ks = t / (m_tiles * n_tiles);
       const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
@@ -249,8 +281,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         if (sh.dbg_clk && lane == 0) sh.dbg_clk[blockIdx.x * 16 + 2] += clock64() - tm0;  // MMA: waiting for TMA data
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(stage_base + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint32_t sa = ring_u32 + (uint32_t)stage * stage_stride;
+          const uint32_t sb = b_res ? smem_u32(stage_base) + (uint32_t)(kb * Cfg::kBBytes) : sa + Cfg::kABytes;
           const uint64_t da = make_smem_desc(sa, a_lbo, a_sbo);
           const uint64_t db = make_smem_desc(sb, b_lbo, b_sbo);
 #pragma unroll
@@ -570,6 +602,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+  if (sh.dbg_clk && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    sh.dbg_clk[blockIdx.x * 16 + 14] = t;
   }
 }
 

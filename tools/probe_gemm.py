@@ -167,6 +167,12 @@ def run_case(name: str) -> dict:
         go(clk)
         torch.cuda.synchronize()
         cm = clk.float().mean(0).tolist()
+        t0, t1 = clk[:, 13].double(), clk[:, 14].double()
+        live = t1 > 0
+        if bool(live.any()):
+            res["wall_us"] = {"span": float((t1[live].max() - t0[live].min()) / 1e3),
+                              "cta_mean": float((t1[live] - t0[live]).mean() / 1e3),
+                              "start_skew": float((t0[live].max() - t0[live].min()) / 1e3)}
         res["clk"] = {"prod_wait_empty": cm[0], "mma_wait_tempty": cm[1], "mma_wait_full": cm[2],
                       "epi0_bar": cm[4], "epi0_wait_tfull": cm[5], "epi0_drain": cm[6], "epi0_tiles": cm[7],
                       "epi1_wait_tfull": cm[9], "epi1_drain": cm[10], "epi1_tiles": cm[11]}
