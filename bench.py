@@ -195,17 +195,25 @@ def run_ours(args):
     terms = tr.terms.tolist()
 
     # ---- end to end: pinned host batch -> H2D -> step -> D2H of the loss, every step ----
-    for _ in range(2):
-        tr.load_batch(host["audio"], host["text"], host["video"], host["feat4"], host["vals"])
-        tr.train_step()
-        float(tr.terms[6].item())
+    # The public API double-buffers host batches: stage_batch() starts the H2D copy of the next batch on a copy
+    # stream while the current step runs, commit_staged() makes it current.  Every timed step still pays its own
+    # 1.2 GB H2D copy (n_e2e copies inside the region) and a synchronous D2H read of its loss.
+    hb = (host["audio"], host["text"], host["video"], host["feat4"], host["vals"])
+
+    def e2e_steps(n):
+        tr.stage_batch(*hb)
+        for i in range(n):
+            tr.commit_staged()
+            if i + 1 < n:
+                tr.stage_batch(*hb)
+            tr.train_step()
+            float(tr.terms[6].item())
+
+    e2e_steps(2)
     barrier()
     n_e2e = max(3, min(args.steps, 10))
     e0.record()
-    for _ in range(n_e2e):
-        tr.load_batch(host["audio"], host["text"], host["video"], host["feat4"], host["vals"])
-        tr.train_step()
-        float(tr.terms[6].item())
+    e2e_steps(n_e2e)
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))

@@ -50,14 +50,13 @@ constexpr int kFwdThreads = 256;
 template <int NQ>
 __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a) {
   extern __shared__ __align__(128) unsigned char dyn[];
-  // layout: ring [2][tile] | QpB hi, lo [2][8][264] bf16 | o_s [8][256] f32 | S_s [L][8] f32
+  // layout: ring [2][tile] | QpB hi, lo [2][8][264] bf16 | S_s [L][8] f32
   // (queries and probabilities enter the tensor-core products as bf16 hi + lo pairs: ~16 mantissa bits for
   //  twice the - negligible - mma work; the frame operands K and X' are bf16 in memory anyway)
   unsigned char* ring = dyn;
   __nv_bfloat16* QpB = reinterpret_cast<__nv_bfloat16*>(dyn + kFwdStages * kFwdTile);
   __nv_bfloat16* QpL = QpB + 8 * kFwdPitch;
-  float* o_s = reinterpret_cast<float*>(QpL + 8 * kFwdPitch);
-  float* S_s = o_s + 8 * G;
+  float* S_s = reinterpret_cast<float*>(QpL + 8 * kFwdPitch);
   __shared__ float4 sp_x[kFwdThreads];
   __shared__ __align__(8) uint64_t full_bar[kFwdStages];
   const int b = blockIdx.x;
@@ -120,7 +119,6 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
       }
     }
   }
-  for (int i = tid; i < 8 * G; i += kFwdThreads) o_s[i] = 0.f;
   __syncthreads();
 
   float acc[8][4];       // O^T fragments: [m-tile of 16 columns][(col gid, q 2tq) (col gid, q 2tq+1) (col gid+8, ...)]
@@ -212,18 +210,21 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
     if (j + kFwdStages < n_total) issue_stage(j + kFwdStages);
   }
 
-  // O: fragments of the four row-slab warps -> shared memory -> global (+ output dropout)
+  // O: fragments of the four row-slab warps -> per-slab partials in the (now idle) ring -> summed in a fixed
+  // order (bitwise reproducible, unlike shared-memory atomics) -> global (+ output dropout)
+  float* part = reinterpret_cast<float*>(ring);            // [4 slabs][8 q][256]: 32 KB of the 66 KB ring
 #pragma unroll
   for (int mt = 0; mt < 8; ++mt) {
     const int c = hc + mt * 16 + gid, q = 2 * tq;
-    if (q < NQ)     { atomicAdd(&o_s[q * G + c], acc[mt][0]);       atomicAdd(&o_s[q * G + c + 8], acc[mt][2]); }
-    if (q + 1 < NQ) { atomicAdd(&o_s[(q + 1) * G + c], acc[mt][1]); atomicAdd(&o_s[(q + 1) * G + c + 8], acc[mt][3]); }
+    float* pr = part + rw * 8 * G;
+    pr[q * G + c] = acc[mt][0];       pr[q * G + c + 8] = acc[mt][2];
+    pr[(q + 1) * G + c] = acc[mt][1]; pr[(q + 1) * G + c + 8] = acc[mt][3];
   }
   __syncthreads();
   const uint32_t thr = drop_threshold(a.drop_p);
   const float scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   for (int i = tid; i < NQ * G; i += kFwdThreads) {
-    const float o = o_s[i];
+    const float o = (part[i] + part[8 * G + i]) + (part[2 * 8 * G + i] + part[3 * 8 * G + i]);
     a.O_pre[(long)b * NQ * G + i] = o;
     float y = o;
     if (a.drop_p > 0.f) {
@@ -246,7 +247,7 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
     SDUMC_CHECK_ARG(a.Qp && (reinterpret_cast<uintptr_t>(a.Qp) & 15u) == 0 && a.qp_stride_b % 4 == 0,
                     "pool_fwd: Qp is required with Kt (16-byte aligned, stride a multiple of 4)");
   }
-  const size_t smem = (size_t)kFwdStages * kFwdTile + (size_t)2 * 8 * kFwdPitch * 2 + (size_t)8 * G * 4 + (size_t)a.L * 8 * 4;
+  const size_t smem = (size_t)kFwdStages * kFwdTile + (size_t)2 * 8 * kFwdPitch * 2 + (size_t)a.L * 8 * 4;
   constexpr size_t kMaxDyn = 216 * 1024;
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "pool_fwd: L=%d too long for the shared-memory softmax", a.L);
   static bool attr_done = false;

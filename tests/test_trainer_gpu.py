@@ -1,0 +1,145 @@
+"""GPU parity of the fused train step (sdumc_b200.trainer.Trainer: both passes as one 2B-row batch, 6-term loss,
+backward, Adam, CUDA-graph replay) against the oracle's train_step - the restatement of
+main_frame_val_text_missing.py:120-160 - and of the host-batch staging path."""
+import pytest
+import torch
+
+from oracle import sdumc_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+DIMS, FRAMES, B = (256, 512, 128, 512), (48, 16, 32, 12), 16
+TERMS = ("mse_full", "mse_missing", "rmse_text_hidden", "rmse_cross_text", "rmse_fused", "rnc")
+
+
+def _trainer(P, use_graph, **kw):
+    from sdumc_b200.trainer import Trainer
+    dev = torch.device("cuda", 0)
+    tr = Trainer(DIMS, B, FRAMES, dev, state_dict={k: v.float() for k, v in P.items()}, use_graph=use_graph, **kw)
+    tr.train_dropout = False     # deterministic: comparable with the oracle without re-creating the masks
+    return tr
+
+
+def _load(tr, batch):
+    dev = tr.device
+    tr.load_batch(*(batch[k].bfloat16().to(dev) for k in ("audio", "text", "video", "feat4")), batch["vals"].to(dev))
+
+
+def test_train_steps_follow_the_oracle():
+    """3 optimisation steps (dropout off): every loss term of every step within 1e-2 of the fp64 oracle, and
+    the parameter update after the first step (Adam: lr * sign-like direction) matches in direction."""
+    P = O.init_params(DIMS, seed=100, gain=1.0, dtype=torch.float64)
+    batch = O.synth_batch(B, DIMS, FRAMES, seed=7)
+    b64 = {k: (v.bfloat16().double() if k != "vals" else v.double()) for k, v in batch.items()}
+    tr = _trainer(P, use_graph=False)
+    _load(tr, batch)
+    Pref = {k: v.clone() for k, v in P.items()}
+    state = {}
+    p0 = tr.master.clone()
+    for step in range(3):
+        _, terms, grads, _ = O.train_step(Pref, state, b64["audio"], b64["text"], b64["feat4"], b64["video"],
+                                          b64["vals"], lr=1e-4, weight_decay=1e-5)
+        tr.train_step()
+        torch.cuda.synchronize()
+        got = tr.terms.tolist()
+        for i, name in enumerate(TERMS):
+            ref = float(terms[name])
+            assert abs(got[i] - ref) <= 1e-2 * max(1.0, abs(ref)), (step, name, got[i], ref)
+        if step == 0:
+            # first Adam step moves every live element by ~lr * sign(g): compare the direction on elements whose
+            # oracle gradient is well above the bf16 noise floor of its tensor
+            agree = total = 0
+            for name, g in grads.items():
+                if g is None:
+                    continue
+                d_ref = (Pref[name] - P[name]).flatten()
+                d_got = (tr.layout.view(tr.master, name) - tr.layout.view(p0, name)).double().cpu().flatten()
+                big = g.flatten().abs() > 0.05 * g.abs().max()
+                agree += int((torch.sign(d_ref[big]) == torch.sign(d_got[big])).sum())
+                total += int(big.sum())
+            assert total > 1000 and agree / total > 0.995, (agree, total)
+
+
+def test_graph_replay_equals_eager():
+    """The captured CUDA graph (steps 3+) reproduces the eager step: same loss terms and parameters up to the
+    non-deterministic order of the split-K / bias atomics."""
+    P = O.init_params(DIMS, seed=100, gain=1.0, dtype=torch.float64)
+    batch = O.synth_batch(B, DIMS, FRAMES, seed=7)
+    runs = []
+    for use_graph in (False, True):
+        tr = _trainer(P, use_graph=use_graph)
+        _load(tr, batch)
+        hist = []
+        for _ in range(5):
+            tr.train_step()
+            torch.cuda.synchronize()
+            hist.append(tr.terms.clone())
+        runs.append((torch.stack(hist), tr.master.clone(), tr))
+    assert runs[1][2]._graph is not None, "graph path was not taken"
+    assert torch.allclose(runs[0][0], runs[1][0], rtol=2e-3, atol=2e-4), (runs[0][0], runs[1][0])
+    # parameters: 5 steps of lr 1e-4 -> identical up to a few flipped low-gradient elements
+    diff = (runs[0][1] - runs[1][1]).abs()
+    assert float(diff.max()) <= 1.01e-3 and float(diff.mean()) < 5e-5, (float(diff.max()), float(diff.mean()))
+
+
+def test_dropout_steps_are_reproducible_and_step_dependent():
+    """Train-mode dropout is a pure function of (seed, step, site): two trainers agree step by step, and the
+    masks change from one step to the next (the same batch gives different losses)."""
+    P = O.init_params(DIMS, seed=100, gain=1.0, dtype=torch.float64)
+    batch = O.synth_batch(B, DIMS, FRAMES, seed=7)
+    hists = []
+    for _ in range(2):
+        tr = _trainer(P, use_graph=True)
+        tr.train_dropout = True
+        _load(tr, batch)
+        h = []
+        for _ in range(4):
+            tr.train_step()
+            torch.cuda.synchronize()
+            h.append(tr.terms.clone())
+        hists.append(torch.stack(h))
+    # step 1 depends on the (bitwise reproducible) forward alone; later steps see parameters that went through
+    # the atomics of the backward pass, and the RMSE terms amplify those last-bit differences
+    assert torch.allclose(hists[0][0], hists[1][0], rtol=1e-5, atol=1e-6), (hists[0][0], hists[1][0])
+    assert torch.allclose(hists[0], hists[1], rtol=2e-2, atol=2e-3)
+    assert float((hists[0][2] - hists[0][3]).abs().max()) > 1e-4
+
+
+def test_staged_host_batches_equal_direct_load():
+    """stage_batch()/commit_staged() (pinned host -> staging -> static buffers on a copy stream) feeds the step the
+    same bytes as load_batch(), also for a batch with fewer utterances and frames than the trainer's capacity."""
+    P = O.init_params(DIMS, seed=100, gain=1.0, dtype=torch.float64)
+    tr = _trainer(P, use_graph=False)
+    for (b, frames, seed) in ((B, FRAMES, 7), (B - 5, (40, 9, 32, 7), 8)):
+        batch = O.synth_batch(b, DIMS, frames, seed=seed)
+        host = {k: (v.bfloat16() if k != "vals" else v.float()).contiguous().pin_memory() for k, v in batch.items()}
+        args = (host["audio"], host["text"], host["video"], host["feat4"], host["vals"])
+        tr.load_batch(*args)
+        ref = {k: v.clone() for k, v in tr.score().items()}
+        for key in tr.in_flat:
+            tr.in_flat[key].zero_()
+        tr.stage_batch(*args)
+        tr.commit_staged()
+        got = tr.score()
+        torch.cuda.synchronize()
+        for k in ref:
+            assert torch.equal(ref[k], got[k]), k
+
+
+def test_scoring_path_matches_oracle_and_reference_keys():
+    """score(): the two eval passes of main_frame_val_text_missing_inference.py:158-175."""
+    from tests.parity_common import nerr
+    P = O.init_params(DIMS, seed=100, gain=1.0, dtype=torch.float64)
+    batch = O.synth_batch(B, DIMS, FRAMES, seed=11)
+    b64 = {k: (v.bfloat16().double() if k != "vals" else v.double()) for k, v in batch.items()}
+    tr = _trainer(P, use_graph=False)
+    _load(tr, batch)
+    out = tr.score()
+    o0 = O.forward(P, b64["audio"], b64["text"], b64["video"])
+    o1 = O.forward(P, b64["audio"], b64["feat4"], b64["video"])
+    pairs = {"val_preds_full": o0[0], "val_preds_missing": o1[0], "full_rep": o0[1][0], "missing_rep": o1[1][0],
+             "full_rnc": o0[1][1], "missing_rnc": o1[1][1], "text_rep_query_full": o0[1][2],
+             "text_rep_query_missing": o1[1][2], "text_rep_full": o0[1][3], "text_rep_missing": o1[1][3]}
+    assert set(out) == set(pairs)
+    for k, ref in pairs.items():
+        assert nerr(out[k], ref) < 1e-2, (k, nerr(out[k], ref))
