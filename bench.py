@@ -30,6 +30,10 @@ sys.path.insert(0, str(ROOT))
 METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
 F_TRAIN_PER_SAMPLE = 2.408e9      # algorithmic FLOPs / sample of the S0 train step
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
+# (profiles/r1_gemm_inproj_full.md, profiles/r1_attn_bwd_full.md); None until measured
+TRAFFIC_INPROJ_BYTES = 757_918_720      # 406.6 MB read + 351.3 MB written (4 x 100.7 MB copies partly still in L2)
+TRAFFIC_ATTN_BWD_BYTES = 383_883_520    # 226.3 MB read + 157.6 MB written
 
 
 def load_peaks():
@@ -167,6 +171,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def trace(msg):
+        if os.environ.get("SDUMC_BENCH_TRACE"):
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     def max_over_ranks(ms: float) -> float:
         if world == 1:
             return ms
@@ -190,6 +198,7 @@ def run_ours(args):
         e1.record()
         barrier()
     ms_total = max_over_ranks(e0.elapsed_time(e1))
+    trace("device-resident timing done")
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total / 1e3)
     terms = tr.terms.tolist()
@@ -217,39 +226,78 @@ def run_ours(args):
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    trace("e2e timing done")
     e2e_value = world * B * n_e2e / (ms_e2e / 1e3)
 
-    # ---- dominant kernel alone: the audio in-projection GEMM (tcgen05, bf16, [B*384,1024] x [1024,256]) ----
+    # ---- dominant kernels alone (flushed L2 between launches, CUDA events on the launching stream) ----
     roof = None
+    roof_extra = []
     if rank == 0:
-        X = tr.inputs["a"].view(B * S0_FRAMES[0], S0_DIMS[0])
-        Wt = tr.W.bf16("frame_dim_reshape_0.weight")
-        bias = tr.W.f32("frame_dim_reshape_0.bias")
-        H = torch.empty(X.shape[0], 256, dtype=torch.bfloat16, device=dev)
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-        def go():
-            ops.gemm(X, Wt, M=X.shape[0], N=256, K=X.shape[1], bias=bias, epi_kind=ops.EPI_INPROJ, out_bf16=H)
-        for _ in range(3):
-            go()
-        ts = []
-        for _ in range(10):
-            flush.zero_()
-            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            go()
-            b_.record()
-            torch.cuda.synchronize()
-            ts.append(a.elapsed_time(b_))
-        ms_k = sum(ts) / len(ts)
-        flops = 2.0 * X.shape[0] * 256 * X.shape[1]
-        ach = flops / (ms_k * 1e-3) / 1e12
-        roof = {"bound": "tensor", "kernel": "gemm_tcgen05_kernel<256,bf16> (audio in-projection)", "achieved": ach,
-                "peak": peaks["tc_burst"], "unit": "TFLOP/s", "frac": ach / peaks["tc_burst"], "traffic": None,
+        def time_alone(go, n=10):
+            for _ in range(3):
+                go()
+            ts = []
+            for _ in range(n):
+                flush.zero_()
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                go()
+                b_.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b_))
+            return sum(ts) / len(ts)
+
+        # (1) the largest single launch of the step: the audio in-projection GEMM as the train step runs it -
+        #     tcgen05 bf16 [B*384,1024] x [1024,256], epilogue writes the 4 frame-dropout copies (2 blocks x 2 passes).
+        #     Arithmetic intensity 128 FLOP/B is below the ridge (peak TF / peak GB/s ~ 250): HBM-bound.
+        La, Da = S0_FRAMES[0], S0_DIMS[0]
+        X = tr.inputs["a"].view(B * La, Da)
+        Wt = tr.W.bf16("frame_dim_reshape_0.weight")
+        bias = tr.W.f32("frame_dim_reshape_0.bias")
+        tg = [torch.empty(B * La, 256, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+
+        def go_inproj():
+            ops.gemm(X, Wt, M=B * La, N=256, K=Da, bias=bias, epi_kind=ops.EPI_INPROJ, targets=tg,
+                     target_sites=[1, 2, 3, 4], seed=5, step=1)
+        ms_k = time_alone(go_inproj)
+        nbytes = X.numel() * 2 + Wt.numel() * 2 + sum(t.numel() * 2 for t in tg)
+        flops = 2.0 * B * La * 256 * Da
+        gbs = nbytes / (ms_k * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "gemm_tcgen05_kernel<256,bf16,INPROJ> (audio in-projection, 4 dropout copies)",
+                "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
+                "traffic": TRAFFIC_INPROJ_BYTES, "algorithmic_bytes": nbytes,
                 "peak_source": peaks["src"] + " (burst: kernel timed alone)", "ms_per_launch": ms_k,
-                "hbm_gbs": (X.numel() * 2 + H.numel() * 2 + Wt.numel() * 2) / (ms_k * 1e-3) / 1e9,
-                "hbm_frac": (X.numel() * 2 + H.numel() * 2 + Wt.numel() * 2) / (ms_k * 1e-3) / 1e9 / peaks["hbm"],
+                "tensor_tflops": flops / (ms_k * 1e-3) / 1e12,
+                "tensor_frac": flops / (ms_k * 1e-3) / 1e12 / peaks["tc_burst"],
                 "step_tensor_frac": value / world * F_TRAIN_PER_SAMPLE / (peaks["tc_sustained"] * 1e12)}
+        del tg
+        # (2) the largest kernel family by step share: the attention backward (7 queries, audio): reads X' and K,
+        #     writes dZ and dH, 4 x [B*384,256] bf16
+        rows = B * La
+        Xp = torch.randn(rows, 256, device=dev).bfloat16()
+        Kt = torch.tanh(torch.randn(rows, 256, device=dev)).bfloat16()
+        Pm = torch.softmax(torch.randn(B, La, 7, device=dev), dim=1).reshape(rows, 7).contiguous()
+        dOut = torch.randn(B, 7, 256, device=dev)
+        Opre = torch.randn(B, 7, 256, device=dev)
+        Qp = torch.randn(B, 7, 256, device=dev) * 0.5
+        dZ = torch.empty(rows, 256, dtype=torch.bfloat16, device=dev)
+        dH = torch.empty(rows, 256, dtype=torch.bfloat16, device=dev)
+        dQp = torch.zeros(B, 7, 256, device=dev)
+        db = torch.zeros(256, device=dev)
+
+        def go_attn():
+            ops.attn_bwd(Xp, Kt, Pm, dOut, dout_stride_b=7 * 256, O_pre=Opre, Qp=Qp, qp_stride_b=7 * 256, B=B, L=La, nq=7,
+                         out_drop_p=0.5, out_site=3, dZ=dZ, dH=dH, dh_mode=0, fmask_site=2, dQp=dQp,
+                         dqp_stride_b=7 * 256, db=db, seed=5, step=1)
+        ms_a = time_alone(go_attn)
+        nb_a = 4 * rows * 256 * 2 + Pm.numel() * 4 + 4 * B * 7 * 256 * 4
+        roof_extra.append({"bound": "hbm", "kernel": "attn_bwd_kernel<7> (audio Cross_Attention backward)",
+                           "achieved": nb_a / (ms_a * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
+                           "frac": nb_a / (ms_a * 1e-3) / 1e9 / peaks["hbm"], "traffic": TRAFFIC_ATTN_BWD_BYTES,
+                           "algorithmic_bytes": nb_a, "ms_per_launch": ms_a})
+        del Xp, Kt, Pm, dZ, dH
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -275,12 +323,15 @@ def run_ours(args):
             "gpu_launches_per_step": launches,
             "clocks": clk.summary(),
             "roofline": roof,
+            "roofline_extra": roof_extra,
             "cpu_baseline": cpu,
             "loss_terms": dict(zip(("mse_full", "mse_missing", "rmse_text_hidden", "rmse_cross_text", "rmse_fused",
                                     "rnc", "total"), terms[:7])),
         }
         print(json.dumps(line), flush=True)
+    tr.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -96,11 +96,26 @@ def load_splits(args):
     return tuple(stores)
 
 
+def prefetched(tr, batches):
+    """Iterates (batch, vals, names) with the NEXT batch's host->device copy already in flight on the trainer's
+    copy stream (the reference gets the same overlap from DataLoader workers + pin_memory)."""
+    it = iter(batches)
+    nxt = next(it, None)
+    if nxt is not None:
+        tr.stage_batch(nxt[0]["audio"], nxt[0]["text"], nxt[0]["video"], nxt[0]["feat4"], nxt[1])
+    while nxt is not None:
+        cur = nxt
+        tr.commit_staged()
+        nxt = next(it, None)
+        if nxt is not None:
+            tr.stage_batch(nxt[0]["audio"], nxt[0]["text"], nxt[0]["video"], nxt[0]["feat4"], nxt[1])
+        yield cur
+
+
 def run_split(tr, store, batch_size, train: bool, rank, world):
     """train_or_eval_model (main…:74-178): one pass over a split.  Returns the reference's result dict."""
     preds_full, preds_missing, labels, names = [], [], [], []
-    for batch, vals, nm in store.batches(batch_size, rank, world, lockstep=train):
-        tr.load_batch(batch["audio"], batch["text"], batch["video"], batch["feat4"], vals)
+    for batch, vals, nm in prefetched(tr, store.batches(batch_size, rank, world, lockstep=train)):
         if train:
             tr.train_step()
             pf, pm = tr.predictions()
@@ -225,8 +240,7 @@ def main_inference(argv=None):
         acc = {k: [] for k in keys}
         labels, names = [], []
         t0 = time.time()
-        for batch, vals, nm in store.batches(args.batch_size, rank, world):    # whole reference batches per rank
-            tr.load_batch(batch["audio"], batch["text"], batch["video"], batch["feat4"], vals)
+        for batch, vals, nm in prefetched(tr, store.batches(args.batch_size, rank, world)):   # whole reference batches per rank
             out = tr.score()
             for k in keys:
                 acc[k].append(out[k].float().cpu().numpy())

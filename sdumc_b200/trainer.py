@@ -53,7 +53,10 @@ class Trainer:
             self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         else:
             self.world, self.rank = 1, 0
-        self.use_graph = use_graph and self.world == 1
+        # the data-parallel step (NCCL all_gather / all_reduce inside) is captured too: NCCL collectives are graph
+        # nodes like any kernel; SDUMC_DP_GRAPH=0 falls back to eager launches for debugging
+        import os
+        self.use_graph = use_graph and (self.world == 1 or os.environ.get("SDUMC_DP_GRAPH", "1") != "0")
         dev, L = self.device, self.layout
         z = lambda n, dt=torch.float32: torch.zeros(n, dtype=dt, device=dev)  # noqa: E731
         self.master, self.grads, self.m, self.v = z(L.n_total), z(L.n_total), z(L.n_live), z(L.n_live)
@@ -261,6 +264,13 @@ class Trainer:
         else:
             self._graph.replay()
         self.n_steps += 1
+
+    def close(self):
+        """Drops the captured graph (it holds NCCL kernels of the process group in the data-parallel case) and
+        drains the device; call before torch.distributed.destroy_process_group()."""
+        torch.cuda.synchronize(self.device)
+        self._graph = None
+        torch.cuda.synchronize(self.device)
 
     def predictions(self):
         """(vals_full [B,1], vals_missing [B,1]) of the last step (device tensors)."""

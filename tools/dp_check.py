@@ -47,11 +47,20 @@ if __name__ == "__main__":
             res["grad_rel_diff"] = g
         else:
             res["terms_dp_dropout"] = tr.terms[:7].tolist()
+    # a few replays of the captured data-parallel step (NCCL collectives as graph nodes)
+    for _ in range(3):
+        tr.train_step()
+    torch.cuda.synchronize()
+    res["graph_captured"] = tr._graph is not None
+    res["terms_dp_replay"] = tr.terms[:7].tolist()
     # replicas stay identical
     n = tr.layout.n_live
     mine = tr.master[:n].clone()
     dist.broadcast(mine, src=0)
     res["replica_divergence"] = (mine - tr.master[:n]).abs().max().item()
     if rank == 0:
-        print("DPCHECK " + json.dumps(res))
+        print("DPCHECK " + json.dumps(res), flush=True)
+    tr.close()
+    dist.barrier()
     dist.destroy_process_group()
+    print(f"rank {rank} clean exit", flush=True)
