@@ -159,6 +159,16 @@ int sdumc_attn_bwd(const sdumc_attn_bwd_args* a, void* stream);
 int sdumc_cast_bf16(const float* src, SDUMC_BF16* dst, int64_t n, void* stream);
 int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, float* out256, void* stream);
 
+/* Collate of a device-resident feature store: the right-zero-padding batch builder of
+ * toolkit/utils/read_data.py:223-248 (pad_to_maxlen_pre_modality_tensor_4) as a gather.
+ *   packed      all utterances of one modality, rows back to back: bf16 [sum_T, D]
+ *   row_offset  [n_utt + 1] first row of each utterance (device, int64)
+ *   idx         [b] utterances of the batch (device, int32)
+ *   out         bf16 [b, Lpad, D]: out[i, l] = packed[row_offset[idx[i]] + l] for l < T_i, else 0
+ * D % 8 == 0, 16-byte aligned pointers; utterances longer than Lpad are an error the caller rules out. */
+int sdumc_collate_pad(const SDUMC_BF16* packed, const int64_t* row_offset, const int32_t* idx, int32_t b,
+                      int32_t Lpad, int32_t D, SDUMC_BF16* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * 4. Utterance-level glue between the MLP GEMMs (reference :301-320, :346-364) and the
  *    ReLU/dropout backward.

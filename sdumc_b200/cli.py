@@ -59,6 +59,8 @@ def build_parser(inference: bool) -> argparse.ArgumentParser:
                    help='text file of train utterances to drop (the reference drops 51 over-long ones, cmumosei.py:10-62)')
     p.add_argument('--synthetic', type=int, default=0, help='N synthetic S0-shaped utterances per split instead of files')
     p.add_argument('--synthetic_ragged', action='store_true', help='ragged synthetic lengths (padding semantics)')
+    p.add_argument('--device_store', action='store_true',
+                   help='keep the feature store in HBM and build batches with the collate kernel (no per-step H2D)')
     p.add_argument('--folds', type=int, default=1, help='K-fold cross-validation over the train split (reference: 1)')
     p.add_argument('--checkpoint', type=str, default=None,
                    help='checkpoint with ["state_dict"] (inference; the reference hard-codes its path, ..._inference.py:341)')
@@ -96,9 +98,16 @@ def load_splits(args):
     return tuple(stores)
 
 
-def prefetched(tr, batches):
+def prefetched(tr, batches, store=None):
     """Iterates (batch, vals, names) with the NEXT batch's host->device copy already in flight on the trainer's
-    copy stream (the reference gets the same overlap from DataLoader workers + pin_memory)."""
+    copy stream (the reference gets the same overlap from DataLoader workers + pin_memory).  A DeviceStore4F
+    yields index lists instead: the batch is gathered on the device by the collate kernel."""
+    from .dataset import DeviceStore4F
+    if isinstance(store, DeviceStore4F):
+        for idx, vals, nm in batches:
+            tr.load_from_store(store, idx)
+            yield idx, vals, nm
+        return
     it = iter(batches)
     nxt = next(it, None)
     if nxt is not None:
@@ -115,7 +124,7 @@ def prefetched(tr, batches):
 def run_split(tr, store, batch_size, train: bool, rank, world):
     """train_or_eval_model (main…:74-178): one pass over a split.  Returns the reference's result dict."""
     preds_full, preds_missing, labels, names = [], [], [], []
-    for batch, vals, nm in prefetched(tr, store.batches(batch_size, rank, world, lockstep=train)):
+    for batch, vals, nm in prefetched(tr, store.batches(batch_size, rank, world, lockstep=train), store):
         if train:
             tr.train_step()
             pf, pm = tr.predictions()
@@ -156,6 +165,9 @@ def main_train(argv=None):
         print(args)
         print('====== Reading Data =======')
     train, val, test = load_splits(args)
+    if args.device_store:
+        from .dataset import DeviceStore4F
+        train, val, test = (DeviceStore4F(st_, device) for st_ in (train, val, test))
     args.input_dims = train.dims
     if rank == 0:
         print('====== Training and Evaluation =======')
@@ -227,6 +239,9 @@ def main_inference(argv=None):
     world, rank, pg = _dist()
     device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     train, val, test = load_splits(args)
+    if args.device_store:
+        from .dataset import DeviceStore4F
+        train, val, test = (DeviceStore4F(st_, device) for st_ in (train, val, test))
     sd = None
     if args.checkpoint:
         ck = torch.load(args.checkpoint, map_location="cpu")
@@ -240,7 +255,7 @@ def main_inference(argv=None):
         acc = {k: [] for k in keys}
         labels, names = [], []
         t0 = time.time()
-        for batch, vals, nm in prefetched(tr, store.batches(args.batch_size, rank, world)):   # whole reference batches per rank
+        for batch, vals, nm in prefetched(tr, store.batches(args.batch_size, rank, world), store):   # whole reference batches per rank
             out = tr.score()
             for k in keys:
                 acc[k].append(out[k].float().cpu().numpy())

@@ -107,6 +107,11 @@ int sdumc_cast_bf16(const float* src, SDUMC_BF16* dst, int64_t n, void* stream) 
 int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, float* out256, void* stream) {
   return launch_colsum_bf16(X, ld, rows, out256, static_cast<cudaStream_t>(stream));
 }
+int sdumc_collate_pad(const SDUMC_BF16* packed, const int64_t* row_offset, const int32_t* idx, int32_t b,
+                      int32_t Lpad, int32_t D, SDUMC_BF16* out, void* stream) {
+  return launch_collate_pad(packed, reinterpret_cast<const long long*>(row_offset), idx, b, Lpad, D, out,
+                            static_cast<cudaStream_t>(stream));
+}
 int sdumc_sqdiff_sum(const float* a, const float* b, int64_t n, float* out_sum, void* stream) {
   return launch_sqdiff_sum(a, b, n, out_sum, static_cast<cudaStream_t>(stream));
 }

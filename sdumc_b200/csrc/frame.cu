@@ -664,6 +664,36 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t 
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// collate of the device-resident feature store: gather + right-zero-pad (read_data.py:223-248).
+// One warp per output row, 16-byte accesses; HBM-bound copy (2 * D bytes read + 2 * D written per row).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) collate_pad_kernel(const __nv_bfloat16* __restrict__ packed,
+                                                           const long long* __restrict__ row_offset,
+                                                           const int* __restrict__ idx, int b, int Lpad, int D,
+                                                           __nv_bfloat16* __restrict__ out) {
+  const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= (long)b * Lpad) return;
+  const int i = (int)(row / Lpad), l = (int)(row - (long)i * Lpad);
+  const int u = __ldg(idx + i);
+  const long long r0 = __ldg(row_offset + u), r1 = __ldg(row_offset + u + 1);
+  const bool live = l < (int)(r1 - r0);
+  const uint4* src = reinterpret_cast<const uint4*>(packed + (r0 + l) * (long long)D);
+  uint4* dst = reinterpret_cast<uint4*>(out + row * D);
+  for (int c = threadIdx.x & 31; c < D / 8; c += 32) dst[c] = live ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
+}
+int launch_collate_pad(const __nv_bfloat16* packed, const long long* row_offset, const int* idx, int b, int Lpad, int D,
+                       __nv_bfloat16* out, cudaStream_t stream) {
+  SDUMC_CHECK_ARG(packed && row_offset && idx && out, "collate_pad: null pointer");
+  SDUMC_CHECK_ARG(b > 0 && Lpad > 0 && D > 0 && D % 8 == 0, "collate_pad: bad shape b=%d Lpad=%d D=%d", b, Lpad, D);
+  SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
+                  "collate_pad: pointers must be 16-byte aligned");
+  const long rows = (long)b * Lpad;
+  collate_pad_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(packed, row_offset, idx, b, Lpad, D, out);
+  SDUMC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // column sums of a bf16 matrix [rows, 256] -> atomicAdd into out[256]   (bias gradient of the in-projection)
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long ld, long rows,
                                                            float* __restrict__ out) {

@@ -74,6 +74,16 @@ def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     check(_lib.lib().sdumc_cast_bf16(ptr(src), ptr(dst), src.numel(), current_stream()), "sdumc_cast_bf16")
 
 
+def collate_pad(packed: torch.Tensor, row_offset: torch.Tensor, idx: torch.Tensor, Lpad: int, out: torch.Tensor) -> None:
+    """out[b, Lpad, D] = right-zero-padded utterances idx of the packed device store (read_data.py:223-248)."""
+    assert packed.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and packed.is_contiguous() and out.is_contiguous()
+    assert row_offset.dtype == torch.int64 and idx.dtype == torch.int32
+    b, D = idx.numel(), packed.shape[1]
+    assert out.numel() == b * Lpad * D
+    check(_lib.lib().sdumc_collate_pad(ptr(packed), ptr(row_offset), ptr(idx), b, Lpad, D, ptr(out), current_stream()),
+          "sdumc_collate_pad")
+
+
 def colsum_bf16(X: torch.Tensor, out: torch.Tensor) -> None:
     """out[256] += column sums of the bf16 matrix X [rows,256]."""
     assert X.dtype == torch.bfloat16 and X.shape[1] == G and out.numel() == G

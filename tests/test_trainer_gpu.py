@@ -143,3 +143,29 @@ def test_scoring_path_matches_oracle_and_reference_keys():
     assert set(out) == set(pairs)
     for k, ref in pairs.items():
         assert nerr(out[k], ref) < 1e-2, (k, nerr(out[k], ref))
+
+
+def test_device_store_collate_equals_host_collate():
+    """DeviceStore4F + the collate kernel (gather + right-zero-pad to the batch maximum, read_data.py:223-248)
+    builds byte-identical batches to the pinned-host Store4F.collate, for ragged utterances."""
+    from sdumc_b200.dataset import DeviceStore4F, Store4F
+    P = O.init_params(DIMS, seed=100, gain=1.0, dtype=torch.float64)
+    tr = _trainer(P, use_graph=False)
+    host = Store4F.synthetic(40, DIMS, FRAMES, seed=5, ragged=True)
+    devs = DeviceStore4F(host, tr.device)
+    hb = list(host.batches(B))
+    db = list(devs.batches(B))
+    assert len(hb) == len(db) == 3
+    for (batch, vals, names), (idx, vals_d, names_d) in zip(hb, db):
+        assert names == names_d and torch.equal(vals, vals_d)
+        tr.load_batch(batch["audio"], batch["text"], batch["video"], batch["feat4"], vals)
+        ref_in = {k: v.clone() for k, v in tr.inputs.items()}
+        ref = {k: v.clone() for k, v in tr.score().items()}
+        for key in tr.in_flat:
+            tr.in_flat[key].fill_(7.0)                       # stale data must be overwritten, pads included
+        tr.load_from_store(devs, idx)
+        for k in ref_in:
+            assert tr.inputs[k].shape == ref_in[k].shape and torch.equal(tr.inputs[k], ref_in[k]), k
+        got = tr.score()
+        for k in ref:
+            assert torch.equal(ref[k], got[k]), k
