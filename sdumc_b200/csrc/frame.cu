@@ -277,10 +277,11 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
 //   dQp^T [256 x 8 q]     += K^T[256 x 16 rows] * dS      A: ldmatrix.trans from the K tile, B: movmatrix(dS)
 //   dK  [16 x 256]         = dS[16 x 8] * Qp              A: the dP accumulator fragment, reused as operand
 //   dXv [16 x 256]         = P [16 x 8] * dO
-// One CTA (8 warps) per sample; a stage is 64 frame rows of X' and K, brought into a 2-deep shared-memory
-// ring by per-row bulk copies (rows padded to 528 B so ldmatrix is conflict-free).  Warp w works on rows
-// 16*(w&3).. of the stage and on column half (w>>2) of every product; the only exchange inside a warp
-// pair is the 16x8 partial dP (each half reduces over its own 128 columns).
+// 16 warps per CTA; a stage is 64 frame rows of X' and K, brought into a 2-deep shared-memory ring by per-row
+// bulk copies (rows padded to 528 B so ldmatrix is conflict-free).  Warp w works on rows 16*(w&3).. of the
+// stage and on column quarter (w>>2) of every product (4 warps per scheduler hide the dependent-chain
+// latency that bounded the 8-warp version); the only exchange inside a quartet is the 16x8 partial dP (each
+// quarter reduces over its own 64 columns) and the hand-over of finished rows to the warp that stores them.
 // dZ and the value-path gradient are written back into the tiles in place and leave through bulk
 // stores; the "+= old dH" of the accumulate mode is a bulk reduce-add performed at L2, so the old
 // gradient is never read by the SM.
@@ -288,7 +289,7 @@ constexpr int kBwdStages = 2;
 constexpr int kBwdRows = 64;                       // rows per stage (16 per warp)
 constexpr int kBwdPitch = G + 8;                   // bf16 elements per padded shared-memory row (528 B)
 constexpr int kBwdTile = kBwdRows * kBwdPitch * 2; // bytes of one padded bf16 [64,256] tile
-constexpr int kBwdThreads = 256;
+constexpr int kBwdThreads = 512;
 
 template <int NQ>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a) {
@@ -307,8 +308,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   // uniform registers (no per-lane serialisation loop around UBLKCP)
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int gid = lane >> 2, tq = lane & 3;           // fragment coordinates: row group / column pair
-  const int rw = warp & 3, hc = (warp >> 2) * (G / 2); // row slab of the stage / first column of this warp's half
-  __shared__ float4 dp_x[kBwdThreads];                // partial dP exchange inside a warp pair
+  const int rw = warp & 3, qc = warp >> 2;             // row slab of the stage / column quarter
+  const int hc = qc * (G / 4);                        // first column of this warp's quarter
+  __shared__ float4 dp_x[kBwdThreads];                // partial dP exchange inside a warp quartet
   const int L = a.L;
   const int n_iter = (L + kBwdRows - 1) / kBwdRows;
   const bool rmw = a.dh_mode == 1;
@@ -321,7 +323,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   const int u_begin = (int)(((long)n_units * blockIdx.x) / gridDim.x);
   const int my_units = (int)(((long)n_units * (blockIdx.x + 1)) / gridDim.x) - u_begin;
 
-  auto issue_stage = [&](int k) {                     // lane 0 of warp w: rows 8w..8w+7 of X' and of K of unit k
+  auto issue_stage = [&](int k) {                     // lane 0 of warp w: rows 4w..4w+3 of X' and of K of unit k
     const int u = u_begin + k;
     const int ub = u / n_iter, it = u - ub * n_iter;
     const int slot = k % kBwdStages;
@@ -329,8 +331,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
     unsigned char* dst = ring + slot * 2 * kBwdTile;
     if (lane == 0) {
       if (warp == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2 * 2);
-      const int r1 = min(rows, warp * 8 + 8);
-      for (int r = warp * 8; r < r1; ++r) {
+      const int r1 = min(rows, warp * 4 + 4);
+      for (int r = warp * 4; r < r1; ++r) {
         const long src = (((long)ub * L + (long)it * kBwdRows) + r) * G;   // host guarantees dense [B*L,256] tensors
         bulk_load(dst + r * kBwdPitch * 2, a.X + src, G * 2, &full_bar[slot]);
         bulk_load(dst + kBwdTile + r * kBwdPitch * 2, a.Kt + src, G * 2, &full_bar[slot]);
@@ -427,18 +429,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   dl1 = delta_s[2 * tq + 1];
   };
 
-  float dq_acc[8][4];    // dQp^T fragments: [m-tile of 16 columns][(col gid, q 2tq) (col gid, q 2tq+1) (col gid+8, ...)]
-  float db_acc[16][2];   // column sums of dZ over this thread's rows, per 8-column tile
+  float dq_acc[4][4];    // dQp^T fragments: [m-tile of 16 columns][(col gid, q 2tq) (col gid, q 2tq+1) (col gid+8, ...)]
+  float db_acc[8][2];    // column sums of dZ over this thread's rows, per 8-column tile
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f; }
+  for (int i = 0; i < 4; ++i) { dq_acc[i][0] = dq_acc[i][1] = dq_acc[i][2] = dq_acc[i][3] = 0.f; }
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { db_acc[i][0] = db_acc[i][1] = 0.f; }
+  for (int i = 0; i < 8; ++i) { db_acc[i][0] = db_acc[i][1] = 0.f; }
 
   // dQp of the finished sample: fragments of the four row-slab warps -> shared memory -> global atomics
   // (a sample may be shared with the neighbouring CTAs; the host zero-fills dQp)
   auto flush_dqp = [&](int b) {
 #pragma unroll
-    for (int mt = 0; mt < 8; ++mt) {
+    for (int mt = 0; mt < 4; ++mt) {
       const int c = hc + mt * 16 + gid, q = 2 * tq;
       if (q < NQ)     { atomicAdd(&dqp_s[q * G + c], dq_acc[mt][0]);       atomicAdd(&dqp_s[q * G + c + 8], dq_acc[mt][2]); }
       if (q + 1 < NQ) { atomicAdd(&dqp_s[(q + 1) * G + c], dq_acc[mt][1]); atomicAdd(&dqp_s[(q + 1) * G + c + 8], dq_acc[mt][3]); }
@@ -467,13 +469,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
     const int slot = k % kBwdStages;
     mbar_wait(&full_bar[slot], (uint32_t)((k / kBwdStages) & 1));
     unsigned char* st = ring + slot * 2 * kBwdTile;
-    __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(st) + rw * 16 * kBwdPitch + hc;            // this warp's 16 rows x 128 columns
+    __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(st) + rw * 16 * kBwdPitch + hc;            // this warp's 16 rows x 64 columns
     __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(st + kBwdTile) + rw * 16 * kBwdPitch + hc;
     const int l0 = it * kBwdRows + rw * 16;           // first frame of this warp's slab
     const int valid = min(16, L - l0);                // may be <= 0 for a trailing warp
     if (valid < 16) {                                 // rows past L: zero so they add nothing to dQp / db
-      for (int i = lane; i < 16 * (G / 16); i += 32) {
-        const int r = i / (G / 16), c = (i % (G / 16)) * 8;
+      for (int i = lane; i < 16 * (G / 32); i += 32) {
+        const int r = i / (G / 32), c = (i % (G / 32)) * 8;
         if (r >= valid) {
           *reinterpret_cast<uint4*>(Xs + r * kBwdPitch + c) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(Ks + r * kBwdPitch + c) = make_uint4(0, 0, 0, 0);
@@ -482,13 +484,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       __syncwarp();
     }
     if (valid > 0) {
-      // (1) dP = X' * dO^T: this warp's 128 columns, then add the partner warp's partial
+      // (1) dP = X' * dO^T: this warp's 64 columns, then add the partials of the other three quarters
       float dP[4] = {0.f, 0.f, 0.f, 0.f};
       {
         const __nv_bfloat16* arow = Xs + ((lane & 7) + ((lane >> 3) & 1) * 8) * kBwdPitch + (lane >> 4) * 8;
         const __nv_bfloat16* brow = dO_b + gid * kBwdPitch + hc + 2 * tq;
 #pragma unroll
-        for (int kk = 0; kk < G / 32; ++kk) {
+        for (int kk = 0; kk < G / 64; ++kk) {
           uint32_t af[4];
           ldsm_x4(af, arow + kk * 16);
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + kk * 16);
@@ -496,9 +498,12 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
           mma_16816(dP, af, b0, b1);
         }
         dp_x[tid] = make_float4(dP[0], dP[1], dP[2], dP[3]);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + rw) : "memory");
-        const float4 o = dp_x[tid ^ 128];
-        dP[0] += o.x; dP[1] += o.y; dP[2] += o.z; dP[3] += o.w;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + rw) : "memory");
+        // all four quarters add the partials in the same order: identical dS in every warp of the quartet
+        const float4 o0 = dp_x[(rw << 5) + lane], o1 = dp_x[128 + (rw << 5) + lane];
+        const float4 o2 = dp_x[256 + (rw << 5) + lane], o3 = dp_x[384 + (rw << 5) + lane];
+        dP[0] = (o0.x + o1.x) + (o2.x + o3.x); dP[1] = (o0.y + o1.y) + (o2.y + o3.y);
+        dP[2] = (o0.z + o1.z) + (o2.z + o3.z); dP[3] = (o0.w + o1.w) + (o2.w + o3.w);
       }
       // (2) dS = alpha * P * (dP - delta) on the accumulator layout: rows gid / gid+8, queries 2tq / 2tq+1
       const bool v0 = gid < valid, v1 = gid + 8 < valid;
@@ -512,23 +517,23 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
         const uint32_t bt0 = movmatrix_trans(dS_lo), bt1 = movmatrix_trans(dS_hi);
         const __nv_bfloat16* arow = Ks + ((lane & 7) + (lane >> 4) * 8) * kBwdPitch + ((lane >> 3) & 1) * 8;
 #pragma unroll
-        for (int mt = 0; mt < 8; ++mt) {
+        for (int mt = 0; mt < 4; ++mt) {
           uint32_t af[4];
           ldsm_x4_trans(af, arow + mt * 16);
           mma_16816(dq_acc[mt], af, bt0, bt1);
         }
       }
-      // frame-mask words of this thread's two rows (this warp's 128-column half)
+      // frame-mask words of this thread's two rows (the 128-column block holding this warp's quarter)
       U4 ma, mb;
       if (a.fmask_site) {
         const uint32_t r0 = (uint32_t)((long)b * L + l0 + gid);
-        ma = frame_mask_words(key, a.fmask_site, r0, (uint32_t)(warp >> 2));
-        mb = frame_mask_words(key, a.fmask_site, r0 + 8, (uint32_t)(warp >> 2));
+        ma = frame_mask_words(key, a.fmask_site, r0, (uint32_t)(qc >> 1));
+        mb = frame_mask_words(key, a.fmask_site, r0 + 8, (uint32_t)(qc >> 1));
       }
       // (3) dK = dS * Qp, dXv = P * dO, eight columns at a time; dZ and the masked dXv replace K and X' in place
 #pragma unroll
-      for (int nt = 0; nt < 16; ++nt) {
-        const int col = nt * 8 + 2 * tq;               // relative to this warp's half
+      for (int nt = 0; nt < 8; ++nt) {
+        const int col = nt * 8 + 2 * tq;               // relative to this warp's quarter
         const uint32_t bq = *reinterpret_cast<const uint32_t*>(QpT + (hc + nt * 8 + gid) * 8 + 2 * tq);
         const uint32_t bo = *reinterpret_cast<const uint32_t*>(dOT + (hc + nt * 8 + gid) * 8 + 2 * tq);
         float dK[4], dX[4];
@@ -546,7 +551,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
         *k0p = pack2(z00, z01);
         *k1p = pack2(z10, z11);
         if (a.fmask_site) {
-          const int w = (nt >> 2) & 3;
+          const int w = ((qc & 1) * 2 + (nt >> 2)) & 3;   // 32-column word inside the 128-column block
           const uint32_t wa = (w == 0 ? ma.x : (w == 1 ? ma.y : (w == 2 ? ma.z : ma.w))) >> ((nt & 3) * 8 + 2 * tq);
           const uint32_t wb = (w == 0 ? mb.x : (w == 1 ? mb.y : (w == 2 ? mb.z : mb.w))) >> ((nt & 3) * 8 + 2 * tq);
           dX[0] = (wa & 1u) ? 2.f * dX[0] : 0.f; dX[1] = (wa & 2u) ? 2.f * dX[1] : 0.f;
@@ -555,15 +560,18 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
         *reinterpret_cast<uint32_t*>(Xs + gid * kBwdPitch + col) = pack2(dX[0], dX[1]);
         *reinterpret_cast<uint32_t*>(Xs + (gid + 8) * kBwdPitch + col) = pack2(dX[2], dX[3]);
       }
-      // tiles -> global: one bulk store per row and tensor, issued by the lane that owns the row
+      // tiles -> global: the quartet's 16 finished rows leave as full 512-byte rows, four per warp
       fence_proxy_async();
-      __syncwarp();
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + rw) : "memory");
       if (lane == 0) {
-        for (int r = 0; r < valid; ++r) {
-          const long dst = (long)(l0 + r) * G + hc;
-          bulk_store(Zb + dst, Ks + r * kBwdPitch, G);
-          if (rmw) bulk_reduce_add_bf16(Hb + dst, Xs + r * kBwdPitch, G);
-          else     bulk_store(Hb + dst, Xs + r * kBwdPitch, G);
+        const __nv_bfloat16* Kr = Ks - hc;             // row starts of this slab
+        const __nv_bfloat16* Xr = Xs - hc;
+        const int r1 = min(valid, qc * 4 + 4);
+        for (int r = qc * 4; r < r1; ++r) {
+          const long dst = (long)(l0 + r) * G;
+          bulk_store(Zb + dst, Kr + r * kBwdPitch, G * 2);
+          if (rmw) bulk_reduce_add_bf16(Hb + dst, Xr + r * kBwdPitch, G * 2);
+          else     bulk_store(Hb + dst, Xr + r * kBwdPitch, G * 2);
         }
       }
       bulk_commit();
@@ -576,7 +584,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   if (b >= 0) flush_dqp(b);
   // db: reduce over the 8 row groups of the warp, then over the warps through shared memory
 #pragma unroll
-  for (int nt = 0; nt < 16; ++nt) {
+  for (int nt = 0; nt < 8; ++nt) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       float v = db_acc[nt][j];
@@ -591,7 +599,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   __syncthreads();
   if (gid == 0) {
 #pragma unroll
-    for (int nt = 0; nt < 16; ++nt) {
+    for (int nt = 0; nt < 8; ++nt) {
       atomicAdd(&db_s[hc + nt * 8 + 2 * tq], db_acc[nt][0]);
       atomicAdd(&db_s[hc + nt * 8 + 2 * tq + 1], db_acc[nt][1]);
     }
@@ -618,7 +626,7 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
                   a.dout_stride_b % 4 == 0 && a.qp_stride_b % 4 == 0,
                   "attn_bwd: dOut / Qp / O_pre must be 16-byte aligned with strides that are multiples of 4");
   const size_t smem = attn_bwd_smem(a.L);
-  constexpr size_t kMaxDyn = 220 * 1024;   // + ~1.1 KB static stays under the 227 KB per-CTA limit
+  constexpr size_t kMaxDyn = 216 * 1024;   // + 9.1 KB static (dP exchange, db) stays under the 227 KB per-CTA limit
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
   static bool attr_done = false;
   if (!attr_done) {
