@@ -394,7 +394,26 @@ __global__ void __launch_bounds__(256) rnc_col_kernel(RncArgs a, const float* Cm
   for (int d0 = dg * 8; d0 < D; d0 += 64) {
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     float csum = 0.f;
-    for (int il = il0; il < il1; ++il) {
+    // 8 anchor rows per trip with all loads issued first: the loop is a chain of L2 round trips otherwise
+    int il = il0;
+    for (; il + 8 <= il1; il += 8) {
+      float c[8];
+      float4 u[8], v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        c[k] = __ldg(Cmat + (long)(il + k) * n + j);
+        const float4* fi = reinterpret_cast<const float4*>(a.feats + (long)(a.row_begin + il + k) * D + d0);
+        u[k] = __ldg(fi);
+        v[k] = __ldg(fi + 1);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        csum += c[k];
+        acc[0] = fmaf(c[k], u[k].x, acc[0]); acc[1] = fmaf(c[k], u[k].y, acc[1]); acc[2] = fmaf(c[k], u[k].z, acc[2]); acc[3] = fmaf(c[k], u[k].w, acc[3]);
+        acc[4] = fmaf(c[k], v[k].x, acc[4]); acc[5] = fmaf(c[k], v[k].y, acc[5]); acc[6] = fmaf(c[k], v[k].z, acc[6]); acc[7] = fmaf(c[k], v[k].w, acc[7]);
+      }
+    }
+    for (; il < il1; ++il) {
       const float c = Cmat[(long)il * n + j];
       const float4* fi = reinterpret_cast<const float4*>(a.feats + (long)(a.row_begin + il) * D + d0);
       const float4 u = __ldg(fi), v = __ldg(fi + 1);
@@ -424,7 +443,22 @@ __global__ void __launch_bounds__(256) rnc_rowgrad_kernel(RncArgs a, const float
     float csum = 0.f;
     const int d = d0 + dl * 4;
     if (d < D) {
-      for (int j = jg; j < n; j += 16) {
+      int j = jg;
+      for (; j + 7 * 16 < n; j += 8 * 16) {     // 8 independent loads in flight per thread
+        float c[8];
+        float4 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          c[k] = __ldg(crow + j + 16 * k);
+          v[k] = __ldg(reinterpret_cast<const float4*>(a.feats + (long)(j + 16 * k) * D + d));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          csum += c[k];
+          acc[0] = fmaf(c[k], v[k].x, acc[0]); acc[1] = fmaf(c[k], v[k].y, acc[1]); acc[2] = fmaf(c[k], v[k].z, acc[2]); acc[3] = fmaf(c[k], v[k].w, acc[3]);
+        }
+      }
+      for (; j < n; j += 16) {
         const float c = crow[j];
         const float4 v = __ldg(reinterpret_cast<const float4*>(a.feats + (long)j * D + d));
         csum += c;
