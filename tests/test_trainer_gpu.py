@@ -169,3 +169,30 @@ def test_device_store_collate_equals_host_collate():
         got = tr.score()
         for k in ref:
             assert torch.equal(ref[k], got[k]), k
+
+
+@pytest.mark.parametrize("b,frames", [(2, (1, 1, 1, 1)), (3, (1500, 2, 5, 3)), (5, (33, 17, 1, 17))])
+def test_edge_shapes_score_and_step(b, frames):
+    """Smallest batch the reference survives (B = 2; its squeeze() breaks B = 1), single-frame utterances (the
+    softmax over one frame is 1), and a long utterance near the shared-memory limit of the attention kernels."""
+    from sdumc_b200.trainer import Trainer
+    from tests.parity_common import nerr
+    dims = (64, 128, 32, 128)
+    P = O.init_params(dims, seed=100, gain=1.0, dtype=torch.float64)
+    batch = O.synth_batch(b, dims, frames, seed=21)
+    b64 = {k: (v.bfloat16().double() if k != "vals" else v.double()) for k, v in batch.items()}
+    dev = torch.device("cuda", 0)
+    tr = Trainer(dims, b, frames, dev, state_dict={k: v.float() for k, v in P.items()}, use_graph=False)
+    tr.load_batch(*(batch[k].bfloat16().to(dev) for k in ("audio", "text", "video", "feat4")), batch["vals"].to(dev))
+    out = tr.score()
+    o0 = O.forward(P, b64["audio"], b64["text"], b64["video"])
+    o1 = O.forward(P, b64["audio"], b64["feat4"], b64["video"])
+    for k, ref in (("val_preds_full", o0[0]), ("val_preds_missing", o1[0]), ("full_rep", o0[1][0]),
+                   ("missing_rnc", o1[1][1]), ("text_rep_query_full", o0[1][2]), ("text_rep_missing", o1[1][3])):
+        if k.startswith("val_preds"):      # predictions live on the label scale [-3, 3]: absolute tolerance 1e-2
+            assert float((out[k].double().cpu() - ref).abs().max()) < 1e-2, k
+        else:
+            assert nerr(out[k], ref) < 2.5e-2, (k, nerr(out[k], ref))   # EMB_TOL of tests/test_model_gpu.py
+    tr.train_step()
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(tr.terms[:7]).all()) and bool(torch.isfinite(tr.master).all())
