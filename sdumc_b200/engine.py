@@ -299,20 +299,18 @@ class Engine:
             L = cfg.frames[_unit_stream(p, m)]
             X = st.t[f"Xc.{p}.{m}"]
             S = st.t[f"Sc.{p}.{m}"]
-            Kt = st.t[f"Kc.{p}.{m}"] if keep else None
             pre = f"cross_att_fra2utt_{m}"
             qp = Qp[m][p * B * NQ:(p + 1) * B * NQ]
-            if keep:   # training: K is materialised for the backward pass; the 7 scores per row come from the
-                       # pooling kernel's tensor-core product instead of 7 x 256 SIMT FMAs in the GEMM epilogue
-                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                         act=ops.ACT_TANH, out_bf16=Kt)
-            else:
-                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                         act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, qv=qp, q_stride=NQ * G, nq=NQ, L=L, scores=S)
+            # K is materialised (kept for the backward pass when training, a temporary when scoring): the 7 scores
+            # per row come from the pooling kernel's tensor-core product instead of 7 x 256 SIMT FMAs in the GEMM
+            # epilogue - writing and re-reading K costs less than those FMAs
+            Kt = st.t[f"Kc.{p}.{m}"] if keep else torch.empty(B * L, G, dtype=torch.bfloat16, device=dev)
+            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                     act=ops.ACT_TANH, out_bf16=Kt)
             ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=st.t[f"Oc_pre.{p}.{m}"], out=C[m][p * B * NQ:(p + 1) * B * NQ],
                          out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
                          drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step,
-                         step_dev=cfg.step_dev, Kt=Kt, Qp=qp if keep else None, qp_stride_b=NQ * G)
+                         step_dev=cfg.step_dev, Kt=Kt, Qp=qp, qp_stride_b=NQ * G)
         self._parallel(len(units), cross_unit)
 
         # 5. utterance chain B

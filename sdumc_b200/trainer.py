@@ -99,6 +99,7 @@ class Trainer:
         self.n_steps = 0
         self._graph = None
         self._outputs = None
+        self._score_graph, self._score_out, self._score_calls = None, None, 0
 
     # ---- parameters ------------------------------------------------------------------------
     def load_state_dict(self, sd: Dict[str, torch.Tensor]):
@@ -289,7 +290,7 @@ class Trainer:
         """Drops the captured graph (it holds NCCL kernels of the process group in the data-parallel case) and
         drains the device; call before torch.distributed.destroy_process_group()."""
         torch.cuda.synchronize(self.device)
-        self._graph = None
+        self._graph = self._score_graph = self._score_out = None
         torch.cuda.synchronize(self.device)
 
     def predictions(self):
@@ -298,12 +299,28 @@ class Trainer:
         return vals[0], vals[1]
 
     # ---- scoring (main_frame_val_text_missing_inference.py:158-175) --------------------------
-    @torch.no_grad()
-    def score(self):
-        """Both passes in eval mode on the batch in the static buffers.  Returns the dict of device tensors
-        the inference CLI collects: predictions + the 4 embeddings of each pass."""
+    def _score_body(self):
         st = self._forward(dropout=False, need_grad=False)
         vals, f, rnc, th, ct = Engine.outputs(st)
         return {"val_preds_full": vals[0], "val_preds_missing": vals[1], "full_rep": f[0], "missing_rep": f[1],
                 "full_rnc": rnc[0], "missing_rnc": rnc[1], "text_rep_query_full": th[0].contiguous(),
                 "text_rep_query_missing": th[1].contiguous(), "text_rep_full": ct[0], "text_rep_missing": ct[1]}
+
+    @torch.no_grad()
+    def score(self):
+        """Both passes in eval mode on the batch in the static buffers.  Returns the dict of device tensors
+        the inference CLI collects: predictions + the 4 embeddings of each pass.  Full-size batches replay a
+        captured CUDA graph (~100 launches per batch otherwise dominate at the reference's inference batch of
+        128): the returned tensors are then overwritten by the next score() call - copy what must survive."""
+        full = self.cur_B == self.B and self.cur_frames == self.frames
+        if not self.use_graph or not full or self._score_calls == 0:
+            self._score_calls += 1
+            return self._score_body()
+        if self._score_graph is None:
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._score_out = self._score_body()
+            self._score_graph = g
+        self._score_graph.replay()
+        return self._score_out
