@@ -297,6 +297,8 @@ typedef struct sdumc_rnc_args {
   float grad_scale;
   void* workspace;
   uint64_t workspace_bytes;
+  int32_t reuse_sort;  /* 1: the workspace still holds the label sort of a previous call with the same labels */
+  int32_t reserved;
 } sdumc_rnc_args;
 uint64_t sdumc_rnc_workspace_bytes(int32_t n, int32_t D);
 int sdumc_rnc(const sdumc_rnc_args* a, void* stream);

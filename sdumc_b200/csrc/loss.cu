@@ -10,6 +10,7 @@
 //     the negative set {j : d_ij >= d_ik - 1e-4} is a prefix plus a suffix of the sorted order, found
 //     by two binary searches that evaluate the reference's fp32 predicate verbatim: O(n^2 log n),
 //     forward and backward.
+#include <algorithm>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -191,10 +192,11 @@ __global__ void __launch_bounds__(1024) rnc_sort_kernel(const float* labels, int
   }
 }
 
-// inclusive scan (double) of src[0..n) into dst[0..n); 256 threads, contiguous chunk per thread
-__device__ void block_scan_256(const float* src, double* dst, int n, double* wsum /*[8]*/) {
+// inclusive scan (double) of src[0..n) into dst[0..n); blockDim.x threads (a multiple of 32, <= 1024),
+// contiguous chunk per thread
+__device__ void block_scan(const float* src, double* dst, int n, double* wsum /*[32]*/) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int chunk = (n + 255) / 256;
+  const int chunk = (n + (int)blockDim.x - 1) / (int)blockDim.x;
   const int lo = t * chunk, hi = min(n, lo + chunk);
   double run = 0.0;
   for (int i = lo; i < hi; ++i) {
@@ -264,7 +266,9 @@ __global__ void __launch_bounds__(256) rnc_dist_kernel(RncArgs a, float* dist) {
 
 // One CTA per anchor row.  Shared memory: pre[n] (double), e[n], aux[n] (logits, then 1/D), dist[n] (float).
 // Cmat holds the row's distances on entry (rnc_dist_kernel) and its gradient coefficients on exit.
-__global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm, const float* ys, const int* pos,
+// The per-element work is a chain of ~50 dependent binary-search steps: the kernel is latency-bound, so it
+// runs with up to 1024 threads per CTA (n = 8192 took 630 us per 512 anchors with 256).
+__global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* perm, const float* ys, const int* pos,
                                                        float* Cmat) {
   extern __shared__ unsigned char smraw[];
   const int n = a.n, D = a.D;
@@ -272,9 +276,10 @@ __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm
   float* e = reinterpret_cast<float*>(pre + n);
   float* aux = e + n;
   float* dist_s = aux + n;
-  __shared__ float red[8];
-  __shared__ double wsum[8];
+  __shared__ float red[32];
+  __shared__ double wsum[32];
   __shared__ float bcast;
+  const int NT = blockDim.x, NW = NT >> 5;
 
   const int i = a.row_begin + blockIdx.x;
   const int t = threadIdx.x;
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm
 
   // 1. logits in sorted order (the whole distance row moves to shared memory before crow is overwritten), running max
   float mx = -INFINITY;
-  for (int s = t; s < n; s += 256) {
+  for (int s = t; s < n; s += NT) {
     const int j = perm[s];
     const float ds = crow[j];
     dist_s[s] = ds;
@@ -302,21 +307,21 @@ __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm
   __syncthreads();
   if (t == 0) {
     float m = red[0];
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w]);
+    for (int w = 1; w < NW; ++w) m = fmaxf(m, red[w]);
     bcast = m;
   }
   __syncthreads();
   mx = bcast;
-  for (int s = t; s < n; s += 256) e[s] = (s == pi) ? 0.f : __expf(aux[s] - mx);
+  for (int s = t; s < n; s += NT) e[s] = (s == pi) ? 0.f : __expf(aux[s] - mx);
   __syncthreads();
 
   // 2. prefix sums of e in label order
-  block_scan_256(e, pre, n, wsum);
+  block_scan(e, pre, n, wsum);
   const double total = pre[n - 1];
 
   // 3. per positive k: denominator = prefix [0,lo) + suffix [hi,n)
   float lsum = 0.f;
-  for (int s = t; s < n; s += 256) {
+  for (int s = t; s < n; s += NT) {
     float rinv = 0.f;
     if (s != pi) {
       const float thr = fabsf(yi - ys[s]) - 0.0001f;
@@ -344,16 +349,16 @@ __global__ void __launch_bounds__(256) rnc_row_kernel(RncArgs a, const int* perm
   __syncthreads();
   if (t == 0) {
     float tot = 0.f;
-    for (int w = 0; w < 8; ++w) tot += red[w];
+    for (int w = 0; w < NW; ++w) tot += red[w];
     atomicAdd(a.loss, tot / ((float)n * (float)(n - 1)));
   }
   if (!a.dfeats) return;
 
   // 4. backward: G_j = sum of 1/D_k over the k whose negative set contains j (a window around i)
   __syncthreads();
-  block_scan_256(aux, pre, n, wsum);  // pre = prefix sums of 1/D_k
+  block_scan(aux, pre, n, wsum);  // pre = prefix sums of 1/D_k
   const float cscale = a.grad_scale / ((float)n * (float)(n - 1));
-  for (int s = t; s < n; s += 256) {
+  for (int s = t; s < n; s += NT) {
     const int j = perm[s];
     float c = 0.f;
     if (s != pi) {
@@ -423,57 +428,68 @@ __global__ void __launch_bounds__(256) rnc_col_kernel(RncArgs a, const float* Cm
     }
     // - sum_i c_ij (f_i - f_j) = f_j * csum - sum_i c_ij f_i
     const float* fj = a.feats + (long)j * D + d0;
+    float o[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) atomicAdd(a.dfeats + (long)j * D + d0 + u, fj[u] * csum - acc[u]);
+    for (int u = 0; u < 8; ++u) o[u] = fj[u] * csum - acc[u];
+    float* dst = a.dfeats + (long)j * D + d0;          // D % 4 == 0 and d0 % 8 == 0: 16-byte aligned
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
   }
 }
-// row part: dfeats[i] += sum_j c_ij (f_i - f_j) = f_i * rowsum - sum_j c_ij f_j ; one CTA per anchor row
+// row part: dfeats[i] += sum_j c_ij (f_i - f_j) = f_i * rowsum - sum_j c_ij f_j, a [rows x n] x [n x D] product.
+// CTA = 32 anchor rows x one slice of the j range (gridDim.y slices, partial results meet in vector reds);
+// 64-column chunks of C (transposed) and 64 rows of F go through shared memory, a thread owns 4 rows x 2 dims
+// per 64-dim block: one 16-byte broadcast load of C and one 8-byte load of F per 8 FMAs.  (One CTA per anchor row
+// re-read the whole feature matrix from L2 per row: 127 us per 512 anchors at n = 8192.)
 __global__ void __launch_bounds__(256) rnc_rowgrad_kernel(RncArgs a, const float* Cmat) {
-  __shared__ float sacc[64];
-  __shared__ float ssum;
+  __shared__ __align__(16) float CsT[64][36];   // [j][row], rows padded to 36 (16-byte aligned quads)
+  __shared__ __align__(16) float Fs[64][64];
   const int n = a.n, D = a.D;
-  const int i = a.row_begin + blockIdx.x;
-  const float* crow = Cmat + (long)blockIdx.x * n;
-  const int dl = threadIdx.x & 15, jg = threadIdx.x >> 4;  // 16 lanes x 4 dims = 64 dims; 16 j-groups
+  const int rows = a.row_end - a.row_begin;
+  const int il0 = blockIdx.x * 32;
+  const int jlo = (int)(((long)n * blockIdx.y) / gridDim.y), jhi = (int)(((long)n * (blockIdx.y + 1)) / gridDim.y);
+  const int rg = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int d0 = 0; d0 < D; d0 += 64) {
-    if (threadIdx.x < 64) sacc[threadIdx.x] = 0.f;
-    if (threadIdx.x == 0) ssum = 0.f;
-    __syncthreads();
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float csum = 0.f;
-    const int d = d0 + dl * 4;
+    const int dw = min(64, D - d0);
+    float acc[4][2] = {};
+    float csum[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j0 = jlo; j0 < jhi; j0 += 64) {
+      for (int x = threadIdx.x; x < 32 * 64; x += 256) {
+        const int r = x >> 6, jj = x & 63;
+        const int il = il0 + r, j = j0 + jj;
+        CsT[jj][r] = (il < rows && j < jhi) ? __ldg(Cmat + (long)il * n + j) : 0.f;
+      }
+      for (int x = threadIdx.x; x < 64 * 64; x += 256) {
+        const int jj = x >> 6, d = x & 63;
+        const int j = j0 + jj;
+        Fs[jj][d] = (j < jhi && d < dw) ? __ldg(a.feats + (long)j * D + d0 + d) : 0.f;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int jj = 0; jj < 64; ++jj) {
+        const float4 c = *reinterpret_cast<const float4*>(&CsT[jj][4 * rg]);
+        const float2 f = *reinterpret_cast<const float2*>(&Fs[jj][2 * lane]);
+        csum[0] += c.x; csum[1] += c.y; csum[2] += c.z; csum[3] += c.w;
+        acc[0][0] = fmaf(c.x, f.x, acc[0][0]); acc[0][1] = fmaf(c.x, f.y, acc[0][1]);
+        acc[1][0] = fmaf(c.y, f.x, acc[1][0]); acc[1][1] = fmaf(c.y, f.y, acc[1][1]);
+        acc[2][0] = fmaf(c.z, f.x, acc[2][0]); acc[2][1] = fmaf(c.z, f.y, acc[2][1]);
+        acc[3][0] = fmaf(c.w, f.x, acc[3][0]); acc[3][1] = fmaf(c.w, f.y, acc[3][1]);
+      }
+      __syncthreads();
+    }
+    const int d = d0 + 2 * lane;
     if (d < D) {
-      int j = jg;
-      for (; j + 7 * 16 < n; j += 8 * 16) {     // 8 independent loads in flight per thread
-        float c[8];
-        float4 v[8];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          c[k] = __ldg(crow + j + 16 * k);
-          v[k] = __ldg(reinterpret_cast<const float4*>(a.feats + (long)(j + 16 * k) * D + d));
-        }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          csum += c[k];
-          acc[0] = fmaf(c[k], v[k].x, acc[0]); acc[1] = fmaf(c[k], v[k].y, acc[1]); acc[2] = fmaf(c[k], v[k].z, acc[2]); acc[3] = fmaf(c[k], v[k].w, acc[3]);
-        }
+      for (int u = 0; u < 4; ++u) {
+        const int il = il0 + 4 * rg + u;
+        if (il >= rows) continue;
+        const long i = a.row_begin + il;
+        const float2 fi = *reinterpret_cast<const float2*>(a.feats + i * D + d);
+        float* dst = a.dfeats + i * D + d;              // D % 4 == 0, d even: 8-byte aligned
+        asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dst), "f"(fi.x * csum[u] - acc[u][0]),
+                     "f"(fi.y * csum[u] - acc[u][1]) : "memory");
       }
-      for (; j < n; j += 16) {
-        const float c = crow[j];
-        const float4 v = __ldg(reinterpret_cast<const float4*>(a.feats + (long)j * D + d));
-        csum += c;
-        acc[0] = fmaf(c, v.x, acc[0]); acc[1] = fmaf(c, v.y, acc[1]); acc[2] = fmaf(c, v.z, acc[2]); acc[3] = fmaf(c, v.w, acc[3]);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) atomicAdd(&sacc[dl * 4 + u], acc[u]);
-      if (dl == 0) atomicAdd(&ssum, csum);
     }
-    __syncthreads();
-    if (threadIdx.x < 64 && d0 + threadIdx.x < D) {
-      const int dd = d0 + threadIdx.x;
-      atomicAdd(a.dfeats + (long)i * D + dd, a.feats[(long)i * D + dd] * ssum - sacc[threadIdx.x]);
-    }
-    __syncthreads();
   }
 }
 
@@ -508,17 +524,24 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
                                     kRncMaxN * 20));
     attr_done = true;
   }
-  rnc_sort_kernel<<<1, 1024, (size_t)n2 * 8, stream>>>(a.labels, a.n, n2, perm, ys, pos);
-  SDUMC_CUDA(cudaGetLastError());
+  if (!a.reuse_sort) {   // a data-parallel rank calls once per anchor range with the same labels: sort once
+    rnc_sort_kernel<<<1, 1024, (size_t)n2 * 8, stream>>>(a.labels, a.n, n2, perm, ys, pos);
+    SDUMC_CUDA(cudaGetLastError());
+  }
   rnc_dist_kernel<<<dim3((a.n + 63) / 64, (rows + 63) / 64), 256, 0, stream>>>(a, Cmat);
   SDUMC_CUDA(cudaGetLastError());
   const size_t smem = (size_t)a.n * 20;
-  rnc_row_kernel<<<rows, 256, smem, stream>>>(a, perm, ys, pos, Cmat);
+  const int row_threads = a.n >= 4096 ? 1024 : (a.n >= 1024 ? 512 : 256);
+  rnc_row_kernel<<<rows, row_threads, smem, stream>>>(a, perm, ys, pos, Cmat);
   SDUMC_CUDA(cudaGetLastError());
   if (a.dfeats) {
-    rnc_rowgrad_kernel<<<rows, 256, 0, stream>>>(a, Cmat);
+    const int row_tiles = (rows + 31) / 32;
+    const int jsplit = std::max(1, std::min(a.n / 256, (2 * 148 + row_tiles - 1) / row_tiles));
+    rnc_rowgrad_kernel<<<dim3(row_tiles, jsplit), 256, 0, stream>>>(a, Cmat);
     SDUMC_CUDA(cudaGetLastError());
-    const int ysplit = rows >= 512 ? 16 : (rows >= 64 ? 4 : 1);
+    // anchor rows per CTA of the column kernel: enough CTAs to fill the GPU, few enough partial sums
+    const int jblocks = (a.n + 31) / 32;
+    const int ysplit = std::max(1, std::min(rows / 32, (4 * 148 + jblocks - 1) / jblocks));
     rnc_col_kernel<<<dim3((a.n + 31) / 32, ysplit), 256, 0, stream>>>(a, Cmat);
     SDUMC_CUDA(cudaGetLastError());
   }

@@ -217,7 +217,7 @@ def rnc_workspace_bytes(n: int, D: int) -> int:
 
 
 def rnc(feats, labels, *, loss, dfeats=None, row_begin=0, row_end=None, temperature=2.0, grad_scale=1.0,
-        workspace=None) -> None:
+        workspace=None, reuse_sort=False) -> None:
     """Rank-N-Contrast over feats [n,D] (rows = view-0 samples then view-1 samples), labels [n]."""
     n, D = feats.shape
     a = STRUCTS["sdumc_rnc_args"]()
@@ -227,7 +227,8 @@ def rnc(feats, labels, *, loss, dfeats=None, row_begin=0, row_end=None, temperat
     if workspace is None:
         workspace = torch.empty(rnc_workspace_bytes(n, D), dtype=torch.uint8, device=feats.device)
     a.workspace, a.workspace_bytes = ptr(workspace), workspace.numel()
-    call("sdumc_rnc", a, launches=5 if dfeats is not None else 3)
+    a.reuse_sort = 1 if reuse_sort else 0
+    call("sdumc_rnc", a, launches=(5 if dfeats is not None else 3) - (1 if reuse_sort else 0))
 
 
 def adam(p, g, m, v, *, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0,

@@ -244,9 +244,12 @@ class Trainer:
             from . import dp
             dp.reduce_sums(self.sums, self.pg)
 
-            def rnc_fn(feats_g, y_g, lo, hi, loss, dfeats):
+            calls = [0]
+
+            def rnc_fn(feats_g, y_g, lo, hi, loss, dfeats):   # both anchor ranges share one label sort
                 ops.rnc(feats_g, y_g, loss=loss, dfeats=dfeats, row_begin=lo, row_end=hi, grad_scale=w6,
-                        workspace=self.rnc_ws)
+                        workspace=self.rnc_ws, reuse_sort=calls[0] > 0)
+                calls[0] += 1
             loss_g, d_local = dp.rnc_global(rnc.contiguous(), y.contiguous(), self.pg, rnc_fn)
             self.rnc_val.copy_(loss_g)
             d_rnc.view(2, B, 64).copy_(d_local)
