@@ -90,3 +90,70 @@ def test_device_philox_matches_numpy():
             w = philox([r, c0 >> 7, site, step], key)[(c0 >> 5) & 3]
             want_row = np.array([2.0 if (w >> j) & 1 else 0.0 for j in range(32)], dtype=np.float32)
             assert np.array_equal(fm[r, c0:c0 + 32], want_row)
+
+
+def test_rnc_kernels_at_data_parallel_size():
+    """n = 4096 rows (the global Rank-N-Contrast problem of a 4-GPU job): the large-n launch configuration
+    (1024-thread anchor kernel, tiled row-gradient kernel, split column kernel, shared label sort).
+    Loss and gradient against fp64 (autograd) evaluations of loss.py:278-315 on the device for subsets of the
+    anchors, and the sum over 8 anchor slices (what 8 calls of a data-parallel rank compute) against one full call."""
+    from sdumc_b200 import ops
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    Bq, D = 2048, 64
+    n = 2 * Bq
+    base = torch.randn(Bq, D, device=dev, generator=g) * 0.4
+    feats = torch.cat([base, base + 0.05 * torch.randn(Bq, D, device=dev, generator=g)], 0).contiguous()
+    y = (torch.randn(Bq, device=dev, generator=g).clamp(-3, 3) * 4).round() / 4      # many tied labels
+    y2 = y.repeat(2).contiguous()
+    ws = torch.empty(ops.rnc_workspace_bytes(n, D), dtype=torch.uint8, device=dev)
+
+    def run(f, grads=True, slices=1):
+        loss = torch.zeros(1, device=dev)
+        df = torch.zeros(n, D, device=dev) if grads else None
+        step = n // slices
+        for k in range(slices):
+            ops.rnc(f, y2, loss=loss, dfeats=df, row_begin=k * step, row_end=(k + 1) * step, workspace=ws,
+                    reuse_sort=k > 0)
+        return loss, df
+
+    loss, df = run(feats)
+    # fp64 reference of the loss (anchor loop of the reference, vectorised over positives and negatives)
+    f64, y64 = feats.double(), y2.double()
+    logit = -torch.cdist(f64, f64) / 2.0
+    dlab = (y64[:, None] - y64[None, :]).abs()
+    off = ~torch.eye(n, dtype=torch.bool, device=dev)
+    total = torch.zeros((), dtype=torch.float64, device=dev)
+    for i in range(0, n, 7):                   # every 7th anchor: ~600 rows of the 4096
+        li, di = logit[i][off[i]], dlab[i][off[i]]
+        li = li - li.max()
+        member = di[None, :] >= (di[:, None] - 0.0001)
+        denom = (member.double() * li.exp()[None, :]).sum(1)
+        total = total - (li - denom.log()).sum() / (n * (n - 1))
+    sub = torch.zeros(1, device=dev)
+    for i in range(0, n, 7):
+        ops.rnc(feats, y2, loss=sub, dfeats=None, row_begin=i, row_end=i + 1, workspace=ws, reuse_sort=i > 0)
+    assert abs(float(sub) - float(total)) <= 1e-4 * abs(float(total)), (float(sub), float(total))
+    # gradient: fp64 autograd of the same formula restricted to the first 64 anchors vs the kernels on that range
+    A = 64
+    fr = feats.double().clone().requires_grad_(True)
+    tot = torch.zeros((), dtype=torch.float64, device=dev)
+    ar = torch.arange(n, device=dev)
+    for i in range(A):
+        m = ar != i
+        li = -(fr[i][None, :] - fr[m]).norm(dim=1) / 2.0
+        di = dlab[i][m]
+        li = li - li.max().detach()
+        member = di[None, :] >= (di[:, None] - 0.0001)
+        denom = (member.double() * li.exp()[None, :]).sum(1)
+        tot = tot - (li - denom.log()).sum() / (n * (n - 1))
+    tot.backward()
+    lossA, dfA = torch.zeros(1, device=dev), torch.zeros(n, D, device=dev)
+    ops.rnc(feats, y2, loss=lossA, dfeats=dfA, row_begin=0, row_end=A, workspace=ws)
+    assert abs(float(lossA) - float(tot)) <= 1e-4 * abs(float(tot)), (float(lossA), float(tot))
+    gerr = float((dfA.double() - fr.grad).abs().max() / fr.grad.abs().max())
+    assert gerr <= 1e-3, gerr
+    # 8 anchor slices sharing one sort == one call
+    loss8, df8 = run(feats, slices=8)
+    assert abs(float(loss8) - float(loss)) <= 1e-5 * abs(float(loss))
+    assert float((df8 - df).abs().max()) <= 1e-5 * float(df.abs().max()) + 1e-9
