@@ -83,3 +83,59 @@ def test_reader_and_collate_follow_reference_padding(tmp_path):
     st6 = Store4F.from_disk(str(tmp_path), feats, nm, vals)
     assert [len(b[2]) for b in st6.batches(2, rank=1, world=2)] == [2]
     assert [len(b[2]) for b in st6.batches(2, rank=0, world=2, lockstep=True)] == [2]
+
+
+def test_device_store_mirrors_the_host_store_batching():
+    """DeviceStore4F (packed rows + offsets; here on the CPU device - the collate kernel itself is a GPU test):
+    same batch composition, labels, names and per-batch padded lengths as Store4F, for every rank."""
+    from sdumc_b200.dataset import STREAMS, DeviceStore4F, Store4F
+    host = Store4F.synthetic(23, dims=(16, 24, 8, 24), frames=(12, 5, 9, 5), seed=3, ragged=True)
+    dev = DeviceStore4F(host, "cpu")
+    for s in STREAMS:
+        lens = [int(x.shape[0]) for x in host.feats[s]]
+        assert dev.packed[s].shape == (sum(lens), host.feats[s][0].shape[1])
+        assert dev.offsets[s].tolist() == [0] + list(np.cumsum(lens))
+        i = 7
+        assert torch.equal(dev.packed[s][dev.offsets[s][i]:dev.offsets[s][i + 1]], host.feats[s][i])
+    for rank, world, lock in ((0, 1, False), (1, 2, False), (0, 2, True)):
+        hb = list(host.batches(4, rank, world, lockstep=lock))
+        db = list(dev.batches(4, rank, world, lockstep=lock))
+        assert len(hb) == len(db) > 0
+        for (batch, vals, names), (idx, vals_d, names_d) in zip(hb, db):
+            assert names == names_d and torch.equal(vals, vals_d)
+            assert dev.batch_frames(idx) == tuple(batch[s].shape[1] for s in STREAMS)
+
+
+def test_prefetch_iterator_stages_one_batch_ahead():
+    """cli.prefetched: batch i+1 is staged (H2D in flight) before batch i is handed to the step, every batch is
+    committed exactly once and in order; a DeviceStore4F goes through load_from_store instead."""
+    from sdumc_b200.cli import prefetched
+    from sdumc_b200.dataset import DeviceStore4F, Store4F
+
+    class FakeTrainer:
+        def __init__(self):
+            self.log = []
+
+        def stage_batch(self, a, t, v, f, vals):
+            self.log.append(("stage", int(a.shape[0])))
+
+        def commit_staged(self):
+            self.log.append(("commit",))
+
+        def load_from_store(self, store, idx):
+            self.log.append(("gather", tuple(idx)))
+
+    host = Store4F.synthetic(10, dims=(16, 24, 8, 24), frames=(6, 3, 4, 3), seed=1)
+    tr = FakeTrainer()
+    seen = []
+    for batch, vals, names in prefetched(tr, host.batches(4), host):
+        seen.append(len(names))
+        tr.log.append(("step", len(names)))
+    assert seen == [4, 4, 2]
+    assert tr.log == [("stage", 4), ("commit",), ("stage", 4), ("step", 4), ("commit",), ("stage", 2), ("step", 4),
+                      ("commit",), ("step", 2)]
+    tr = FakeTrainer()
+    dev = DeviceStore4F(host, "cpu")
+    got = [idx for idx, vals, names in prefetched(tr, dev.batches(4), dev)]
+    assert got == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
+    assert tr.log == [("gather", (0, 1, 2, 3)), ("gather", (4, 5, 6, 7)), ("gather", (8, 9))]
