@@ -17,12 +17,17 @@ def _all_gather(t: torch.Tensor, pg) -> torch.Tensor:
 
 def global_views(rnc_local: torch.Tensor, y_local: torch.Tensor, pg) -> Tuple[torch.Tensor, torch.Tensor]:
     """rnc_local [2,B,D] (view, sample), y_local [B] -> feats_g [2*Bg,D], y_g [2*Bg] in the row order a single
-    process would build (toolkit/utils/loss.py:282-283): all view-0 rows (rank-major), then all view-1 rows."""
-    feats_all = _all_gather(rnc_local, pg)                      # [W,2,B,D]
-    y_all = _all_gather(y_local, pg)                            # [W,B]
-    W, _, B, D = feats_all.shape
-    feats_g = feats_all.permute(1, 0, 2, 3).reshape(2 * W * B, D).contiguous()
-    y_g = y_all.reshape(W * B).repeat(2).contiguous()
+    process would build (toolkit/utils/loss.py:282-283): all view-0 rows (rank-major), then all view-1 rows.
+    One collective: both views and the label travel as one packed row [2*D + 1] per sample."""
+    _, B, D = rnc_local.shape
+    pack = torch.empty(B, 2 * D + 1, dtype=rnc_local.dtype, device=rnc_local.device)
+    pack[:, :D] = rnc_local[0]
+    pack[:, D:2 * D] = rnc_local[1]
+    pack[:, 2 * D] = y_local.to(rnc_local.dtype)
+    allp = _all_gather(pack, pg)                                 # [W,B,2D+1]
+    W = allp.shape[0]
+    feats_g = torch.cat((allp[:, :, :D].reshape(W * B, D), allp[:, :, D:2 * D].reshape(W * B, D)), dim=0).contiguous()
+    y_g = allp[:, :, 2 * D].reshape(W * B).to(y_local.dtype).repeat(2).contiguous()
     return feats_g, y_g
 
 
@@ -33,20 +38,29 @@ def anchor_ranges(B: int, world: int, rank: int):
 
 
 def rnc_global(rnc_local: torch.Tensor, y_local: torch.Tensor, pg,
-               rnc_fn: Callable[[torch.Tensor, torch.Tensor, int, int, torch.Tensor, torch.Tensor], None]):
+               rnc_fn: Callable[[torch.Tensor, torch.Tensor, int, int, torch.Tensor, torch.Tensor], None],
+               extra: torch.Tensor = None):
     """Global Rank-N-Contrast over the sharded batch.  rnc_fn(feats_g, y_g, row_begin, row_end, loss, dfeats)
     adds the share of the loss of anchors [row_begin,row_end) to loss[0] and its gradient w.r.t. ALL rows to
-    dfeats.  Returns (global loss [1], d loss / d rnc_local [2,B,D])."""
+    dfeats.  Returns (global loss [1], d loss / d rnc_local [2,B,D]).
+    `extra` (optional 1-D tensor of the same dtype, e.g. the sums of squares of the MSE / RMSE terms) is summed over
+    the ranks in place by the same all-reduce: two collectives per step instead of five."""
     world, rank = dist.get_world_size(pg), dist.get_rank(pg)
     B, D = rnc_local.shape[1], rnc_local.shape[2]
     feats_g, y_g = global_views(rnc_local, y_local, pg)
-    loss = torch.zeros(1, dtype=feats_g.dtype, device=feats_g.device)
-    dfeats = torch.zeros_like(feats_g)
+    n = feats_g.shape[0]
+    k = 0 if extra is None else extra.numel()
+    buf = torch.zeros(n * D + 1 + k, dtype=feats_g.dtype, device=feats_g.device)   # [dfeats | loss | extra]
+    dfeats, loss = buf[:n * D].view(n, D), buf[n * D:n * D + 1]
     for lo, hi in anchor_ranges(B, world, rank):
         rnc_fn(feats_g, y_g, lo, hi, loss, dfeats)
-    dist.all_reduce(loss, group=pg)
-    dist.all_reduce(dfeats, group=pg)
-    return loss, dfeats.view(2, world, B, D)[:, rank].contiguous()
+    if k:
+        assert extra.dtype == buf.dtype and extra.dim() == 1
+        buf[n * D + 1:] = extra
+    dist.all_reduce(buf, group=pg)
+    if k:
+        extra.copy_(buf[n * D + 1:])
+    return loss.clone(), dfeats.view(2, world, B, D)[:, rank].contiguous()
 
 
 def reduce_sums(sums: torch.Tensor, pg) -> torch.Tensor:

@@ -242,7 +242,6 @@ class Trainer:
             ops.rnc(st.t["rnc"], y2, loss=self.rnc_val, dfeats=d_rnc, grad_scale=w6, workspace=self.rnc_ws)
         else:
             from . import dp
-            dp.reduce_sums(self.sums, self.pg)
 
             calls = [0]
 
@@ -250,7 +249,8 @@ class Trainer:
                 ops.rnc(feats_g, y_g, loss=loss, dfeats=dfeats, row_begin=lo, row_end=hi, grad_scale=w6,
                         workspace=self.rnc_ws, reuse_sort=calls[0] > 0)
                 calls[0] += 1
-            loss_g, d_local = dp.rnc_global(rnc.contiguous(), y.contiguous(), self.pg, rnc_fn)
+            # one all_gather (features + labels) and one all_reduce (RnC gradient + loss + the sums of squares)
+            loss_g, d_local = dp.rnc_global(rnc.contiguous(), y.contiguous(), self.pg, rnc_fn, extra=self.sums)
             self.rnc_val.copy_(loss_g)
             d_rnc.view(2, B, 64).copy_(d_local)
         ops.loss_finish(vals[0], vals[1], y, th[0], th[1], ct[0], ct[1], f[0], f[1], B=B, sums=self.sums,

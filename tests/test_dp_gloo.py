@@ -40,9 +40,13 @@ def _worker(rank, world, port, B, q):
         loss += l.detach()
         dfeats += f.grad
 
-    loss_g, d_local = dp.rnc_global(local, y[sl].contiguous(), dist.group.WORLD, rnc_fn)
+    # the sums of squares ride on the RnC all-reduce (what the trainer does) ...
     sums = torch.tensor([((a[sl] - b[sl]) ** 2).sum()], dtype=torch.float64)
-    dp.reduce_sums(sums, dist.group.WORLD)
+    loss_g, d_local = dp.rnc_global(local, y[sl].contiguous(), dist.group.WORLD, rnc_fn, extra=sums)
+    # ... and the stand-alone reduction gives the same value
+    sums2 = torch.tensor([((a[sl] - b[sl]) ** 2).sum()], dtype=torch.float64)
+    dp.reduce_sums(sums2, dist.group.WORLD)
+    assert torch.equal(sums, sums2)
     # single-process reference on the whole batch
     fr = feats.clone().requires_grad_(True)
     lr = O.rnc_loss(fr, y.unsqueeze(1))
