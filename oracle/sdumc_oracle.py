@@ -167,7 +167,7 @@ def pool_attention(P: Params, prefix: str, H: torch.Tensor, queries: Optional[to
 
 
 def forward(P: Params, audio: torch.Tensor, text: torch.Tensor, video: torch.Tensor,
-            drop: Optional[DropFn] = None, lin=None, rnd=None, relu=None):
+            drop: Optional[DropFn] = None, lin=None, rnd=None, relu=None, pool=None):
     """WengnetMOSEIMultViewsTextMissing.forward (:275-370).
 
     Returns (vals_out [B,1], [fused [B,128], feat4rnc [B,64], text_hidden [B,256], cross_text [B,7,128]]).
@@ -175,18 +175,20 @@ def forward(P: Params, audio: torch.Tensor, text: torch.Tensor, video: torch.Ten
     replaces every nn.Linear evaluation, `rnd(tag, x)` is applied to the tanh key projections and
     `relu(name, z)` replaces the ReLUs (tests use the hooks to emulate the rounding points of the CUDA path
     and to pin the ReLU on/off pattern to the one the CUDA forward took); the math is unchanged.
+    `pool(prefix, modality, queries)` optionally replaces the six pooling attentions (forward_varlen).
     """
     drop = drop or _identity_drop
     lin = lin or _linear
     relu = relu or _relu
     mlp = lambda name, x, n: _mlp(P, name, x, n, drop, lin, relu)  # noqa: E731
-    Ha = lin(P, "frame_dim_reshape_0", audio)
-    Ht = lin(P, "frame_dim_reshape_1", text)
-    Hv = lin(P, "frame_dim_reshape_2", video)
+    if pool is None:
+        Hs = (lin(P, "frame_dim_reshape_0", audio), lin(P, "frame_dim_reshape_1", text),
+              lin(P, "frame_dim_reshape_2", video))
+        pool = lambda prefix, m, q: pool_attention(P, prefix, Hs[m], q, drop, lin, rnd)[0]  # noqa: E731
 
-    ua, _ = pool_attention(P, "fra2utt_0", Ha, None, drop, lin, rnd)
-    ut, _ = pool_attention(P, "fra2utt_1", Ht, None, drop, lin, rnd)
-    uv, _ = pool_attention(P, "fra2utt_2", Hv, None, drop, lin, rnd)
+    ua = pool("fra2utt_0", 0, None)
+    ut = pool("fra2utt_1", 1, None)
+    uv = pool("fra2utt_2", 2, None)
 
     ha = mlp("audio_mlp", ua, 2)
     ht = mlp("text_mlp", ut, 2)
@@ -204,9 +206,9 @@ def forward(P: Params, audio: torch.Tensor, text: torch.Tensor, video: torch.Ten
     text_hidden = qs[5]                                   # re-bound at :329; this is embedding #3
     Q = torch.stack(qs, dim=1)                            # [B,7,G]
 
-    Ca, _ = pool_attention(P, "cross_att_fra2utt_0", Ha, Q, drop, lin, rnd)
-    Ct, _ = pool_attention(P, "cross_att_fra2utt_1", Ht, Q, drop, lin, rnd)
-    Cv, _ = pool_attention(P, "cross_att_fra2utt_2", Hv, Q, drop, lin, rnd)
+    Ca = pool("cross_att_fra2utt_0", 0, Q)
+    Ct = pool("cross_att_fra2utt_1", 1, Q)
+    Cv = pool("cross_att_fra2utt_2", 2, Q)
 
     ca = mlp("cross_audio_mlp", Ca, 2)                    # [B,7,128]
     ct = mlp("cross_text_mlp", Ct, 2)
@@ -219,6 +221,46 @@ def forward(P: Params, audio: torch.Tensor, text: torch.Tensor, video: torch.Ten
     vals_out = lin(P, "fc_out_v", f)
     feat4rnc = lin(P, "orgin_linear_change.2", relu("orgin_linear_change.0", lin(P, "orgin_linear_change.0", f)))
     return vals_out, [f, feat4rnc, text_hidden, ct]
+
+
+def forward_varlen(P: Params, audio: List[torch.Tensor], text: List[torch.Tensor], video: List[torch.Tensor],
+                   pad_to: Sequence[int]):
+    """Eval-mode forward on RAGGED utterances that equals forward() on the batch right-zero-padded to `pad_to`
+    frames per modality (read_data.py:223-248) without touching the padded frames.
+
+    The reference has no mask, so a padded frame (x = 0) still takes part in both softmaxes: its in-projection
+    is the bias alone, h_pad = b_m; its key k_pad = tanh(W_in h_pad + b_in) and its score s_pad,q = k_pad . Qp_q
+    are the same for every padded frame of a sample.  With n_pad = L_pad - T such frames the softmax denominator
+    gains n_pad * exp(0.3 s_pad,q) and the pooled value n_pad * p_pad,q * h_pad: a closed form per (sample, query).
+    Train mode has no such form (the input dropout makes every padded row different).
+    audio/text/video: lists of [T_b, D_m] tensors."""
+    feats = (audio, text, video)
+    B = len(audio)
+    Hs = [[_linear(P, f"frame_dim_reshape_{m}", x) for x in feats[m]] for m in range(3)]
+
+    def pool(prefix, m, queries):
+        h_pad = P[f"frame_dim_reshape_{m}.bias"]
+        k_pad = torch.tanh(_linear(P, f"{prefix}.input_proj", h_pad[None, :]))[0]
+        outs = []
+        for b in range(B):
+            H = Hs[m][b]                                              # [T,G] valid frames only
+            n_pad = pad_to[m] - H.shape[0]
+            assert n_pad >= 0
+            K = torch.tanh(_linear(P, f"{prefix}.input_proj", H))
+            if queries is None:
+                Qp = P[f"{prefix}.attention_context_vector"].reshape(1, -1)
+            else:
+                Qp = _linear(P, f"{prefix}.query_proj", queries[b])      # [Nq,G]
+            S = SOFTMAX_SCALE * (K @ Qp.t())                          # [T,Nq]
+            s_pad = SOFTMAX_SCALE * (Qp @ k_pad)                      # [Nq]
+            mx = torch.maximum(S.max(dim=0).values, s_pad) if H.shape[0] else s_pad
+            E, e_pad = (S - mx).exp(), (s_pad - mx).exp()
+            den = E.sum(dim=0) + n_pad * e_pad
+            O = (E / den).t() @ H + (n_pad * e_pad / den)[:, None] * h_pad[None, :]
+            outs.append(O[0] if queries is None else O)
+        return torch.stack(outs, dim=0)
+
+    return forward(P, None, None, None, pool=pool)
 
 
 def dropout_sites() -> List[Tuple[str, float]]:

@@ -119,3 +119,30 @@ def test_standalone_losses(golden):
 def test_lr_schedule():
     # main_frame_val_text_missing.py:318-320
     assert [round(O.lr_lambda(e), 6) for e in (0, 4, 5, 13, 14, 24)] == [0.2, 1.0, 1.0, 1.0, 0.9, 0.81]
+
+
+def test_varlen_closed_form_equals_the_padded_forward():
+    """SURVEY 8f N2 groundwork: the eval-mode forward on ragged utterances with the closed-form contribution of
+    the padded frames (oracle.forward_varlen) equals the reference semantics - forward() on the right-zero-padded
+    batch, where padded frames take part in the softmaxes - also when the batch is padded beyond its maximum."""
+    from oracle import sdumc_oracle as O
+    dims, frames, B = (24, 40, 16, 40), (11, 6, 9, 6), 5
+    P = O.init_params(dims, seed=100, gain=1.3, dtype=torch.float64)
+    batch = O.synth_batch(B, dims, frames, seed=3, dtype=torch.float64)
+    g = torch.Generator().manual_seed(0)
+    lens = [[int(torch.randint(1, frames[m] + 1, (1,), generator=g)) for _ in range(B)] for m in range(3)]
+    keys = ("audio", "text", "video")
+    ragged = [[batch[k][b, : lens[m][b]] for b in range(B)] for m, k in enumerate(keys)]
+    for extra in (0, 3):
+        pad_to = [max(lens[m]) + extra for m in range(3)]
+        padded = []
+        for m, k in enumerate(keys):
+            x = torch.zeros(B, pad_to[m], dims[m], dtype=torch.float64)
+            for b in range(B):
+                x[b, : lens[m][b]] = ragged[m][b]
+            padded.append(x)
+        ref = O.forward(P, *padded)
+        got = O.forward_varlen(P, *ragged, pad_to=pad_to)
+        assert torch.allclose(got[0], ref[0], rtol=0, atol=1e-12)
+        for a, b_ in zip(got[1], ref[1]):
+            assert torch.allclose(a, b_, rtol=0, atol=1e-12)
