@@ -76,8 +76,6 @@ typedef struct sdumc_gemm_desc {
   uint64_t seed; /* dropout RNG */
   uint32_t step;
   const uint32_t* step_dev; /* optional device counter added to step */
-  uint32_t dbg_lbo, dbg_sbo; /* test-only descriptor overrides, 0 = default */
-  uint64_t* dbg_clk;         /* test-only: [grid][16] cycle counters of the pipeline phases, or NULL */
 } sdumc_gemm_desc;
 
 int sdumc_gemm(const sdumc_gemm_desc* d, void* stream);

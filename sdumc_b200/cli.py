@@ -61,7 +61,13 @@ def build_parser(inference: bool) -> argparse.ArgumentParser:
     p.add_argument('--synthetic_ragged', action='store_true', help='ragged synthetic lengths (padding semantics)')
     p.add_argument('--device_store', action='store_true',
                    help='keep the feature store in HBM and build batches with the collate kernel (no per-step H2D)')
-    p.add_argument('--folds', type=int, default=1, help='K-fold cross-validation over the train split (reference: 1)')
+    p.add_argument('--folds', type=int, default=1,
+                   help='K > 1: K-fold cross-validation over the train split (KFold, shuffle, random_state=--seed; a fresh '
+                        'model / optimizer / schedule per fold like the reference loop :295-321); 1 = the reference\'s '
+                        'single train/val/test run')
+    p.add_argument('--synthetic_frames', type=str, default=None, help='La,Lt,Lv,L4 of --synthetic (default S0: 384,64,256,64)')
+    p.add_argument('--synthetic_dims', type=str, default=None, help='Da,Dt,Dv,D4 of --synthetic (default S0: 1024,4096,1024,4096)')
+    p.add_argument('--no_dropout', action='store_true', help='train without dropout (deterministic parity runs)')
     p.add_argument('--checkpoint', type=str, default=None,
                    help='checkpoint with ["state_dict"] (inference; the reference hard-codes its path, ..._inference.py:341)')
     p.add_argument('--save_checkpoints', action='store_true', help='torch.save the best epochs (commented out in the reference :375)')
@@ -82,7 +88,8 @@ def _dist():
 def load_splits(args):
     from .dataset import Store4F, read_names_labels
     if args.synthetic:
-        dims, frames = (1024, 4096, 1024, 4096), (384, 64, 256, 64)
+        dims = tuple(int(x) for x in args.synthetic_dims.split(',')) if args.synthetic_dims else (1024, 4096, 1024, 4096)
+        frames = tuple(int(x) for x in args.synthetic_frames.split(',')) if args.synthetic_frames else (384, 64, 256, 64)
         mk = lambda n, seed: Store4F.synthetic(n, dims, frames, seed=seed, ragged=args.synthetic_ragged)  # noqa: E731
         return mk(args.synthetic, 1234), mk(max(args.batch_size, args.synthetic // 8), 4321), \
             mk(max(args.batch_size, args.synthetic // 8), 9876)
@@ -148,9 +155,14 @@ def make_trainer(args, stores, device, pg, state_dict=None):
     max_frames = tuple(max(s.max_frames[i] for s in stores) for i in range(4))
     w = (args.full_mse_loss_w, args.missing_mse_loss_w, args.text_feat_loss_w, args.text_query_feat_loss_w,
          args.features_loss_w, args.rnc_loss_w)
-    cap = max(args.batch_size + 1, 2)                         # +1: a trailing single sample joins the last batch
-    return Trainer(store.dims, cap, max_frames, device, lr=args.lr, weight_decay=args.l2, loss_w=w,
-                   seed=args.seed, process_group=pg, state_dict=state_dict, use_graph=True)
+    # +1 only when some split really ends with a single sample that joins its last batch (batch_chunks); the step is
+    # captured per recurring batch shape (Trainer.train_step), so regular batches replay a graph either way
+    merge = any(len(s) > args.batch_size and len(s) % args.batch_size == 1 for s in stores)
+    cap = max(args.batch_size + (1 if merge else 0), 2)
+    tr = Trainer(store.dims, cap, max_frames, device, lr=args.lr, weight_decay=args.l2, loss_w=w,
+                 seed=args.seed, process_group=pg, state_dict=state_dict, use_graph=True)
+    tr.train_dropout = not getattr(args, "no_dropout", False)
+    return tr
 
 
 def main_train(argv=None):
@@ -173,25 +185,36 @@ def main_train(argv=None):
         print('====== Training and Evaluation =======')
     best_valid = {'mae': 1.0, 'f1': 0}
     best_full, best_missing = {'mae': 1.0, 'f1': 0}, {'mae': 1.0, 'f1': 0}
-    for ii in range(args.folds):
+    if args.folds > 1:
+        from .dataset import kfold_indices
+        folds = [(train.subset(tr_i), train.subset(va_i)) for tr_i, va_i in kfold_indices(len(train), args.folds, args.seed)]
+    else:
+        folds = [(train, val)]
+    fold_val = []                                             # per fold: val MSE (full, missing) after the last epoch
+    saved = []
+    for ii, (train_f, val_f) in enumerate(folds):
         if rank == 0:
             print(f'>>>>> Cross-validation: training on the {ii+1} folder >>>>>')
             print('Step1: build model (each folder has its own model)')
         start = time.time()
         torch.manual_seed(args.seed + ii)
-        tr = make_trainer(args, (train, val, test), device, pg)
+        tr = make_trainer(args, (train_f, val_f, test), device, pg)
         if rank == 0:
             print('Step2: training (multiple epoches)')
+        vres = None
         for epoch in range(args.epochs):
             tr.set_lr(args.lr * lr_lambda(epoch))             # LambdaLR, stepped once per epoch (:318-321,:342)
             t0 = time.time()
-            tres = run_split(tr, train, args.batch_size, True, rank, world)
+            tres = run_split(tr, train_f, args.batch_size, True, rank, world)
             if rank == 0:
                 print('used: {} s'.format(time.time() - t0))
-            run_split(tr, val, args.batch_size, False, 0, 1)
+            vres = run_split(tr, val_f, args.batch_size, False, 0, 1)
             if rank == 0:
                 print('epoch:%d; train_val_mse_full:%.4f; train_val_mse_missing:%.4f' %
                       (epoch + 1, tres['val_mse_full'], tres['val_mse_missing']))
+                if args.folds > 1:
+                    print('epoch:%d; fold:%d; val_mse_full:%.4f; val_mse_missing:%.4f' %
+                          (epoch + 1, ii + 1, vres['val_mse_full'], vres['val_mse_missing']))
             te = run_split(tr, test, args.batch_size, False, 0, 1)
             r_full = eval_mosei_metric(te['val_preds_full'], te['val_labels'], te['names'])
             r_miss = eval_mosei_metric(te['val_preds_missing'], te['val_labels'], te['names'])
@@ -199,22 +222,28 @@ def main_train(argv=None):
                 best_full = dict(r_full, epoch=epoch)
                 if rank == 0:
                     print("***************better full**********************")
-                    if args.save_checkpoints:
-                        torch.save({'epoch': epoch + 1, 'state_dict': tr.state_dict()},
-                                   f'mosei_mult-view_kd_full_{best_full["mae"]}_{epoch+1}.pt')
+                    if args.save_checkpoints:                 # the reference's commented-out torch.save (:375)
+                        os.makedirs(args.save_root, exist_ok=True)
+                        path = os.path.join(args.save_root, f'mosei_mult-view_kd_full_{best_full["mae"]}_{epoch+1}.pt')
+                        torch.save(tr.checkpoint(epoch + 1), path)
+                        saved.append(path)
             if r_miss['mae'] <= best_missing['mae']:
                 best_missing = dict(r_miss, epoch=epoch)
                 if rank == 0:
                     print("===============better missing===================")
-                    if args.save_checkpoints:
-                        torch.save({'epoch': epoch + 1, 'state_dict': tr.state_dict()},
-                                   f'mosei_mult-view_kd_missing_{best_missing["mae"]}_{epoch+1}.pt')
+                    if args.save_checkpoints:                 # (:384)
+                        os.makedirs(args.save_root, exist_ok=True)
+                        path = os.path.join(args.save_root, f'mosei_mult-view_kd_missing_{best_missing["mae"]}_{epoch+1}.pt')
+                        torch.save(tr.checkpoint(epoch + 1), path)
+                        saved.append(path)
             if rank == 0:
                 print("test full:")
                 print(r_full)
                 print("test missing:")
                 print(r_miss)
                 print("-" * 50)
+        fold_val.append((vres['val_mse_full'], vres['val_mse_missing']) if vres else None)
+        tr.close()
         if rank == 0:
             print(f'>>>>> Finish: training on the {ii+1} data, duration: {time.time() - start} >>>>>')
     if rank == 0:
@@ -231,6 +260,8 @@ def main_train(argv=None):
                     f'--features_loss_w={args.features_loss_w} --rnc_loss_w={args.rnc_loss_w}\n')
             f.write(str(best_full) + '\n' + str(best_missing) + '\n')
         print(f'{args.audio_feature}+{args.text_feature}+{args.video_feature}')
+    return {"fold_val_mse": fold_val, "best_test_full": best_full, "best_test_missing": best_missing,
+            "checkpoints": saved}
 
 
 def main_inference(argv=None):

@@ -39,8 +39,6 @@ int sdumc_gemm(const sdumc_gemm_desc* d, void* stream) {
   sh.M = d->M; sh.N = d->N; sh.K = d->K;
   sh.a_mn = d->a_mn; sh.b_mn = d->b_mn;
   sh.k_splits = d->k_splits;
-  sh.dbg_lbo = d->dbg_lbo; sh.dbg_sbo = d->dbg_sbo;
-  sh.dbg_clk = reinterpret_cast<unsigned long long*>(d->dbg_clk);
   GemmEpi ep{};
   ep.kind = d->epi_kind;
   ep.bias = d->bias;

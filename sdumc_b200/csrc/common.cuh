@@ -28,6 +28,10 @@ enum : int {
 
 int set_error(int code, const char* fmt, ...);  // returns code; message via sdumc_last_error()
 
+constexpr int kMaxDevices = 64;
+int current_device();   // cudaGetDevice(), clamped to [0, kMaxDevices)
+int num_sms();          // SM count of the current device (cached per device)
+
 #define SDUMC_CHECK_ARG(cond, ...)                                   \
   do {                                                               \
     if (!(cond)) return ::sdumc::set_error(::sdumc::SDUMC_ERR_ARG, __VA_ARGS__); \

@@ -250,11 +250,12 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
   const size_t smem = (size_t)kFwdStages * kFwdTile + (size_t)2 * 8 * kFwdPitch * 2 + (size_t)a.L * 8 * 4;
   constexpr size_t kMaxDyn = 216 * 1024;
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "pool_fwd: L=%d too long for the shared-memory softmax", a.L);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!attr_done[dev]) {
     SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
     SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   if (a.nq == 1) pool_fwd_kernel<1><<<a.B, kFwdThreads, smem, stream>>>(a);
   else           pool_fwd_kernel<7><<<a.B, kFwdThreads, smem, stream>>>(a);
@@ -628,20 +629,15 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   const size_t smem = attn_bwd_smem(a.L);
   constexpr size_t kMaxDyn = 216 * 1024;   // + 9.1 KB static (dP exchange, db) stays under the 227 KB per-CTA limit
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!attr_done[dev]) {
     SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
     SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
-    attr_done = true;
-  }
-  static int num_sms = 0;
-  if (!num_sms) {
-    int dev = 0;
-    SDUMC_CUDA(cudaGetDevice(&dev));
-    SDUMC_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_done[dev] = true;
   }
   const long n_units = (long)a.B * ((a.L + kBwdRows - 1) / kBwdRows);
-  const int grid = (int)std::min<long>(n_units, num_sms);   // one resident CTA per SM (shared-memory bound)
+  const int grid = (int)std::min<long>(n_units, num_sms());   // one resident CTA per SM (shared-memory bound)
   if (a.nq == 1) attn_bwd_kernel<1><<<grid, kBwdThreads, smem, stream>>>(a);
   else           attn_bwd_kernel<7><<<grid, kBwdThreads, smem, stream>>>(a);
   SDUMC_CUDA(cudaGetLastError());
@@ -724,7 +720,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 int launch_colsum_bf16(const __nv_bfloat16* X, long ld, long rows, float* out, cudaStream_t stream) {
   SDUMC_CHECK_ARG(X && out && rows > 0 && ld % 8 == 0, "colsum_bf16: bad arguments");
   long blocks = (rows + 63) / 64;
-  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks > (long)num_sms() * 8) blocks = (long)num_sms() * 8;
   colsum_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, ld, rows, out);
   SDUMC_CUDA(cudaGetLastError());
   return 0;

@@ -109,28 +109,33 @@ void clear_tmap_cache() {
   g_tmaps.clear();
 }
 
-static int g_num_sms = 0;
+// per-device caches (a process may drive several GPUs): SM counts and "attribute already set" flags are indexed
+// by the current device; racing first calls write the same values
+int current_device() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+  return dev;
+}
 int num_sms() {
-  if (g_num_sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      g_num_sms = n;
-    else
-      g_num_sms = 148;
+  static int sms[kMaxDevices] = {0};
+  const int dev = current_device();
+  if (sms[dev] == 0) {
+    int n = 0;
+    sms[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
   }
-  return g_num_sms;
+  return sms[dev];
 }
 
 template <int kBlockN, bool kTF32, int kKind>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& sh, const GemmEpi& ep,
                        int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN>;
-  static bool attr_done = false;
+  static bool attr_done[kMaxDevices] = {false};
   auto kern = gemm_tcgen05_kernel<kBlockN, kTF32, kKind>;
-  if (!attr_done) {
+  const int dev = current_device();
+  if (!attr_done[dev]) {
     SDUMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, sh, ep);
   SDUMC_CUDA(cudaGetLastError());
@@ -199,9 +204,9 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
   int grid = (int)(tiles < sms ? tiles : sms);
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   // resident B: one N tile whose whole K extent fits beside an A-only ring, and at least two tiles per CTA to
-  // amortise it (bit 18 of dbg_sbo disables it for A/B timing)
+  // amortise it
   const int stages = block_n == 256 ? 4 : (block_n == 128 ? 6 : 8);
-  sh.b_res = (n_tiles == 1 && sh.k_splits == 1 && nkb <= stages && tiles >= 2L * grid && !((sh.dbg_sbo >> 16) & 4u)) ? 1 : 0;
+  sh.b_res = (n_tiles == 1 && sh.k_splits == 1 && nkb <= stages && tiles >= 2L * grid) ? 1 : 0;
 
   if (tf32) {
     SDUMC_CHECK_ARG(epi.kind == EPI_GENERIC, "gemm: tf32 operands support the generic epilogue only");

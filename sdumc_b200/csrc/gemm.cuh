@@ -68,9 +68,6 @@ struct GemmShape {
   int a_mn, b_mn;  // 0 = K-major, 1 = MN-major
   int k_splits;
   int b_res;       // 1: the whole B operand (one N tile, K <= kStages k-blocks) stays resident in shared memory
-  // debug overrides of the MN-major descriptor fields (0 = computed); see tests/test_gemm_gpu.py
-  uint32_t dbg_lbo, dbg_sbo;
-  unsigned long long* dbg_clk;  // bring-up: per-CTA cycle counters of the pipeline phases (nullptr in production)
 };
 
 
@@ -160,11 +157,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  if (sh.dbg_clk && threadIdx.x == 0) {   // bring-up: CTA start / end wall clock (ns), slots 13 / 14
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    sh.dbg_clk[blockIdx.x * 16 + 13] = t;
-  }
 
   const int m_tiles = (sh.M + 127) / 128;
   const int n_tiles = (sh.N + kBlockN - 1) / kBlockN;
@@ -221,9 +213,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
         const int kb1 = (int)(((long)(ks + 1) * nkb) / sh.k_splits);
         for (int kb = kb0; kb < kb1; ++kb) {
-          const long long tw0 = sh.dbg_clk ? clock64() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          if (sh.dbg_clk) sh.dbg_clk[blockIdx.x * 16 + 0] += clock64() - tw0;   // producer: waiting for a free stage
           uint8_t* sa = ring_base + stage * stage_stride;
           uint8_t* sb = sa + Cfg::kABytes;
           mbar_expect_tx(&full_bar[stage], b_res ? Cfg::kABytes : Cfg::kStageBytes);
@@ -252,8 +242,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     const uint32_t idesc = make_idesc(kFmt, (uint32_t)sh.a_mn, (uint32_t)sh.b_mn, (uint32_t)kBlockN);
-    const uint32_t mn_lbo = sh.dbg_lbo ? sh.dbg_lbo : (uint32_t)(kBlockK * 128);
-    const uint32_t mn_sbo = (sh.dbg_sbo & 0xffffu) ? (sh.dbg_sbo & 0xffffu) : 1024u;
+    const uint32_t mn_lbo = (uint32_t)(kBlockK * 128);
+    const uint32_t mn_sbo = 1024u;
     const uint32_t a_lbo = sh.a_mn ? mn_lbo : 16u, a_sbo = sh.a_mn ? mn_sbo : 1024u;
     const uint32_t b_lbo = sh.b_mn ? mn_lbo : 16u, b_sbo = sh.b_mn ? mn_sbo : 1024u;
     // descriptor start-address advance per UMMA_K step, in 16-byte units
@@ -270,15 +260,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int ks = t / (m_tiles * n_tiles);
       const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
       const int kb1 = (int)(((long)(ks + 1) * nkb) / sh.k_splits);
-      long long tm0 = sh.dbg_clk ? clock64() : 0;
       mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
-      if (sh.dbg_clk && lane == 0) sh.dbg_clk[blockIdx.x * 16 + 1] += clock64() - tm0;   // MMA: waiting for a drained accumulator
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * kBlockN);
       for (int kb = kb0; kb < kb1; ++kb) {
-        tm0 = sh.dbg_clk ? clock64() : 0;
         mbar_wait(&full_bar[stage], phase);
-        if (sh.dbg_clk && lane == 0) sh.dbg_clk[blockIdx.x * 16 + 2] += clock64() - tm0;  // MMA: waiting for TMA data
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = ring_u32 + (uint32_t)stage * stage_stride;
@@ -325,14 +311,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         bias_s[j] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.f;
         if (ctx_shared) ctx_s[j] = n < sh.N ? __ldg(ep.qv + n) : 0.f;
       }
-      const bool clk = sh.dbg_clk && ew == 0 && lane == 0;
-      long long te0 = sh.dbg_clk ? clock64() : 0;
       asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
-      if (clk) sh.dbg_clk[blockIdx.x * 16 + 4 + grp * 4] += clock64() - te0;   // epilogue: staging barrier
-      te0 = sh.dbg_clk ? clock64() : 0;
       mbar_wait(&tfull_bar[acc], acc_phase);
-      if (clk) sh.dbg_clk[blockIdx.x * 16 + 5 + grp * 4] += clock64() - te0;   // epilogue: waiting for the accumulator
-      te0 = sh.dbg_clk ? clock64() : 0;
       tc_fence_after();
       const int r0 = m_blk * 128 + ew * 32;  // first row of this warp's slab
       const int r = r0 + lane;
@@ -567,18 +547,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       // flight while chunk c is processed
       uint32_t bufA[32], bufB[32];
       uint32_t oldA[16], oldB[16];
-      const uint32_t dbg = sh.dbg_sbo >> 16;   // bring-up switches (tools/probe_gemm.py), 0 in production
-      if (dbg != 1) {
-        issue(0, bufA, oldA);
+      issue(0, bufA, oldA);
 #pragma unroll 1
-        for (int c = 0; c < NC; c += 2) {
-          tmem_ld_wait();
-          issue(c + 1, bufB, oldB);
-          if (dbg != 2) process(c, bufA, oldA);
-          tmem_ld_wait();
-          if (c + 2 < NC) issue(c + 2, bufA, oldA);
-          if (dbg != 2) process(c + 1, bufB, oldB);
-        }
+      for (int c = 0; c < NC; c += 2) {
+        tmem_ld_wait();
+        issue(c + 1, bufB, oldB);
+        process(c, bufA, oldA);
+        tmem_ld_wait();
+        if (c + 2 < NC) issue(c + 2, bufA, oldA);
+        process(c + 1, bufB, oldB);
       }
       if (kKind == KIND_KEYPROJ && row_ok) {
         float* srow = ep.scores + (long)r * ep.nq;
@@ -589,10 +566,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-      if (clk) {
-        sh.dbg_clk[blockIdx.x * 16 + 6 + grp * 4] += clock64() - te0;          // epilogue: draining one tile
-        sh.dbg_clk[blockIdx.x * 16 + 7 + grp * 4] += 1;                         // tiles
-      }
       acc_phase ^= 1u;
     }
   }
@@ -602,11 +575,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
-  }
-  if (sh.dbg_clk && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    sh.dbg_clk[blockIdx.x * 16 + 14] = t;
   }
 }
 

@@ -517,12 +517,13 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
 
   int n2 = 1;
   while (n2 < a.n) n2 <<= 1;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[kMaxDevices] = {false};
+  const int dev = current_device();
+  if (!attr_done[dev]) {
     SDUMC_CUDA(cudaFuncSetAttribute(rnc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRncMaxN * 8));
     SDUMC_CUDA(cudaFuncSetAttribute(rnc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     kRncMaxN * 20));
-    attr_done = true;
+    attr_done[dev] = true;
   }
   if (!a.reuse_sort) {   // a data-parallel rank calls once per anchor range with the same labels: sort once
     rnc_sort_kernel<<<1, 1024, (size_t)n2 * 8, stream>>>(a.labels, a.n, n2, perm, ys, pos);

@@ -44,6 +44,56 @@ def read_names_labels(label_path: str, split: str, debug: bool = False, exclude:
     return names, [float(corpus[n]["val"]) for n in names]
 
 
+def batch_chunks(n: int, batch_size: int, rank: int = 0, world: int = 1, lockstep: bool = False) -> List[List[int]]:
+    """Index lists of the batches `rank` processes, for a split of n utterances.
+
+    Single process / scoring: the reference's batches [i*bs, (i+1)*bs) in order (its train loader does not shuffle,
+    cmumosei.py:104-110), dealt round-robin to the ranks at whole-batch granularity (a sample's output depends on
+    its batch's padding) and never leaving a trailing batch of size 1 (the reference model crashes on B == 1).
+
+    lockstep=True (data-parallel training): every optimisation step is ONE global batch of world*bs consecutive
+    utterances cut into `world` equal shards, so all ranks take the same number of steps with the SAME shard size
+    (the all-gather / all-reduce buffers and the global normalisation B*world assume it).  The remainder after the
+    last full global batch becomes one more step of floor(remainder / world) utterances per rank when that is >= 2;
+    fewer than `world` (or, in that last case, 2*world) trailing utterances are dropped."""
+    if world > 1 and lockstep:
+        out: List[List[int]] = []
+        g = world * batch_size
+        full = n // g
+        for s in range(full):
+            lo = s * g + rank * batch_size
+            out.append(list(range(lo, lo + batch_size)))
+        rest = n - full * g
+        per = rest // world
+        if per >= 2:
+            lo = full * g + rank * per
+            out.append(list(range(lo, lo + per)))
+        return out
+    chunks = [list(range(b, min(n, b + batch_size))) for b in range(0, n, batch_size)]
+    if len(chunks) > 1 and len(chunks[-1]) == 1:
+        chunks[-2] += chunks[-1]
+        chunks.pop()
+    return [c for i, c in enumerate(chunks) if i % world == rank]
+
+
+def kfold_indices(n: int, n_splits: int, seed: int = 100):
+    """[(train_idx, val_idx)] * n_splits: sklearn.model_selection.KFold(n_splits, shuffle=True, random_state=seed)
+    semantics (a seeded permutation cut into n_splits contiguous folds, the first n % n_splits one larger), index
+    lists sorted so that batches keep the dataset order."""
+    rng = np.random.RandomState(seed)
+    perm = rng.permutation(n)
+    sizes = np.full(n_splits, n // n_splits, dtype=int)
+    sizes[: n % n_splits] += 1
+    out, cur = [], 0
+    for k in range(n_splits):
+        val = np.sort(perm[cur:cur + sizes[k]])
+        mask = np.ones(n, dtype=bool)
+        mask[val] = False
+        out.append((np.nonzero(mask)[0].tolist(), val.tolist()))
+        cur += sizes[k]
+    return out
+
+
 class Store4F:
     """Four per-utterance feature lists resident in pinned host memory (bf16) + labels."""
 
@@ -100,21 +150,16 @@ class Store4F:
             out[s] = buf
         return out, self.vals[list(idx)], [self.names[i] for i in idx]
 
+    def subset(self, idx: Sequence[int]) -> "Store4F":
+        """A store over the utterances idx (shares the feature tensors): one side of a cross-validation fold."""
+        idx = list(idx)
+        return Store4F({s: [self.feats[s][i] for i in idx] for s in STREAMS}, self.vals[idx].tolist(),
+                       [self.names[i] for i in idx])
+
     def batches(self, batch_size: int, rank: int = 0, world: int = 1, lockstep: bool = False) -> Iterator:
-        """Reference batches [i*bs, (i+1)*bs) in order (the reference train loader does not shuffle,
-        cmumosei.py:104-110), dealt round-robin to the ranks at whole-batch granularity (a sample's output
-        depends on its batch's padding), never leaving a trailing batch of size 1."""
-        n = len(self)
-        bounds = list(range(0, n, batch_size))
-        chunks = [list(range(b, min(n, b + batch_size))) for b in bounds]
-        if len(chunks) > 1 and len(chunks[-1]) == 1:        # the reference model crashes on B == 1 (SURVEY §7)
-            chunks[-2] += chunks[-1]
-            chunks.pop()
-        if world > 1 and lockstep:
-            chunks = chunks[: len(chunks) // world * world]  # every rank takes the same number of (collective) steps
-        for i, c in enumerate(chunks):
-            if i % world == rank:
-                yield self.collate(c)
+        """Collated batches of this rank (composition: batch_chunks)."""
+        for c in batch_chunks(len(self), batch_size, rank, world, lockstep):
+            yield self.collate(c)
 
 
 class DeviceStore4F:
@@ -124,6 +169,7 @@ class DeviceStore4F:
     bf16, far inside the 180 GB of a B200."""
 
     def __init__(self, store: Store4F, device):
+        self._ids: Optional[List[int]] = None          # subset(): local position -> utterance of the packed store
         self.names, self.vals_host = store.names, store.vals
         self.dims, self.max_frames = store.dims, store.max_frames
         self.device = torch.device(device)
@@ -137,21 +183,28 @@ class DeviceStore4F:
         self.vals = store.vals.to(self.device)
 
     def __len__(self):
-        return len(self.names)
+        return len(self.names) if self._ids is None else len(self._ids)
+
+    def subset(self, idx: Sequence[int]) -> "DeviceStore4F":
+        """A view over the utterances idx sharing the packed HBM tensors (cross-validation folds cost no memory)."""
+        import copy
+        sub = copy.copy(self)
+        base = self._ids if self._ids is not None else list(range(len(self.names)))
+        sub._ids = [base[i] for i in idx]
+        ml = tuple(max(self.lengths[s][u] for u in sub._ids) for s in STREAMS)
+        sub.max_frames = ml
+        return sub
+
+    def _global(self, local: Sequence[int]) -> List[int]:
+        return list(local) if self._ids is None else [self._ids[i] for i in local]
 
     def batch_frames(self, idx: Sequence[int]) -> Tuple[int, int, int, int]:
-        """Per-modality batch maximum = the padded length the reference collater would produce."""
+        """Per-modality batch maximum = the padded length the reference collater would produce (idx: utterance ids
+        of the packed store, as yielded by batches())."""
         return tuple(max(self.lengths[s][i] for i in idx) for s in STREAMS)
 
     def batches(self, batch_size: int, rank: int = 0, world: int = 1, lockstep: bool = False) -> Iterator:
-        """Same batch composition as Store4F.batches, yielding index lists (+ host labels, names)."""
-        n = len(self)
-        chunks = [list(range(b, min(n, b + batch_size))) for b in range(0, n, batch_size)]
-        if len(chunks) > 1 and len(chunks[-1]) == 1:
-            chunks[-2] += chunks[-1]
-            chunks.pop()
-        if world > 1 and lockstep:
-            chunks = chunks[: len(chunks) // world * world]
-        for i, c in enumerate(chunks):
-            if i % world == rank:
-                yield c, self.vals_host[c], [self.names[j] for j in c]
+        """Same batch composition as Store4F.batches, yielding utterance-id lists (+ host labels, names)."""
+        for c in batch_chunks(len(self), batch_size, rank, world, lockstep):
+            ids = self._global(c)
+            yield ids, self.vals_host[ids], [self.names[j] for j in ids]

@@ -24,8 +24,7 @@ def _ld(t: torch.Tensor) -> int:
 def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_mn=False, b_mn=False, k_splits=1,
          block_n=0, max_ctas=0, bias=None, act=ACT_NONE, gate=None, gate_scale=1.0, drop_p=0.0, drop_site=0,
          fmask_site=0, out_f32=None, f32_mode=OUT_STORE, out_bf16=None, bf16_mode=OUT_STORE, epi_kind=EPI_GENERIC,
-         targets=(), target_sites=(), qv=None, q_stride=0, nq=0, L=1, scores=None, seed=0, step=0, step_dev=None,
-         dbg_lbo=0, dbg_sbo=0, dbg_clk=None) -> None:
+         targets=(), target_sites=(), qv=None, q_stride=0, nq=0, L=1, scores=None, seed=0, step=0, step_dev=None) -> None:
     """C[M,N] = epilogue(op(A) op(B)) — tcgen05/TMA GEMM.
 
     A is stored [M,K] (a_mn=False) or [K,M]; B is stored [N,K] (b_mn=False, the nn.Linear weight
@@ -52,7 +51,6 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_mn=False
             d.ld_bf16 = _ld(t)
     d.qv, d.q_stride, d.nq, d.L, d.scores = ptr(qv), q_stride, nq, L, ptr(scores)
     d.seed, d.step, d.step_dev = seed, step, ptr(step_dev)
-    d.dbg_lbo, d.dbg_sbo, d.dbg_clk = dbg_lbo, dbg_sbo, ptr(dbg_clk)
     check(_lib.lib().sdumc_gemm(C.byref(d), current_stream()), "sdumc_gemm")
 
 

@@ -53,6 +53,10 @@ class Trainer:
             self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
         else:
             self.world, self.rank = 1, 0
+        # dropout counters index LOCAL rows, so data-parallel ranks fold their rank into the Philox key: the masks of
+        # the W shards are independent draws, like the W*B rows of a single-process batch (same seed on every rank
+        # would repeat the same mask pattern in every shard)
+        self.drop_seed = self.seed if self.world == 1 else (self.seed + 0x9E3779B97F4A7C15 * self.rank) & (2 ** 64 - 1)
         # the data-parallel step (NCCL all_gather / all_reduce inside) is captured too: NCCL collectives are graph
         # nodes like any kernel; SDUMC_DP_GRAPH=0 falls back to eager launches for debugging
         import os
@@ -97,20 +101,96 @@ class Trainer:
         self.cur_B = self.B
         self.train_dropout = True      # tests switch dropout off to compare against a deterministic reference
         self.n_steps = 0
-        self._graph = None
+        # captured steps, keyed by the batch shape (utterances, frames per stream): a graph replays a fixed shape, so
+        # every shape that recurs (the full-capacity batch; the fixed trailing batch of an epoch; length buckets) gets
+        # its own graph the second time it is seen.  Least-recently-used graphs are dropped beyond `max_graphs`
+        # (each holds its own activation pool).
+        self.max_graphs = 4
+        self._graphs: Dict[tuple, dict] = {}
+        self._score_graphs: Dict[tuple, dict] = {}
+        self._seen: Dict[tuple, int] = {}
         self._outputs = None
-        self._score_graph, self._score_out, self._score_calls = None, None, 0
+        self._score_calls = 0
 
     # ---- parameters ------------------------------------------------------------------------
-    def load_state_dict(self, sd: Dict[str, torch.Tensor]):
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], strict: bool = False):
+        """Loads parameters by name.  Keys may carry the `model.` prefix of get_models() (toolkit/models/__init__.py)
+        and / or DataParallel's `module.` (stripped like main_frame_val_text_missing_inference.py:341).  Returns
+        (missing, unexpected) like nn.Module.load_state_dict; raises if NOTHING matched (a silently random model is
+        never what the caller wants) or, with strict=True, if anything is missing / unexpected."""
+        norm = {}
+        for k, v in sd.items():
+            k2 = k.replace("module.", "")
+            if k2.startswith("model."):
+                k2 = k2[len("model."):]
+            norm[k2] = v
+        missing = [n for n in self.layout.names if n not in norm]
+        unexpected = [k for k in norm if k not in self.layout.entries]
+        if norm and len(missing) == len(self.layout.names):
+            raise _lib.SdumcError("load_state_dict: no key of the checkpoint matches a model parameter "
+                                  f"(first keys: {list(sd)[:3]})")
+        if strict and (missing or unexpected):
+            raise _lib.SdumcError(f"load_state_dict(strict): missing {missing[:5]}, unexpected {unexpected[:5]}")
         for name in self.layout.names:
-            key = name if name in sd else "model." + name      # get_models() prefixes keys with `model.`
-            if key in sd:
-                self.layout.view(self.master, name).copy_(sd[key].to(self.device, torch.float32))
+            if name in norm:
+                src = norm[name]
+                if tuple(src.shape) != tuple(self.layout.entries[name].shape):
+                    raise _lib.SdumcError(f"load_state_dict: {name} has shape {tuple(src.shape)}, expected "
+                                          f"{tuple(self.layout.entries[name].shape)}")
+                self.layout.view(self.master, name).copy_(src.to(self.device, torch.float32))
         self.W.refresh_shadow()
+        return missing, unexpected
 
-    def state_dict(self) -> Dict[str, torch.Tensor]:
-        return {name: self.layout.view(self.master, name).clone() for name in self.layout.names}
+    def state_dict(self, prefix: str = "") -> Dict[str, torch.Tensor]:
+        """Parameters by reference name; prefix='model.' gives the keys of get_models(args).state_dict()."""
+        return {prefix + name: self.layout.view(self.master, name).clone() for name in self.layout.names}
+
+    def optimizer_state_dict(self) -> dict:
+        """torch.optim.Adam.state_dict() layout over model.parameters() in registration order (the reference's
+        optimizer, main_frame_val_text_missing.py:317): parameters that never receive a gradient have no state."""
+        from .params import is_live
+        step = float(int(self.step_dev.item()))
+        state = {}
+        for i, name in enumerate(self.layout.names):
+            if is_live(name) and step > 0:
+                state[i] = {"step": torch.tensor(step), "exp_avg": self.layout.view(self.m, name).clone().cpu(),
+                            "exp_avg_sq": self.layout.view(self.v, name).clone().cpu()}
+        group = {"lr": self.lr, "betas": (0.9, 0.999), "eps": 1e-8, "weight_decay": self.weight_decay,
+                 "amsgrad": False, "maximize": False, "foreach": None, "capturable": False, "differentiable": False,
+                 "fused": None, "params": list(range(len(self.layout.names)))}
+        return {"state": state, "param_groups": [group]}
+
+    def load_optimizer_state_dict(self, osd: dict):
+        """Restores Adam's moments and step count (so a resumed run continues the bias correction and the dropout
+        stream where the saved one stopped)."""
+        from .params import is_live
+        step = 0
+        self.m.zero_()
+        self.v.zero_()
+        for i, name in enumerate(self.layout.names):
+            st_ = osd["state"].get(i)
+            if st_ is None or not is_live(name):
+                continue
+            self.layout.view(self.m, name).copy_(st_["exp_avg"].to(self.device, torch.float32))
+            self.layout.view(self.v, name).copy_(st_["exp_avg_sq"].to(self.device, torch.float32))
+            step = max(step, int(float(st_["step"])))
+        self.step_dev.fill_(step)
+        if osd.get("param_groups"):
+            g = osd["param_groups"][0]
+            self.weight_decay = float(g.get("weight_decay", self.weight_decay))
+            self.set_lr(float(g.get("lr", self.lr)))
+
+    def checkpoint(self, epoch: int) -> dict:
+        """The dict the reference saves (commented out at main_frame_val_text_missing.py:375):
+        {'epoch', 'state_dict' (keys of get_models().state_dict(), i.e. `model.`-prefixed), 'optimizer'}."""
+        return {"epoch": int(epoch), "state_dict": {k: v.cpu() for k, v in self.state_dict("model.").items()},
+                "optimizer": self.optimizer_state_dict()}
+
+    def load_checkpoint(self, ck: dict, strict: bool = False):
+        out = self.load_state_dict(ck["state_dict"], strict=strict)
+        if "optimizer" in ck:
+            self.load_optimizer_state_dict(ck["optimizer"])
+        return out
 
     def set_lr(self, lr: float):
         self.lr = float(lr)
@@ -216,8 +296,8 @@ class Trainer:
     # ---- the step --------------------------------------------------------------------------
     def _forward(self, dropout: bool, need_grad: bool):
         b = self.cur_B
-        cfg = Cfg(B=b, n_pass=2, frames=dict(self.cur_frames), dropout=dropout, need_grad=need_grad, seed=self.seed,
-                  step=0, step_dev=self.step_dev)
+        cfg = Cfg(B=b, n_pass=2, frames=dict(self.cur_frames), dropout=dropout, need_grad=need_grad,
+                  seed=self.drop_seed, step=0, step_dev=self.step_dev)
         return self.engine.forward(self.W, self.inputs, cfg)
 
     def _loss_and_seeds(self, st):
@@ -272,28 +352,79 @@ class Trainer:
                  p_bf16=self.shadow, n=n, step_dev=self.step_dev, lr_dev=self.lr_dev)
         self._outputs = Engine.outputs(st)
 
+    def _shape_key(self):
+        return (self.cur_B, tuple(self.cur_frames[k] for k in ("a", "t0", "v", "t1")), self.train_dropout)
+
+    def _full_key(self):
+        return (self.B, tuple(self.frames[k] for k in ("a", "t0", "v", "t1")), self.train_dropout)
+
+    def _cache_put(self, cache, key, entry):
+        cache[key] = entry
+        while len(cache) > self.max_graphs:            # dicts iterate in insertion order: the first key is the LRU one
+            cache.pop(next(iter(cache)))
+
+    @staticmethod
+    def _cache_touch(cache, key):
+        cache[key] = cache.pop(key)
+
     def train_step(self):
         """One optimisation step on the batch currently in the static buffers.  Returns nothing; read
-        `terms` (device tensor: 6 loss terms + total) and `predictions()` when needed."""
-        full = self.cur_B == self.B and self.cur_frames == self.frames
-        if not self.use_graph or self.n_steps == 0 or not full:
-            self._step_body()          # first step (one-time kernel attribute setup) and smaller batches run eagerly
-        elif self._graph is None:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):   # capture does not execute ...
-                self._step_body()
-            self._graph = g
-            self._graph.replay()        # ... so this replay is the step
+        `terms` (device tensor: 6 loss terms + total) and `predictions()` when needed.
+
+        The first step of a trainer runs eagerly (one-time kernel attribute setup).  After that a batch shape is
+        captured into a CUDA graph the second time it is seen (the full-capacity shape: immediately) and replayed
+        from then on; shapes seen once (ragged real-data batches) run the same kernels eagerly."""
+        key = self._shape_key()
+        ent = self._graphs.get(key)
+        if ent is not None:
+            self._cache_touch(self._graphs, key)
+            ent["graph"].replay()
+            self._outputs = ent["outputs"]               # the replay refreshed THESE tensors (not an eager step's)
         else:
-            self._graph.replay()
+            seen = self._seen.get(key, 0)
+            self._seen[key] = seen + 1
+            if self.world > 1 and seen == 0:
+                self._check_equal_shards()
+            capture = self.use_graph and self.n_steps > 0 and (key == self._full_key() or seen >= 1)
+            if not capture:
+                self._step_body()
+            else:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):   # capture does not execute ...
+                    self._step_body()
+                self._cache_put(self._graphs, key, {"graph": g, "outputs": self._outputs})
+                g.replay()                  # ... so this replay is the step
         self.n_steps += 1
+
+    def _check_equal_shards(self):
+        """Data-parallel steps need the same shard size on every rank (all-gather counts, the B*world normalisation,
+        the anchor ranges of the global RnC).  Checked once per new batch shape; a mismatch would otherwise hang or
+        corrupt the collectives."""
+        import torch.distributed as dist
+        t = torch.tensor([self.cur_B, -self.cur_B], dtype=torch.int64, device=self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.pg)
+        hi, lo = int(t[0].item()), -int(t[1].item())
+        if hi != lo:
+            raise _lib.SdumcError(f"data-parallel step with unequal shards: this rank has {self.cur_B} utterances, the "
+                                  f"ranks range over [{lo}, {hi}]; use dataset.batch_chunks(lockstep=True)")
+
+    @property
+    def _graph(self):
+        """The captured full-capacity step (None until it exists)."""
+        for tr_drop in (True, False):
+            ent = self._graphs.get(self._full_key()[:2] + (tr_drop,))
+            if ent is not None:
+                return ent["graph"]
+        return None
 
     def close(self):
         """Drops the captured graph (it holds NCCL kernels of the process group in the data-parallel case) and
         drains the device; call before torch.distributed.destroy_process_group()."""
         torch.cuda.synchronize(self.device)
-        self._graph = self._score_graph = self._score_out = None
+        self._graphs.clear()
+        self._score_graphs.clear()
+        self._outputs = None
         torch.cuda.synchronize(self.device)
 
     def predictions(self):
@@ -314,16 +445,24 @@ class Trainer:
         """Both passes in eval mode on the batch in the static buffers.  Returns the dict of device tensors
         the inference CLI collects: predictions + the 4 embeddings of each pass.  Full-size batches replay a
         captured CUDA graph (~100 launches per batch otherwise dominate at the reference's inference batch of
-        128): the returned tensors are then overwritten by the next score() call - copy what must survive."""
-        full = self.cur_B == self.B and self.cur_frames == self.frames
-        if not self.use_graph or not full or self._score_calls == 0:
-            self._score_calls += 1
+        128): the returned tensors are then overwritten by the next score() call on the same batch shape - copy what
+        must survive.  Other recurring shapes get their own graph like train_step()."""
+        key = self._shape_key()[:2]
+        ent = self._score_graphs.get(key)
+        if ent is not None:
+            self._cache_touch(self._score_graphs, key)
+            ent["graph"].replay()
+            return ent["outputs"]
+        seen = self._seen.get(("score",) + key, 0)
+        self._seen[("score",) + key] = seen + 1
+        self._score_calls += 1
+        capture = self.use_graph and self._score_calls > 1 and (key == self._full_key()[:2] or seen >= 1)
+        if not capture:
             return self._score_body()
-        if self._score_graph is None:
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self._score_out = self._score_body()
-            self._score_graph = g
-        self._score_graph.replay()
-        return self._score_out
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self._score_body()
+        self._cache_put(self._score_graphs, key, {"graph": g, "outputs": out})
+        g.replay()
+        return out

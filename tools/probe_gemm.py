@@ -51,7 +51,7 @@ def run_case(name: str) -> dict:
         bias = torch.randn(N, device=dev) if ks == 1 else None
         out = torch.zeros(M, N, device=dev)
         ops.gemm(A, B, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, k_splits=ks, block_n=bn, bias=bias, out_f32=out,
-                 f32_mode=ops.OUT_ATOMIC if ks > 1 else ops.OUT_STORE, dbg_lbo=lbo, dbg_sbo=sbo)
+                 f32_mode=ops.OUT_ATOMIC if ks > 1 else ops.OUT_STORE)
         torch.cuda.synchronize()
         ref = ref_mm(A, B, a_mn, b_mn)
         if dt == torch.float32:  # tf32 truncation of the operands
@@ -142,11 +142,9 @@ def run_case(name: str) -> dict:
         outf = torch.zeros(M, N, device=dev) if ks > 1 else None
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-        clk = torch.zeros(148, 16, dtype=torch.int64, device=dev)
-
-        def go(c=None):
+        def go():
             ops.gemm(A, B, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, k_splits=ks, out_bf16=None if noout else outb,
-                     out_f32=None if noout else outf, block_n=bn, dbg_sbo=dbg << 16, dbg_clk=c,
+                     out_f32=None if noout else outf, block_n=bn,
                      f32_mode=ops.OUT_ATOMIC if ks > 1 else ops.OUT_STORE)
         for _ in range(3):
             go()
@@ -164,18 +162,6 @@ def run_case(name: str) -> dict:
         res["ms"] = ms
         res["tflops"] = 2.0 * M * N * K / ms / 1e9
         res["gbs"] = (A.numel() * 2 + B.numel() * 2 + M * N * (2 if ks == 1 else 4)) / ms / 1e6
-        go(clk)
-        torch.cuda.synchronize()
-        cm = clk.float().mean(0).tolist()
-        t0, t1 = clk[:, 13].double(), clk[:, 14].double()
-        live = t1 > 0
-        if bool(live.any()):
-            res["wall_us"] = {"span": float((t1[live].max() - t0[live].min()) / 1e3),
-                              "cta_mean": float((t1[live] - t0[live]).mean() / 1e3),
-                              "start_skew": float((t0[live].max() - t0[live].min()) / 1e3)}
-        res["clk"] = {"prod_wait_empty": cm[0], "mma_wait_tempty": cm[1], "mma_wait_full": cm[2],
-                      "epi0_bar": cm[4], "epi0_wait_tfull": cm[5], "epi0_drain": cm[6], "epi0_tiles": cm[7],
-                      "epi1_wait_tfull": cm[9], "epi1_drain": cm[10], "epi1_tiles": cm[11]}
         res["ok"] = True
     elif kind == "timeepi":
         # timeepi:inproj:<ntgt>:<K>  |  timeepi:keyproj:<nq>:<store_k>
