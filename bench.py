@@ -30,10 +30,17 @@ sys.path.insert(0, str(ROOT))
 METRIC = "train_samples_per_sec"
 UNIT = "samples/s"
 F_TRAIN_PER_SAMPLE = 2.408e9      # algorithmic FLOPs / sample of the S0 train step
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures
-# (profiles/r1_gemm_inproj_full.md, profiles/r1_attn_bwd_full.md); None until measured
-TRAFFIC_INPROJ_BYTES = 757_918_720      # 406.6 MB read + 351.3 MB written (4 x 100.7 MB copies partly still in L2)
-TRAFFIC_ATTN_BWD_BYTES = 383_883_520    # 226.3 MB read + 157.6 MB written
+F_INFER_PER_SAMPLE = 1.004e9      # ... of the two-pass scoring forward
+
+
+def measured_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch, read from this round's `ncu --set full` captures
+    (profiles/r2_traffic.json, written by tools/ncu_summary.py from the .ncu-rep files); {} until captured."""
+    p = ROOT / "profiles" / "r2_traffic.json"
+    try:
+        return json.loads(p.read_text())
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 def load_peaks():
@@ -242,8 +249,31 @@ def run_ours(args):
     ms_score = max_over_ranks(e0.elapsed_time(e1)) / args.steps
     trace("scoring timing done")
 
-    # ---- dominant kernels alone (flushed L2 between launches, CUDA events on the launching stream) ----
-    roof = None
+    # ---- scoring at BASELINE config 5's batch (B = 128, shell/main_text_missing_icassp_inference.sh:5) ----
+    Bs = 128
+    tr.load_batch(*(batch[k][:Bs] for k in ("audio", "text", "video", "feat4")), batch["vals"][:Bs])
+    for _ in range(3):
+        tr.score()
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        tr.score()
+    e1.record()
+    barrier()
+    ms_score128 = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    tr.load_batch(batch["audio"], batch["text"], batch["video"], batch["feat4"], batch["vals"])
+
+    # ---- roofline: the step is bounded by the tensor cores (99 % of its FLOPs are dense
+    #      contractions; ideal-fusion intensity ~1000 FLOP/B vs a ridge of ~213); the headline fraction is the whole
+    #      step's algorithmic FLOPs over the SUSTAINED measured bf16 peak.  Beside it, the dominant kernels timed alone
+    #      (L2 flushed between launches, CUDA events on the launching stream) against the burst peaks, each with §8d's
+    #      algorithmic bytes (inputs once + outputs once) and, separately, the bytes this design really moves. ----
+    traffic = measured_traffic()
+    step_tf = value / world * F_TRAIN_PER_SAMPLE / 1e12
+    roof = {"bound": "tensor", "kernel": "whole train step (all kernels of one CUDA-graph replay)",
+            "achieved": step_tf, "peak": peaks["tc_sustained"], "unit": "TFLOP/s", "frac": step_tf / peaks["tc_sustained"],
+            "traffic": traffic.get("step"), "algorithmic_flops_per_sample": F_TRAIN_PER_SAMPLE,
+            "peak_source": peaks["src"] + " (sustained: measured inside a long step)"}
     roof_extra = []
     if rank == 0:
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
@@ -262,55 +292,21 @@ def run_ours(args):
                 ts.append(a.elapsed_time(b_))
             return sum(ts) / len(ts)
 
-        # (1) the largest single launch of the step: the audio in-projection GEMM as the train step runs it -
-        #     tcgen05 bf16 [B*384,1024] x [1024,256], epilogue writes the 4 frame-dropout copies (2 blocks x 2 passes).
-        #     Arithmetic intensity 128 FLOP/B is below the ridge (peak TF / peak GB/s ~ 250): HBM-bound.
+        def entry(kernel, ms, flops, alg_bytes, design_bytes, key):
+            tf, gbs = flops / (ms * 1e-3) / 1e12, alg_bytes / (ms * 1e-3) / 1e9
+            return {"kernel": kernel, "ms_per_launch": ms, "bound": "tensor" if flops / alg_bytes > peaks["tc_burst"] * 1e3 / peaks["hbm"] else "hbm",
+                    "tensor_tflops": tf, "tensor_frac": tf / peaks["tc_burst"], "algorithmic_bytes": alg_bytes,
+                    "hbm_gbs": gbs, "hbm_frac": gbs / peaks["hbm"], "design_bytes": design_bytes,
+                    "design_hbm_frac": design_bytes / (ms * 1e-3) / 1e9 / peaks["hbm"], "traffic": traffic.get(key),
+                    "peak_source": peaks["src"] + " (burst: kernel timed alone)"}
+
         La, Da = S0_FRAMES[0], S0_DIMS[0]
-        X = tr.inputs["a"].view(B * La, Da)
+        rows = B * La
+        X = tr.inputs["a"].view(rows, Da)
         Wt = tr.W.bf16("frame_dim_reshape_0.weight")
         bias = tr.W.f32("frame_dim_reshape_0.bias")
-        tg = [torch.empty(B * La, 256, dtype=torch.bfloat16, device=dev) for _ in range(4)]
-
-        def go_inproj():
-            ops.gemm(X, Wt, M=B * La, N=256, K=Da, bias=bias, epi_kind=ops.EPI_INPROJ, targets=tg,
-                     target_sites=[1, 2, 3, 4], seed=5, step=1)
-        ms_k = time_alone(go_inproj)
-        nbytes = X.numel() * 2 + Wt.numel() * 2 + sum(t.numel() * 2 for t in tg)
-        flops = 2.0 * B * La * 256 * Da
-        gbs = nbytes / (ms_k * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "gemm_tcgen05_kernel<256,bf16,INPROJ> (audio in-projection, 4 dropout copies)",
-                "achieved": gbs, "peak": peaks["hbm"], "unit": "GB/s", "frac": gbs / peaks["hbm"],
-                "traffic": TRAFFIC_INPROJ_BYTES, "algorithmic_bytes": nbytes,
-                "peak_source": peaks["src"] + " (burst: kernel timed alone)", "ms_per_launch": ms_k,
-                "tensor_tflops": flops / (ms_k * 1e-3) / 1e12,
-                "tensor_frac": flops / (ms_k * 1e-3) / 1e12 / peaks["tc_burst"],
-                "step_tensor_frac": value / world * F_TRAIN_PER_SAMPLE / (peaks["tc_sustained"] * 1e12)}
-        del tg
-        # (2) the largest kernel family by step share: the attention backward (7 queries, audio): reads X' and K,
-        #     writes dZ and dH, 4 x [B*384,256] bf16
-        rows = B * La
-        Xp = torch.randn(rows, 256, device=dev).bfloat16()
-        Kt = torch.tanh(torch.randn(rows, 256, device=dev)).bfloat16()
-        Pm = torch.softmax(torch.randn(B, La, 7, device=dev), dim=1).reshape(rows, 7).contiguous()
-        dOut = torch.randn(B, 7, 256, device=dev)
-        Opre = torch.randn(B, 7, 256, device=dev)
-        Qp = torch.randn(B, 7, 256, device=dev) * 0.5
-        dZ = torch.empty(rows, 256, dtype=torch.bfloat16, device=dev)
-        dH = torch.empty(rows, 256, dtype=torch.bfloat16, device=dev)
-        dQp = torch.zeros(B, 7, 256, device=dev)
-        db = torch.zeros(256, device=dev)
-
-        def go_attn():
-            ops.attn_bwd(Xp, Kt, Pm, dOut, dout_stride_b=7 * 256, O_pre=Opre, Qp=Qp, qp_stride_b=7 * 256, B=B, L=La, nq=7,
-                         out_drop_p=0.5, out_site=3, dZ=dZ, dH=dH, dh_mode=0, fmask_site=2, dQp=dQp,
-                         dqp_stride_b=7 * 256, db=db, seed=5, step=1)
-        ms_a = time_alone(go_attn)
-        nb_a = 4 * rows * 256 * 2 + Pm.numel() * 4 + 4 * B * 7 * 256 * 4
-        roof_extra.append({"bound": "hbm", "kernel": "attn_bwd_kernel<7> (audio Cross_Attention backward)",
-                           "achieved": nb_a / (ms_a * 1e-3) / 1e9, "peak": peaks["hbm"], "unit": "GB/s",
-                           "frac": nb_a / (ms_a * 1e-3) / 1e9 / peaks["hbm"], "traffic": TRAFFIC_ATTN_BWD_BYTES,
-                           "algorithmic_bytes": nb_a, "ms_per_launch": ms_a})
-        del Xp, Kt, Pm, dZ, dH
+        for extra in bench_kernel_probes(tr, ops, torch, dev, B, La, Da, rows, X, Wt, bias, time_alone, entry):
+            roof_extra.append(extra)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -336,7 +332,16 @@ def run_ours(args):
             "gpu_launches_per_step": launches,
             "clocks": clk.summary(),
             "scoring": {"value": world * B / (ms_score * 1e-3), "unit": "samples/s", "ms_per_batch": ms_score,
-                        "note": "two eval passes per sample, CUDA-graph replay, inputs resident"},
+                        "note": "two eval passes per sample, CUDA-graph replay, inputs resident",
+                        "roofline": {"bound": "tensor", "achieved": B / (ms_score * 1e-3) * F_INFER_PER_SAMPLE / 1e12,
+                                     "peak": peaks["tc_sustained"], "unit": "TFLOP/s",
+                                     "frac": B / (ms_score * 1e-3) * F_INFER_PER_SAMPLE / 1e12 / peaks["tc_sustained"]}},
+            "scoring_b128": {"value": world * Bs / (ms_score128 * 1e-3), "unit": "samples/s", "ms_per_batch": ms_score128,
+                             "note": "BASELINE config 5 batch size (128 utterances per batch and GPU), two eval passes, "
+                                     "CUDA-graph replay, inputs resident",
+                             "roofline": {"bound": "tensor", "achieved": Bs / (ms_score128 * 1e-3) * F_INFER_PER_SAMPLE / 1e12,
+                                          "peak": peaks["tc_sustained"], "unit": "TFLOP/s",
+                                          "frac": Bs / (ms_score128 * 1e-3) * F_INFER_PER_SAMPLE / 1e12 / peaks["tc_sustained"]}},
             "roofline": roof,
             "roofline_extra": roof_extra,
             "cpu_baseline": cpu,
@@ -348,6 +353,44 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def bench_kernel_probes(tr, ops, torch, dev, B, La, Da, rows, X, Wt, bias, time_alone, entry):
+    """The frame-level kernels of the audio stream (196,608 rows at B = 512) as the train step runs them."""
+    G = 256
+    h = rows * G * 2                                            # one bf16 [rows,256] tensor
+    out = []
+    # (1) in-projection X W^T + b with the frame-dropout copies of the 2 blocks x 2 passes that consume it.
+    #     §8d algorithmic bytes: X once + W + H once; design bytes: the copies actually written.
+    tg = [torch.empty(rows, G, dtype=torch.bfloat16, device=dev) for _ in range(4)]
+    ms = time_alone(lambda: ops.gemm(X, Wt, M=rows, N=G, K=Da, bias=bias, epi_kind=ops.EPI_INPROJ, targets=tg,
+                                     target_sites=[1, 2, 3, 4], seed=5, step=1))
+    out.append(entry("gemm_tcgen05_kernel<256,bf16,INPROJ> (audio in-projection, train mode)", ms, 2.0 * rows * G * Da,
+                     X.numel() * 2 + Wt.numel() * 2 + h, X.numel() * 2 + Wt.numel() * 2 + 4 * h, "inproj"))
+    del tg
+    # (2) the K = 256 frame GEMM family (33 % of the round-1 step): Cross_Attention key projection tanh(X' W^T + b)
+    Xp = torch.randn(rows, G, device=dev).bfloat16()
+    Wk = tr.W.bf16("cross_att_fra2utt_0.input_proj.weight")
+    bk = tr.W.f32("cross_att_fra2utt_0.input_proj.bias")
+    Kt = torch.empty(rows, G, dtype=torch.bfloat16, device=dev)
+    ms = time_alone(lambda: ops.gemm(Xp, Wk, M=rows, N=G, K=G, bias=bk, act=ops.ACT_TANH, out_bf16=Kt))
+    out.append(entry("gemm_tcgen05_kernel<256,bf16,GENERIC> (audio key projection, K = 256)", ms, 2.0 * rows * G * G,
+                     2 * h + Wk.numel() * 2, 2 * h + Wk.numel() * 2, "keyproj"))
+    # (3) attention backward, 7 queries: reads X' and K, writes dZ and dH
+    Kt.copy_(torch.tanh(torch.randn(rows, G, device=dev)).bfloat16())
+    Pm = torch.softmax(torch.randn(B, La, 7, device=dev), dim=1).reshape(rows, 7).contiguous()
+    dOut, Opre = torch.randn(B, 7, G, device=dev), torch.randn(B, 7, G, device=dev)
+    Qp = torch.randn(B, 7, G, device=dev) * 0.5
+    dZ = torch.empty(rows, G, dtype=torch.bfloat16, device=dev)
+    dH = torch.empty(rows, G, dtype=torch.bfloat16, device=dev)
+    dQp, db = torch.zeros(B, 7, G, device=dev), torch.zeros(G, device=dev)
+    ms = time_alone(lambda: ops.attn_bwd(Xp, Kt, Pm, dOut, dout_stride_b=7 * G, O_pre=Opre, Qp=Qp, qp_stride_b=7 * G, B=B,
+                                         L=La, nq=7, out_drop_p=0.5, out_site=3, dZ=dZ, dH=dH, dh_mode=0, fmask_site=2,
+                                         dQp=dQp, dqp_stride_b=7 * G, db=db, seed=5, step=1))
+    nb = 4 * h + Pm.numel() * 4 + 4 * B * 7 * G * 4
+    out.append(entry("attn_bwd_kernel<7> (audio Cross_Attention backward, row-wise part)", ms, 2.0 * rows * 4 * 8 * G, nb, nb,
+                     "attn_bwd"))
+    return out
 
 
 def main():

@@ -192,6 +192,7 @@ def main_train(argv=None):
         folds = [(train, val)]
     fold_val = []                                             # per fold: val MSE (full, missing) after the last epoch
     saved = []
+    n_steps = n_replays = 0
     for ii, (train_f, val_f) in enumerate(folds):
         if rank == 0:
             print(f'>>>>> Cross-validation: training on the {ii+1} folder >>>>>')
@@ -243,6 +244,7 @@ def main_train(argv=None):
                 print(r_miss)
                 print("-" * 50)
         fold_val.append((vres['val_mse_full'], vres['val_mse_missing']) if vres else None)
+        n_steps, n_replays = n_steps + tr.n_steps, n_replays + tr.n_replays
         tr.close()
         if rank == 0:
             print(f'>>>>> Finish: training on the {ii+1} data, duration: {time.time() - start} >>>>>')
@@ -261,7 +263,7 @@ def main_train(argv=None):
             f.write(str(best_full) + '\n' + str(best_missing) + '\n')
         print(f'{args.audio_feature}+{args.text_feature}+{args.video_feature}')
     return {"fold_val_mse": fold_val, "best_test_full": best_full, "best_test_missing": best_missing,
-            "checkpoints": saved}
+            "checkpoints": saved, "train_steps": n_steps, "graph_replays": n_replays}
 
 
 def main_inference(argv=None):

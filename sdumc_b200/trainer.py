@@ -32,6 +32,20 @@ def lr_lambda(epoch: int, warm_up_epochs: int = 5, gamma: float = 0.9, stepsize:
     return (epoch + 1) / warm_up_epochs if epoch < warm_up_epochs else gamma ** ((epoch + 1 - warm_up_epochs) // stepsize)
 
 
+def default_state_dict(layout: ParamLayout) -> Dict[str, torch.Tensor]:
+    """Fresh parameters drawn from torch's global CPU generator with the initialisers of the reference's layers
+    (model.WengnetMOSEIMultViewsTextMissing._init_tensor): what `get_models(args)` would hold after construction."""
+    from .model import WengnetMOSEIMultViewsTextMissing
+    sd = {}
+    for name, shape in layout.spec:
+        sd[name] = WengnetMOSEIMultViewsTextMissing._init_tensor(name, shape)
+    for name, shape in layout.spec:   # biases need fan_in of their weight
+        if name.endswith(".bias") and not name.startswith("layer_normali"):
+            bound = 1.0 / (sd[name[:-5] + ".weight"].shape[1] ** 0.5)
+            sd[name] = torch.empty(shape).uniform_(-bound, bound)
+    return sd
+
+
 class Trainer:
     """Owns the flat parameter / gradient / Adam buffers and static batch buffers of one rank."""
 
@@ -68,14 +82,7 @@ class Trainer:
         self.W = Weights(L, self.master, self.shadow, self.grads)
         self.engine = Engine(L, dev)
         if state_dict is None:
-            from .model import WengnetMOSEIMultViewsTextMissing
-            state_dict = {}
-            for name, shape in L.spec:
-                state_dict[name] = WengnetMOSEIMultViewsTextMissing._init_tensor(name, shape)
-            for name, shape in L.spec:   # biases need fan_in of their weight
-                if name.endswith(".bias") and not name.startswith("layer_normali"):
-                    bound = 1.0 / (state_dict[name[:-5] + ".weight"].shape[1] ** 0.5)
-                    state_dict[name] = torch.empty(shape).uniform_(-bound, bound)
+            state_dict = default_state_dict(L)
         self.load_state_dict(state_dict)
         Da, Dt, Dv = self.dims[:3]
         fr = self.frames
@@ -101,6 +108,7 @@ class Trainer:
         self.cur_B = self.B
         self.train_dropout = True      # tests switch dropout off to compare against a deterministic reference
         self.n_steps = 0
+        self.n_replays = 0             # steps that were CUDA-graph replays (the CLI tests assert the fast path is taken)
         # captured steps, keyed by the batch shape (utterances, frames per stream): a graph replays a fixed shape, so
         # every shape that recurs (the full-capacity batch; the fixed trailing batch of an epoch; length buckets) gets
         # its own graph the second time it is seen.  Least-recently-used graphs are dropped beyond `max_graphs`
@@ -379,6 +387,7 @@ class Trainer:
         if ent is not None:
             self._cache_touch(self._graphs, key)
             ent["graph"].replay()
+            self.n_replays += 1
             self._outputs = ent["outputs"]               # the replay refreshed THESE tensors (not an eager step's)
         else:
             seen = self._seen.get(key, 0)

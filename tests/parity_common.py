@@ -94,15 +94,24 @@ def cuda_relu_gates(net):
     return {k: v.cpu() for k, v in g.items()}
 
 
-def make_relu_from_gates(gates, dropped_sites=None, stats=None):
+def make_relu_from_gates(gates, masks=None, stats=None, pin=True):
     """relu(name, z) = z * gate.  Where the oracle's own sign disagrees with the gate AND the unit is not
-    dropped, the unit sits within forward rounding noise of 0 (counted in `stats`)."""
+    dropped, the unit sits within forward rounding noise of 0 (counted in `stats`; `sample_flips` counts the
+    samples that own at least one such unit).  pin=False only counts: the oracle keeps its own ReLU."""
     def relu(name, z):
         gate = gates[name].reshape(z.shape)
         if stats is not None:
+            flip = ((z > 0) & ~gate) | ((z <= 0) & gate)
+            if masks is not None:                      # train mode: a dropped unit is 0 on both sides, not a flip
+                base, idx = name.rsplit(".", 1)
+                site = f"{base}.{int(idx) // 3}"
+                if site in masks:
+                    flip = flip & (masks[site].reshape(z.shape) > 0)
             stats["units"] = stats.get("units", 0) + z.numel()
-            stats["flipped"] = stats.get("flipped", 0) + int(((z > 0) & ~gate).sum()) + int(((z <= 0) & gate).sum())
-        return z * gate.to(z.dtype)
+            stats["flipped"] = stats.get("flipped", 0) + int(flip.sum())
+            per = flip.reshape(flip.shape[0], -1).any(dim=1)
+            stats["sample_flips"] = per if "sample_flips" not in stats else (stats["sample_flips"] | per)
+        return z * gate.to(z.dtype) if pin else torch.relu(z)
     return relu
 
 
@@ -145,7 +154,7 @@ def kernel_masks(net, B, frames_amv, pass_idx: int):
 
 
 def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda", loss_w=None, emulate=False,
-               cotangent=False):
+               cotangent=False, count_flips=False):
     """Returns dict of normalised errors: outputs of both passes, the 6 loss terms, every live gradient.
 
     cotangent=True replaces the distillation loss by sum_p <output_p, C_p> with fixed random cotangents C:
@@ -165,13 +174,13 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
     La, Lt, Lv, L4 = frames
     v0, e0 = net([dev["audio"], dev["text"], dev["video"], False])
     masks0 = kernel_masks(net, B, (La, Lt, Lv), 0) if train else None
-    gates0 = cuda_relu_gates(net) if emulate else None
+    gates0 = cuda_relu_gates(net) if (emulate or count_flips) else None
     v1, e1 = net([dev["audio"], dev["feat4"], dev["video"], True])
     masks1 = kernel_masks(net, B, (La, L4, Lv), 1) if train else None
-    gates1 = cuda_relu_gates(net) if emulate else None
+    gates1 = cuda_relu_gates(net) if (emulate or count_flips) else None
     stats = {}
-    relu0 = make_relu_from_gates(gates0, stats=None if train else stats) if emulate else None
-    relu1 = make_relu_from_gates(gates1, stats=None if train else stats) if emulate else None
+    relu0 = make_relu_from_gates(gates0, masks0, stats=stats, pin=emulate) if (emulate or count_flips) else None
+    relu1 = make_relu_from_gates(gates1, masks1, stats=stats, pin=emulate) if (emulate or count_flips) else None
 
     w = {**O.DEFAULT_LOSS_W, **(loss_w or {})}
     d0 = O.make_drop_from_masks(masks0) if train else None
@@ -197,6 +206,7 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
         res = {"loss": abs(float(loss) - float(oloss)) / scale}
         if stats:
             res["stat/relu_flip_frac"] = stats["flipped"] / max(1, stats["units"])
+            res["stat/sample_flip_frac"] = float(stats["sample_flips"].double().mean())
         for tag, (v, e), (ov, oe) in (("p0", (v0, e0), o0), ("p1", (v1, e1), o1)):
             res[f"{tag}/vals"] = nerr(v, ov)
             for nm, a, b in zip(("fused", "rnc", "text_hidden", "cross_text"), e, oe):

@@ -139,3 +139,62 @@ def test_prefetch_iterator_stages_one_batch_ahead():
     got = [idx for idx, vals, names in prefetched(tr, dev.batches(4), dev)]
     assert got == [[0, 1, 2, 3], [4, 5, 6, 7], [8, 9]]
     assert tr.log == [("gather", (0, 1, 2, 3)), ("gather", (4, 5, 6, 7)), ("gather", (8, 9))]
+
+
+# ---- golden vectors of the reference's own collate code (oracle/make_golden_collate.py) ----------------------
+def _collate_golden():
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "collate_small.npz")
+    streams = ("audio", "text", "video", "feat4")
+    n = z["pads"].shape[1]
+    feats = {s: [torch.from_numpy(z[f"in/{s}/{i}"]).bfloat16() for i in range(n)] for s in streams}
+    return z, feats, n
+
+
+def test_host_collate_equals_reference_padding_golden():
+    """Store4F.collate against the padded batches produced by the reference's pad_to_maxlen_pre_modality_tensor_4
+    (read_data.py:223-248) + torch.stack (feat_data.py:242-247), bit for bit (values are bf16-exact)."""
+    from sdumc_b200.dataset import Store4F
+    z, feats, n = _collate_golden()
+    store = Store4F(feats, [0.0] * n, [f"u{i}" for i in range(n)])
+    batch, _, _ = store.collate(list(range(n)))
+    for s in ("audio", "text", "video", "feat4"):
+        assert np.array_equal(batch[s].float().numpy(), z[f"batch/{s}"]), s
+        lens = np.array([x.shape[0] for x in feats[s]])
+        assert np.array_equal(batch[s].shape[1] - lens, z["pads"][("audio", "text", "video", "feat4").index(s)])
+
+
+def test_batch_chunks_equal_shards_and_reference_order():
+    from sdumc_b200.dataset import batch_chunks
+    # single process: the reference's consecutive batches; a trailing single sample joins the last batch
+    assert [len(c) for c in batch_chunks(65, 32)] == [32, 33]
+    assert batch_chunks(64, 32)[1][0] == 32
+    # scoring over ranks: whole reference batches round-robin
+    assert [c[0] for c in batch_chunks(200, 32, rank=1, world=2)] == [32, 96, 160]
+    # lock-step training: every rank has the same number of steps AND the same shard size at every step
+    for n, bs, w in ((1000, 32, 2), (1000, 32, 8), (70, 32, 2), (20480, 512, 8), (33, 32, 4)):
+        per = [batch_chunks(n, bs, r, w, lockstep=True) for r in range(w)]
+        assert len({len(p) for p in per}) == 1
+        for step in range(len(per[0])):
+            assert len({len(p[step]) for p in per}) == 1
+            assert all(len(p[step]) >= 2 for p in per)
+        used = sorted(i for p in per for c in p for i in c)
+        assert used == list(range(len(used))) and n - len(used) < 2 * w     # a prefix; fewer than 2*world dropped
+
+
+def test_kfold_indices_equal_sklearn_kfold():
+    from sklearn.model_selection import KFold
+    from sdumc_b200.dataset import kfold_indices
+    for n, k, seed in ((103, 5, 100), (20480, 5, 100), (17, 3, 7)):
+        ref = list(KFold(k, shuffle=True, random_state=seed).split(np.arange(n)))
+        for (tr, va), (tr2, va2) in zip(ref, kfold_indices(n, k, seed)):
+            assert tr.tolist() == tr2 and va.tolist() == va2
+
+
+def test_store_subset_shares_tensors():
+    from sdumc_b200.dataset import Store4F
+    z, feats, n = _collate_golden()
+    store = Store4F(feats, list(range(n)), [f"u{i}" for i in range(n)])
+    sub = store.subset([3, 1])
+    assert len(sub) == 2 and sub.names == ["u3", "u1"] and sub.vals.tolist() == [3.0, 1.0]
+    assert sub.feats["audio"][0].data_ptr() == feats["audio"][3].data_ptr()

@@ -196,3 +196,34 @@ def test_edge_shapes_score_and_step(b, frames):
     tr.train_step()
     torch.cuda.synchronize()
     assert bool(torch.isfinite(tr.terms[:7]).all()) and bool(torch.isfinite(tr.master).all())
+
+
+def test_collate_kernel_equals_reference_padding_golden():
+    """sdumc_collate_pad (gather + right-zero-pad from the packed HBM store) against the batches the reference's own
+    pad_to_maxlen_pre_modality_tensor_4 + torch.stack produced (tests/golden/collate_small.npz, generated by
+    oracle/make_golden_collate.py from read_data.py:139-162,223-248), bit for bit; also through a fold subset."""
+    import numpy as np
+    from pathlib import Path
+    from sdumc_b200 import ops
+    from sdumc_b200.dataset import DeviceStore4F, Store4F
+    z = np.load(Path(__file__).parent / "golden" / "collate_small.npz")
+    streams = ("audio", "text", "video", "feat4")
+    n = z["pads"].shape[1]
+    feats = {s: [torch.from_numpy(z[f"in/{s}/{i}"]).bfloat16() for i in range(n)] for s in streams}
+    dev = torch.device("cuda", 0)
+    ds = DeviceStore4F(Store4F(feats, [0.0] * n, [f"u{i}" for i in range(n)]), dev)
+    idx = list(range(n))
+    frames = ds.batch_frames(idx)
+    idx_dev = torch.tensor(idx, dtype=torch.int32, device=dev)
+    for s, L in zip(streams, frames):
+        D = ds.packed[s].shape[1]
+        out = torch.full((n * L * D,), 7.0, dtype=torch.bfloat16, device=dev)
+        ops.collate_pad(ds.packed[s], ds.offsets[s], idx_dev, L, out)
+        assert np.array_equal(out.view(n, L, D).float().cpu().numpy(), z[f"batch/{s}"]), s
+    sub = ds.subset([4, 2, 0])
+    ids, _, names = next(iter(sub.batches(8)))
+    assert ids == [4, 2, 0] and names == ["u4", "u2", "u0"]
+    L = sub.batch_frames(ids)[0]
+    out = torch.empty(3 * L * 16, dtype=torch.bfloat16, device=dev)
+    ops.collate_pad(ds.packed["audio"], ds.offsets["audio"], torch.tensor(ids, dtype=torch.int32, device=dev), L, out)
+    assert np.array_equal(out.view(3, L, 16).float().cpu().numpy(), z["batch/audio"][[4, 2, 0], :L])
