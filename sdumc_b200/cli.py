@@ -67,6 +67,8 @@ def build_parser(inference: bool) -> argparse.ArgumentParser:
                         'single train/val/test run')
     p.add_argument('--synthetic_frames', type=str, default=None, help='La,Lt,Lv,L4 of --synthetic (default S0: 384,64,256,64)')
     p.add_argument('--synthetic_dims', type=str, default=None, help='Da,Dt,Dv,D4 of --synthetic (default S0: 1024,4096,1024,4096)')
+    p.add_argument('--synthetic_label_scale', type=float, default=1.0,
+                   help='multiplies the labels of --synthetic (the reference keeps a checkpoint only below a test MAE of 1.0, :299)')
     p.add_argument('--no_dropout', action='store_true', help='train without dropout (deterministic parity runs)')
     p.add_argument('--checkpoint', type=str, default=None,
                    help='checkpoint with ["state_dict"] (inference; the reference hard-codes its path, ..._inference.py:341)')
@@ -90,7 +92,10 @@ def load_splits(args):
     if args.synthetic:
         dims = tuple(int(x) for x in args.synthetic_dims.split(',')) if args.synthetic_dims else (1024, 4096, 1024, 4096)
         frames = tuple(int(x) for x in args.synthetic_frames.split(',')) if args.synthetic_frames else (384, 64, 256, 64)
-        mk = lambda n, seed: Store4F.synthetic(n, dims, frames, seed=seed, ragged=args.synthetic_ragged)  # noqa: E731
+        def mk(n, seed):
+            st_ = Store4F.synthetic(n, dims, frames, seed=seed, ragged=args.synthetic_ragged)
+            st_.vals = st_.vals * args.synthetic_label_scale
+            return st_
         return mk(args.synthetic, 1234), mk(max(args.batch_size, args.synthetic // 8), 4321), \
             mk(max(args.batch_size, args.synthetic // 8), 9876)
     if not (args.feat_root and args.label_path):

@@ -226,7 +226,7 @@ def rnc(feats, labels, *, loss, dfeats=None, row_begin=0, row_end=None, temperat
         workspace = torch.empty(rnc_workspace_bytes(n, D), dtype=torch.uint8, device=feats.device)
     a.workspace, a.workspace_bytes = ptr(workspace), workspace.numel()
     a.reuse_sort = 1 if reuse_sort else 0
-    call("sdumc_rnc", a, launches=(5 if dfeats is not None else 3) - (1 if reuse_sort else 0))
+    call("sdumc_rnc", a, launches=(6 if dfeats is not None else 4) - (2 if reuse_sort else 0))
 
 
 def adam(p, g, m, v, *, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0,

@@ -94,6 +94,29 @@ def cuda_relu_gates(net):
     return {k: v.cpu() for k, v in g.items()}
 
 
+def state_relu_gates(st, pass_idx: int):
+    """ReLU on/off pattern of pass `pass_idx` of a fused two-pass forward (Trainer: rows [p*B, (p+1)*B) of every
+    utterance-level buffer belong to pass p), keyed like the oracle."""
+    t = st.t
+    G = 256
+    B = st.cfg.B
+    rows = slice(pass_idx * B, (pass_idx + 1) * B)
+    rows7 = slice(pass_idx * B * 7, (pass_idx + 1) * B * 7)
+    g = {}
+    for m, name in enumerate(("audio_mlp", "text_mlp", "video_mlp")):
+        g[f"{name}.0"] = t[f"h1.{m}"][rows] > 0
+        g[f"{name}.3"] = t["cat"][rows, m * G:(m + 1) * G] > 0
+    g["attention_mlp.0"], g["attention_mlp.3"] = t["a1"][rows] > 0, t["a2"][rows] > 0
+    for i, name in enumerate(O.QUERY_MLPS):
+        g[f"{name}.0"] = t["Q"][rows, i * G:(i + 1) * G] > 0
+    for m, name in enumerate(("cross_audio_mlp", "cross_text_mlp", "cross_video_mlp")):
+        g[f"{name}.0"] = (t[f"c1.{m}"][rows7] > 0).view(B, 7, 256)
+        g[f"{name}.3"] = (t[f"c.{m}"][rows7] > 0).view(B, 7, 128)
+    g["cross_attention_mlp.0"], g["cross_attention_mlp.3"] = t["x1"][rows] > 0, t["x2"][rows] > 0
+    g["orgin_linear_change.0"] = t["o1"][rows] > 0
+    return {k: v.cpu() for k, v in g.items()}
+
+
 def make_relu_from_gates(gates, masks=None, stats=None, pin=True):
     """relu(name, z) = z * gate.  Where the oracle's own sign disagrees with the gate AND the unit is not
     dropped, the unit sits within forward rounding noise of 0 (counted in `stats`; `sample_flips` counts the
@@ -154,7 +177,7 @@ def kernel_masks(net, B, frames_amv, pass_idx: int):
 
 
 def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda", loss_w=None, emulate=False,
-               cotangent=False, count_flips=False):
+               cotangent=False, count_flips=False, pin=None):
     """Returns dict of normalised errors: outputs of both passes, the 6 loss terms, every live gradient.
 
     cotangent=True replaces the distillation loss by sum_p <output_p, C_p> with fixed random cotangents C:
@@ -174,13 +197,14 @@ def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda"
     La, Lt, Lv, L4 = frames
     v0, e0 = net([dev["audio"], dev["text"], dev["video"], False])
     masks0 = kernel_masks(net, B, (La, Lt, Lv), 0) if train else None
-    gates0 = cuda_relu_gates(net) if (emulate or count_flips) else None
+    gates0 = cuda_relu_gates(net) if (emulate or count_flips or pin) else None
     v1, e1 = net([dev["audio"], dev["feat4"], dev["video"], True])
     masks1 = kernel_masks(net, B, (La, L4, Lv), 1) if train else None
-    gates1 = cuda_relu_gates(net) if (emulate or count_flips) else None
+    gates1 = cuda_relu_gates(net) if (emulate or count_flips or pin) else None
     stats = {}
-    relu0 = make_relu_from_gates(gates0, masks0, stats=stats, pin=emulate) if (emulate or count_flips) else None
-    relu1 = make_relu_from_gates(gates1, masks1, stats=stats, pin=emulate) if (emulate or count_flips) else None
+    pin = emulate if pin is None else pin     # pin the oracle's ReLU pattern to the CUDA forward's (default: with emulation)
+    relu0 = make_relu_from_gates(gates0, masks0, stats=stats, pin=pin) if (emulate or count_flips or pin) else None
+    relu1 = make_relu_from_gates(gates1, masks1, stats=stats, pin=pin) if (emulate or count_flips or pin) else None
 
     w = {**O.DEFAULT_LOSS_W, **(loss_w or {})}
     d0 = O.make_drop_from_masks(masks0) if train else None

@@ -31,13 +31,14 @@ def main():
     out = {}
     for cname, cfg in (("small", SMALL), ("s0dims", S0DIMS)):
         for train in (False, True):
-            for emulate in (False, True):
+            for emulate, pin in ((False, False), (False, True), (True, False), (True, True)):
                 for cot in (True, False):
-                    if not cot and cname == "small":
+                    if not cot and (cname == "small" or emulate != pin):
                         continue
-                    key = f"{cname}/{'train' if train else 'eval'}/{'emu' if emulate else 'plain'}/{'vjp' if cot else 'loss'}"
+                    key = (f"{cname}/{'train' if train else 'eval'}/{'emu' if emulate else 'plain'}"
+                           f"{'+pin' if pin else ''}/{'vjp' if cot else 'loss'}")
                     res = run_parity(cfg["dims"], cfg["frames"], cfg["B"], gain=1.0, train=train, cotangent=cot,
-                                     emulate=emulate, count_flips=True)
+                                     emulate=emulate, count_flips=True, pin=pin)
                     out[key] = summarise(res)
                     print(key, json.dumps(out[key]), flush=True)
     if len(sys.argv) > 2 and sys.argv[1] == "--json":

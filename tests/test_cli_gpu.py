@@ -15,7 +15,9 @@ from oracle import sdumc_oracle as O
 pytestmark = pytest.mark.gpu
 
 DIMS, FRAMES = (256, 512, 128, 512), (48, 16, 32, 12)
-SYN = ["--synthetic_dims", ",".join(map(str, DIMS)), "--synthetic_frames", ",".join(map(str, FRAMES))]
+SCALE = 0.3          # labels in [-0.9, 0.9]: the reference only keeps a checkpoint below a test MAE of 1.0 (:299, :369)
+SYN = ["--synthetic_dims", ",".join(map(str, DIMS)), "--synthetic_frames", ",".join(map(str, FRAMES)),
+       "--synthetic_label_scale", str(SCALE)]
 
 
 def test_train_cli_replays_graphs_saves_reference_checkpoints_and_inference_cli_loads_them(tmp_path, monkeypatch):
@@ -111,18 +113,19 @@ def test_full_partial_full_batches_keep_their_own_outputs():
 def test_kfold_validation_mse_within_0p005_of_the_oracle(tmp_path, monkeypatch):
     """BASELINE config 3 / north_star: per-fold validation MSE of the CUDA trainer vs the oracle's restatement of the
     reference loop (fresh parameters, Adam and LambdaLR schedule per fold, main_frame_val_text_missing.py:295-342).
-    Reduced set: 2 folds x 3 epochs x 96 utterances, batch 16, dropout off (bit-comparable runs), lr 1e-3 so the
-    parameters move appreciably."""
+    Reduced set: 2 folds x 3 epochs x 96 utterances, batch 16, dropout off (comparable runs), lr 3e-4 so the
+    parameters move appreciably within 9 steps."""
     from sdumc_b200.cli import main_train
     from sdumc_b200.dataset import Store4F, batch_chunks, kfold_indices
     from sdumc_b200.params import ParamLayout
     from sdumc_b200.trainer import default_state_dict, lr_lambda
     monkeypatch.chdir(tmp_path)
-    n, folds, epochs, bs, lr, seed = 96, 2, 3, 16, 1e-3, 100
+    n, folds, epochs, bs, lr, seed = 96, 2, 3, 16, 3e-4, 100
     res = main_train(["--synthetic", str(n), "--epochs", str(epochs), "--batch_size", str(bs), "--folds", str(folds),
                       "--lr", str(lr), "--no_dropout", "--seed", str(seed), *SYN])
     got = res["fold_val_mse"]
     store = Store4F.synthetic(n, DIMS, FRAMES, seed=1234)
+    store.vals = store.vals * SCALE
 
     def tensors(sub, idx):
         b, vals, _ = sub.collate(idx)

@@ -94,7 +94,11 @@ def test_loss_terms_match_the_oracle_on_the_same_forward(setup):
 FULL_PRED_TOL = 1e-2     # max|err| / max|ref| on predictions (north_star)
 FULL_EMB_TOL = 1e-2      # ... on the four embeddings of each pass
 FULL_TERM_TOL = 1e-2     # |term - ref| <= tol * max(1, |ref|)
-FULL_GRAD_TOL = 3e-2     # relative L2 of the in-projection weight gradients vs plain fp32 autograd
+FULL_GRAD_TOL = 2e-2     # relative L2 of the in-projection weight gradients vs the plain fp32 oracle's autograd with
+#                          its ReLU on/off pattern taken from the CUDA forward (north_star: <= 2e-2 on gradients)
+FULL_GRAD_TOL_FREE = 0.2 # ... with the oracle's own ReLU pattern: units within bf16 rounding noise of 0 (~5e-4 of them)
+#                          fall on the other side and each switches a whole unit's backward signal on or off - a
+#                          discontinuity of the model (tests/test_unemulated_gpu.py), not a kernel error
 
 
 def _oracle_forward_chunked(P, batch, chunk=64):
@@ -167,14 +171,20 @@ def test_subbatch_step_through_the_capacity_512_trainer_matches_oracle_autograd(
     torch.cuda.synchronize()
     torch.set_num_threads(max(1, __import__("os").cpu_count() or 1))
     cpu = {k: v.float().cpu() for k, v in batch.items()}
-    _, terms, grads, _ = O.loss_and_grads(P, cpu["audio"], cpu["text"], cpu["feat4"], cpu["video"], cpu["vals"])
+    from tests.parity_common import make_relu_from_gates, state_relu_gates
+    relu0, relu1 = (make_relu_from_gates(state_relu_gates(st, p_)) for p_ in (0, 1))
+    _, terms, grads, _ = O.loss_and_grads(P, cpu["audio"], cpu["text"], cpu["feat4"], cpu["video"], cpu["vals"],
+                                          relu0=relu0, relu1=relu1)
+    _, _, grads_free, _ = O.loss_and_grads(P, cpu["audio"], cpu["text"], cpu["feat4"], cpu["video"], cpu["vals"])
     got = tr.terms.tolist()
     for i, name in enumerate(("mse_full", "mse_missing", "rmse_text_hidden", "rmse_cross_text", "rmse_fused", "rnc")):
         r = float(terms[name])
         assert abs(got[i] - r) <= FULL_TERM_TOL * max(1.0, abs(r)), (name, got[i], r)
-    errs = {}
+    errs, errs_free = {}, {}
     for i in range(3):
         name = f"frame_dim_reshape_{i}.weight"
-        g, ref = tr.W.grad(name).double().cpu(), grads[name].double()
+        g, ref, ref_free = tr.W.grad(name).double().cpu(), grads[name].double(), grads_free[name].double()
         errs[name] = float((g - ref).norm() / ref.norm())
-    assert all(e <= FULL_GRAD_TOL for e in errs.values()), errs
+        errs_free[name] = float((g - ref_free).norm() / ref_free.norm())
+    assert all(e <= FULL_GRAD_TOL for e in errs.values()), (errs, errs_free)
+    assert all(e <= FULL_GRAD_TOL_FREE for e in errs_free.values()), errs_free
