@@ -157,33 +157,42 @@ int launch_sqdiff_grad(const float* a, const float* b, long n, const float* coef
 static constexpr int kRncMaxN = 8192;
 
 // Sort of (label, row index) by counting: pos[i] = #{j : (y_j, j) < (y_i, i)} - a total order, stable w.r.t. the row
-// index.  O(n^2) comparisons spread over ceil(n / 256) CTAs (67 M at n = 8192, ~10 us) instead of a single-CTA bitonic
+// index.  O(n^2) comparisons spread over n / 32 CTAs of 8 warps (67 M at n = 8192) instead of a single-CTA bitonic
 // network (111 us at n = 8192, run redundantly by every data-parallel rank).  Every CTA holds all labels in shared
-// memory; the inner loop reads them as warp broadcasts.
+// memory; a lane owns one row, the 8 warps split the label range and read it as warp broadcasts.
 // Writes perm (sorted pos -> row), ys (sorted labels), pos (row -> sorted pos).
 __global__ void __launch_bounds__(256) rnc_sort_kernel(const float* __restrict__ labels, int n, int* perm, float* ys,
                                                         int* pos) {
   extern __shared__ unsigned char smraw[];
   float* key = reinterpret_cast<float*>(smraw);
+  __shared__ int part[8][32];
   for (int i = threadIdx.x; i < n; i += blockDim.x) key[i] = labels[i];
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float yi = key[i];
+  // CTA = 32 rows (one per lane); warp w counts over the j range [w, w+1) * n/8 (broadcast reads of key[j])
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane;
+  const float yi = i < n ? key[i] : 0.f;
+  const int j0 = (int)(((long)n * w) / 8) & ~3, j1 = w == 7 ? n : ((int)(((long)n * (w + 1)) / 8) & ~3);
   int r0 = 0, r1 = 0, r2 = 0, r3 = 0;
-  int j = 0;
-  for (; j + 4 <= n; j += 4) {
+  int j = j0;
+  for (; j + 4 <= j1; j += 4) {
     const float4 y4 = *reinterpret_cast<const float4*>(key + j);
     r0 += (y4.x < yi) || (y4.x == yi && j < i);
     r1 += (y4.y < yi) || (y4.y == yi && j + 1 < i);
     r2 += (y4.z < yi) || (y4.z == yi && j + 2 < i);
     r3 += (y4.w < yi) || (y4.w == yi && j + 3 < i);
   }
-  for (; j < n; ++j) r0 += (key[j] < yi) || (key[j] == yi && j < i);
-  const int r = (r0 + r1) + (r2 + r3);
-  perm[r] = i;
-  ys[r] = yi;
-  pos[i] = r;
+  for (; j < j1; ++j) r0 += (key[j] < yi) || (key[j] == yi && j < i);
+  part[w][lane] = (r0 + r1) + (r2 + r3);
+  __syncthreads();
+  if (w == 0 && i < n) {
+    int r = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) r += part[k][lane];
+    perm[r] = i;
+    ys[r] = yi;
+    pos[i] = r;
+  }
 }
 
 // Bucket index over the sorted labels: T[b] = first sorted position whose label is >= y_min + b * delta, b in [0, nb],
@@ -209,30 +218,34 @@ __global__ void __launch_bounds__(256) rnc_bucket_kernel(const float* __restrict
     for (int k = b + 1; k <= nb; ++k) T[k] = n;
 }
 
-// inclusive scan (double) of src[0..n) into dst[0..n); blockDim.x threads (a multiple of 32, <= 1024),
-// contiguous chunk per thread
+// inclusive scan (double) of src[0..n) into dst[0..n); blockDim.x threads (a multiple of 32, <= 1024).
+// Warp w owns the contiguous segment [w, w+1) * seg and walks it in groups of 32 consecutive elements (lane = element:
+// conflict-free shared-memory accesses; the contiguous-chunk-per-thread version had 8- and 16-way bank conflicts and
+// took a third of the anchor kernel at n = 8192), a shuffle scan per group and a running carry; then the warps'
+// totals are scanned and added.
 __device__ void block_scan(const float* src, double* dst, int n, double* wsum /*[32]*/) {
   const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int chunk = (n + (int)blockDim.x - 1) / (int)blockDim.x;
-  const int lo = t * chunk, hi = min(n, lo + chunk);
-  double run = 0.0;
-  for (int i = lo; i < hi; ++i) {
-    run += (double)src[i];
-    dst[i] = run;
-  }
-  // exclusive offsets of the per-thread totals
-  double incl = run;
+  const int nw = (int)blockDim.x >> 5;
+  const int seg = ((n + nw - 1) / nw + 31) & ~31;
+  const int lo = warp * seg, hi = min(n, lo + seg);
+  double carry = 0.0;
+  for (int g0 = lo; g0 < hi; g0 += 32) {
+    const int i = g0 + lane;
+    double v = i < hi ? (double)src[i] : 0.0;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const double v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
+    for (int o = 1; o < 32; o <<= 1) {
+      const double u = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += u;
+    }
+    v += carry;
+    if (i < hi) dst[i] = v;
+    carry = __shfl_sync(0xffffffffu, v, 31);
   }
-  if (lane == 31) wsum[warp] = incl;
+  if (lane == 0) wsum[warp] = carry;
   __syncthreads();
-  double woff = 0.0;
-  for (int w = 0; w < warp; ++w) woff += wsum[w];
-  const double off = woff + incl - run;
-  for (int i = lo; i < hi; ++i) dst[i] += off;
+  double off = 0.0;
+  for (int w = 0; w < warp; ++w) off += wsum[w];
+  for (int i = lo + lane; i < hi; i += 32) dst[i] += off;
   __syncthreads();
 }
 
@@ -427,110 +440,75 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
   }
 }
 
-// dfeats[x] += sum over anchor rows i of  [x == i] * sum_j c_ij (f_i - f_j)  -  c_ix (f_i - f_x)
-// block: 32 columns (j) x 8 dim-groups; loops over the anchor rows.
-__global__ void __launch_bounds__(256) rnc_col_kernel(RncArgs a, const float* Cmat) {
+// Gradient with respect to the features from the coefficient matrix C [rows x n] (c_ij multiplies (f_i - f_j) in
+// d loss / d f_i and -(f_i - f_j) in d loss / d f_j):
+//   row part (kCol = false):  dfeats[i] += f_i * sum_j c_ij - sum_j c_ij f_j      = a [rows x n] x [n x D] product
+//   column part (kCol = true): dfeats[j] += f_j * sum_i c_ij - sum_i c_ij f_i      = a [n x rows] x [rows x D] product
+// One register-tiled fp32 kernel serves both: CTA = 64 output rows x 64 feature dims, 256 threads with a 4 x 4
+// micro-tile, the reduction in chunks of 32 through shared memory (two 16-byte shared loads per 16 FMAs), the
+// reduction range split over gridDim.y with the partial results meeting in 16-byte vector reds.  (The first versions
+// - a thread per output row streaming C and F from L2 - ran at ~10 % of the fp32 rate: 50 / 70 us per 512 anchors at
+// n = 8192, a quarter of the data-parallel step's RnC time.)
+template <bool kCol>
+__global__ void __launch_bounds__(256) rnc_grad_kernel(RncArgs a, const float* __restrict__ Cmat) {
+  constexpr int KC = 32;
+  __shared__ __align__(16) float As[KC][68];   // [k][m]  (+4: the transposing store of the row part is 4-way, not 32-way, conflicted)
+  __shared__ __align__(16) float Bs[KC][64];   // [k][d]
   const int n = a.n, D = a.D;
   const int rows = a.row_end - a.row_begin;
-  const int jl = threadIdx.x & 31, dg = threadIdx.x >> 5;  // dims [dg*8, dg*8+8)
-  const int j = blockIdx.x * 32 + jl;
-  if (j >= n) return;
-  // anchor rows are split over gridDim.y blocks (partial sums meet in the fp32 atomics below)
-  const int il0 = (int)(((long)rows * blockIdx.y) / gridDim.y), il1 = (int)(((long)rows * (blockIdx.y + 1)) / gridDim.y);
-  for (int d0 = dg * 8; d0 < D; d0 += 64) {
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    float csum = 0.f;
-    // 8 anchor rows per trip with all loads issued first: the loop is a chain of L2 round trips otherwise
-    int il = il0;
-    for (; il + 8 <= il1; il += 8) {
-      float c[8];
-      float4 u[8], v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        c[k] = __ldg(Cmat + (long)(il + k) * n + j);
-        const float4* fi = reinterpret_cast<const float4*>(a.feats + (long)(a.row_begin + il + k) * D + d0);
-        u[k] = __ldg(fi);
-        v[k] = __ldg(fi + 1);
+  const int M = kCol ? n : rows, K = kCol ? rows : n;
+  const int m0 = blockIdx.x * 64, d0 = blockIdx.z * 64;
+  const int k_lo = (int)(((long)K * blockIdx.y) / gridDim.y), k_hi = (int)(((long)K * (blockIdx.y + 1)) / gridDim.y);
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int k0 = k_lo; k0 < k_hi; k0 += KC) {
+    if (kCol) {   // A[m][k] = C[k][m]: m contiguous in memory
+      for (int x = threadIdx.x; x < KC * 64; x += 256) {
+        const int kk = x >> 6, mm = x & 63;
+        const int k = k0 + kk, m = m0 + mm;
+        As[kk][mm] = (k < k_hi && m < M) ? __ldg(Cmat + (long)k * n + m) : 0.f;
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        csum += c[k];
-        acc[0] = fmaf(c[k], u[k].x, acc[0]); acc[1] = fmaf(c[k], u[k].y, acc[1]); acc[2] = fmaf(c[k], u[k].z, acc[2]); acc[3] = fmaf(c[k], u[k].w, acc[3]);
-        acc[4] = fmaf(c[k], v[k].x, acc[4]); acc[5] = fmaf(c[k], v[k].y, acc[5]); acc[6] = fmaf(c[k], v[k].z, acc[6]); acc[7] = fmaf(c[k], v[k].w, acc[7]);
+    } else {      // A[m][k] = C[m][k]: k contiguous in memory, stored transposed
+      for (int x = threadIdx.x; x < KC * 64; x += 256) {
+        const int kk = x & 31, mm = x >> 5;
+        const int k = k0 + kk, m = m0 + mm;
+        As[kk][mm] = (k < k_hi && m < M) ? __ldg(Cmat + (long)m * n + k) : 0.f;
       }
     }
-    for (; il < il1; ++il) {
-      const float c = Cmat[(long)il * n + j];
-      const float4* fi = reinterpret_cast<const float4*>(a.feats + (long)(a.row_begin + il) * D + d0);
-      const float4 u = __ldg(fi), v = __ldg(fi + 1);
-      csum += c;
-      acc[0] = fmaf(c, u.x, acc[0]); acc[1] = fmaf(c, u.y, acc[1]); acc[2] = fmaf(c, u.z, acc[2]); acc[3] = fmaf(c, u.w, acc[3]);
-      acc[4] = fmaf(c, v.x, acc[4]); acc[5] = fmaf(c, v.y, acc[5]); acc[6] = fmaf(c, v.z, acc[6]); acc[7] = fmaf(c, v.w, acc[7]);
+    for (int x = threadIdx.x; x < KC * 64; x += 256) {
+      const int kk = x >> 6, dd = x & 63;
+      const int k = k0 + kk, d = d0 + dd;
+      const long frow = kCol ? (long)(a.row_begin + k) : (long)k;
+      Bs[kk][dd] = (k < k_hi && d < D) ? __ldg(a.feats + frow * D + d) : 0.f;
     }
-    // - sum_i c_ij (f_i - f_j) = f_j * csum - sum_i c_ij f_i
-    const float* fj = a.feats + (long)j * D + d0;
-    float o[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) o[u] = fj[u] * csum - acc[u];
-    float* dst = a.dfeats + (long)j * D + d0;          // D % 4 == 0 and d0 % 8 == 0: 16-byte aligned
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
-    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + 4), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
-  }
-}
-// row part: dfeats[i] += sum_j c_ij (f_i - f_j) = f_i * rowsum - sum_j c_ij f_j, a [rows x n] x [n x D] product.
-// CTA = 32 anchor rows x one slice of the j range (gridDim.y slices, partial results meet in vector reds);
-// 64-column chunks of C (transposed) and 64 rows of F go through shared memory, a thread owns 4 rows x 2 dims
-// per 64-dim block: one 16-byte broadcast load of C and one 8-byte load of F per 8 FMAs.  (One CTA per anchor row
-// re-read the whole feature matrix from L2 per row: 127 us per 512 anchors at n = 8192.)
-__global__ void __launch_bounds__(256) rnc_rowgrad_kernel(RncArgs a, const float* Cmat) {
-  __shared__ __align__(16) float CsT[64][36];   // [j][row], rows padded to 36 (16-byte aligned quads)
-  __shared__ __align__(16) float Fs[64][64];
-  const int n = a.n, D = a.D;
-  const int rows = a.row_end - a.row_begin;
-  const int il0 = blockIdx.x * 32;
-  const int jlo = (int)(((long)n * blockIdx.y) / gridDim.y), jhi = (int)(((long)n * (blockIdx.y + 1)) / gridDim.y);
-  const int rg = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int d0 = 0; d0 < D; d0 += 64) {
-    const int dw = min(64, D - d0);
-    float acc[4][2] = {};
-    float csum[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j0 = jlo; j0 < jhi; j0 += 64) {
-      for (int x = threadIdx.x; x < 32 * 64; x += 256) {
-        const int r = x >> 6, jj = x & 63;
-        const int il = il0 + r, j = j0 + jj;
-        CsT[jj][r] = (il < rows && j < jhi) ? __ldg(Cmat + (long)il * n + j) : 0.f;
-      }
-      for (int x = threadIdx.x; x < 64 * 64; x += 256) {
-        const int jj = x >> 6, d = x & 63;
-        const int j = j0 + jj;
-        Fs[jj][d] = (j < jhi && d < dw) ? __ldg(a.feats + (long)j * D + d0 + d) : 0.f;
-      }
-      __syncthreads();
+    __syncthreads();
 #pragma unroll 8
-      for (int jj = 0; jj < 64; ++jj) {
-        const float4 c = *reinterpret_cast<const float4*>(&CsT[jj][4 * rg]);
-        const float2 f = *reinterpret_cast<const float2*>(&Fs[jj][2 * lane]);
-        csum[0] += c.x; csum[1] += c.y; csum[2] += c.z; csum[3] += c.w;
-        acc[0][0] = fmaf(c.x, f.x, acc[0][0]); acc[0][1] = fmaf(c.x, f.y, acc[0][1]);
-        acc[1][0] = fmaf(c.y, f.x, acc[1][0]); acc[1][1] = fmaf(c.y, f.y, acc[1][1]);
-        acc[2][0] = fmaf(c.z, f.x, acc[2][0]); acc[2][1] = fmaf(c.z, f.y, acc[2][1]);
-        acc[3][0] = fmaf(c.w, f.x, acc[3][0]); acc[3][1] = fmaf(c.w, f.y, acc[3][1]);
-      }
-      __syncthreads();
-    }
-    const int d = d0 + 2 * lane;
-    if (d < D) {
+    for (int kk = 0; kk < KC; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float af[4] = {av.x, av.y, av.z, av.w};
+      const float bf[4] = {bv.x, bv.y, bv.z, bv.w};
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const int il = il0 + 4 * rg + u;
-        if (il >= rows) continue;
-        const long i = a.row_begin + il;
-        const float2 fi = *reinterpret_cast<const float2*>(a.feats + i * D + d);
-        float* dst = a.dfeats + i * D + d;              // D % 4 == 0, d even: 8-byte aligned
-        asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(dst), "f"(fi.x * csum[u] - acc[u][0]),
-                     "f"(fi.y * csum[u] - acc[u][1]) : "memory");
+        csum[u] += af[u];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = fmaf(af[u], bf[v], acc[u][v]);
       }
     }
+    __syncthreads();
+  }
+  const int d = d0 + tx * 4;
+  if (d >= D) return;            // D % 4 == 0 (checked on the host)
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int m = m0 + ty * 4 + u;
+    if (m >= M) continue;
+    const long r = kCol ? (long)m : (long)(a.row_begin + m);
+    const float4 f = *reinterpret_cast<const float4*>(a.feats + r * D + d);
+    float* dst = a.dfeats + r * D + d;
+    asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst), "f"(f.x * csum[u] - acc[u][0]),
+                 "f"(f.y * csum[u] - acc[u][1]), "f"(f.z * csum[u] - acc[u][2]), "f"(f.w * csum[u] - acc[u][3]) : "memory");
   }
 }
 
@@ -566,7 +544,7 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
     attr_done[dev] = true;
   }
   if (!a.reuse_sort) {   // a data-parallel rank calls once per anchor range with the same labels: sort once
-    rnc_sort_kernel<<<(a.n + 255) / 256, 256, (size_t)a.n * 4, stream>>>(a.labels, a.n, perm, ys, pos);
+    rnc_sort_kernel<<<(a.n + 31) / 32, 256, (size_t)a.n * 4, stream>>>(a.labels, a.n, perm, ys, pos);
     SDUMC_CUDA(cudaGetLastError());
     rnc_bucket_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(ys, a.n, T, hdr);
     SDUMC_CUDA(cudaGetLastError());
@@ -578,14 +556,17 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
   rnc_row_kernel<<<rows, row_threads, smem, stream>>>(a, perm, ys, pos, T, hdr, Cmat);
   SDUMC_CUDA(cudaGetLastError());
   if (a.dfeats) {
-    const int row_tiles = (rows + 31) / 32;
-    const int jsplit = std::max(1, std::min(a.n / 256, (2 * 148 + row_tiles - 1) / row_tiles));
-    rnc_rowgrad_kernel<<<dim3(row_tiles, jsplit), 256, 0, stream>>>(a, Cmat);
+    SDUMC_CHECK_ARG((reinterpret_cast<uintptr_t>(a.dfeats) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.feats) & 15u) == 0,
+                    "rnc: feats / dfeats must be 16-byte aligned");
+    const int sms = num_sms();
+    const int dt = (a.D + 63) / 64;
+    // reduction splits: ~2 CTAs per SM in total, at least 64 reduction steps per CTA
+    const int rt = (rows + 63) / 64, ct = (a.n + 63) / 64;
+    const int rsplit = std::max(1, std::min(a.n / 64, (2 * sms + rt * dt - 1) / (rt * dt)));
+    rnc_grad_kernel<false><<<dim3(rt, rsplit, dt), 256, 0, stream>>>(a, Cmat);
     SDUMC_CUDA(cudaGetLastError());
-    // anchor rows per CTA of the column kernel: enough CTAs to fill the GPU, few enough partial sums
-    const int jblocks = (a.n + 31) / 32;
-    const int ysplit = std::max(1, std::min(rows / 32, (4 * 148 + jblocks - 1) / jblocks));
-    rnc_col_kernel<<<dim3((a.n + 31) / 32, ysplit), 256, 0, stream>>>(a, Cmat);
+    const int csplit = std::max(1, std::min(rows / 64, (2 * sms + ct * dt - 1) / (ct * dt)));
+    rnc_grad_kernel<true><<<dim3(ct, csplit, dt), 256, 0, stream>>>(a, Cmat);
     SDUMC_CUDA(cudaGetLastError());
   }
   return 0;

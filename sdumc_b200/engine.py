@@ -362,9 +362,12 @@ class Engine:
                 t["Q"].view(NP, B, NQ, G)[:, :, 5, :], t["c.1"].view(NP, B, NQ, 128))
 
     # ------------------------------------------------------------------ backward
-    def backward(self, W: Weights, st: State, d_vals=None, d_fused=None, d_rnc=None, d_th=None, d_ct=None):
+    def backward(self, W: Weights, st: State, d_vals=None, d_fused=None, d_rnc=None, d_th=None, d_ct=None,
+                 on_chain_grads_final=None):
         """Accumulates parameter gradients into W.grads.  d_* are fp32, contiguous, shaped like outputs()
-        flattened over passes ([R,...]); None = zero."""
+        flattened over passes ([R,...]); None = zero.  on_chain_grads_final() is called (on the launching stream) once
+        every gradient except those of the in-projections and the FRA2UTT_new blocks has been issued - the
+        data-parallel trainer starts their all-reduce there, under the rest of the backward pass."""
         cfg = st.cfg
         assert cfg.need_grad, "forward was run without need_grad"
         B, NP = cfg.B, cfg.n_pass
@@ -462,6 +465,8 @@ class Engine:
                              Y=t["cat"][:, m * G:(m + 1) * G], dropped=True, dX=dh1s[m])
             self._linear_bwd(W, st, name + ".0", dh1s[m], t[f"u_bf16.{m}"], Y=t[f"h1.{m}"], dropped=True, dX=du[m])
         self._parallel(3, modality_mlp_bwd)
+        if on_chain_grads_final is not None:
+            on_chain_grads_final()
         # B10. FRA2UTT_new blocks
         def fra2utt_bwd(m):
             pre = f"fra2utt_{m}"

@@ -107,6 +107,13 @@ class Trainer:
         self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64), dtype=torch.uint8, device=dev)
         self.cur_B = self.B
         self.train_dropout = True      # tests switch dropout off to compare against a deterministic reference
+        self._comm_stream = None
+        # first flat-buffer offset after the in-projection and FRA2UTT_new parameters (the reference constructor
+        # registers them first, :193-226): gradients from there on are final before the last third of the backward
+        late = [e for e in L.entries.values() if e.live and e.name.startswith(("frame_dim_reshape_", "fra2utt_"))]
+        self._chain_begin = max(e.offset + (e.numel + 63) // 64 * 64 for e in late)
+        assert all(e.offset >= self._chain_begin for e in L.entries.values()
+                   if e.live and not e.name.startswith(("frame_dim_reshape_", "fra2utt_")))
         self.n_steps = 0
         self.n_replays = 0             # steps that were CUDA-graph replays (the CLI tests assert the fast path is taken)
         # captured steps, keyed by the batch shape (utterances, frames per stream): a graph replays a fixed shape, so
@@ -331,13 +338,10 @@ class Trainer:
         else:
             from . import dp
 
-            calls = [0]
-
-            def rnc_fn(feats_g, y_g, lo, hi, loss, dfeats):   # both anchor ranges share one label sort
+            def rnc_fn(feats_g, y_g, lo, hi, loss, dfeats):   # this rank's anchors: one contiguous row range
                 ops.rnc(feats_g, y_g, loss=loss, dfeats=dfeats, row_begin=lo, row_end=hi, grad_scale=w6,
-                        workspace=self.rnc_ws, reuse_sort=calls[0] > 0)
-                calls[0] += 1
-            # one all_gather (features + labels) and one all_reduce (RnC gradient + loss + the sums of squares)
+                        workspace=self.rnc_ws)
+            # one all_gather (features + labels) and one reduce_scatter (RnC gradient + loss + the sums of squares)
             loss_g, d_local = dp.rnc_global(rnc.contiguous(), y.contiguous(), self.pg, rnc_fn, extra=self.sums)
             self.rnc_val.copy_(loss_g)
             d_rnc.view(2, B, 64).copy_(d_local)
@@ -351,10 +355,29 @@ class Trainer:
         st = self._forward(dropout=self.train_dropout, need_grad=True)
         d_vals, d_f, d_rnc, d_th, d_ct = self._loss_and_seeds(st)
         self.grads.zero_()
-        self.engine.backward(self.W, st, d_vals=d_vals, d_fused=d_f, d_rnc=d_rnc, d_th=d_th, d_ct=d_ct)
-        if self.world > 1:
+        if self.world == 1:
+            self.engine.backward(self.W, st, d_vals=d_vals, d_fused=d_f, d_rnc=d_rnc, d_th=d_th, d_ct=d_ct)
+        else:
+            # gradient all-reduce overlapped with the backward pass, in two buckets that are contiguous ranges of
+            # the flat gradient buffer (params.ParamLayout orders the live tensors like the reference constructor):
+            #   early  [chain_begin, n_live): utterance chain, heads and Cross_Attention blocks - final once the modality
+            #          MLPs are done; reduced on a side stream while the FRA2UTT_new blocks and the in-projection weight
+            #          gradients (the last ~1/3 of the backward pass) still run;
+            #   late   [0, chain_begin): in-projections + FRA2UTT_new blocks, reduced when the backward pass ends.
             import torch.distributed as dist
-            dist.all_reduce(self.grads[:self.layout.n_live], group=self.pg)
+            main = torch.cuda.current_stream()
+            if self._comm_stream is None:
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+            comm, split = self._comm_stream, self._chain_begin
+
+            def early_bucket():
+                comm.wait_stream(main)
+                with torch.cuda.stream(comm):
+                    dist.all_reduce(self.grads[split:self.layout.n_live], group=self.pg)
+            self.engine.backward(self.W, st, d_vals=d_vals, d_fused=d_f, d_rnc=d_rnc, d_th=d_th, d_ct=d_ct,
+                                 on_chain_grads_final=early_bucket)
+            dist.all_reduce(self.grads[:split], group=self.pg)
+            main.wait_stream(comm)
         n = self.layout.n_live
         ops.adam(self.master, self.grads, self.m, self.v, lr=self.lr, step=1, weight_decay=self.weight_decay,
                  p_bf16=self.shadow, n=n, step_dev=self.step_dev, lr_dev=self.lr_dev)

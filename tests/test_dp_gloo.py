@@ -32,10 +32,15 @@ def _worker(rank, world, port, B, q):
     local = feats[sl].permute(1, 0, 2).contiguous()                            # [2,B,64] (view, sample)
 
     def rnc_fn(feats_g, y_g, lo, hi, loss, dfeats):
+        # rows arrive rank-major ([rank, view, sample]); the oracle wants [Bg,2,D] and numbers its anchors view-major
         n = feats_g.shape[0]
         f = feats_g.clone().requires_grad_(True)
-        views = torch.stack((f[: n // 2], f[n // 2:]), dim=1)                  # back to [Bg,2,D]
-        l = O.rnc_loss(views, y_g[: n // 2].unsqueeze(1), anchors=range(lo, hi))
+        views = f.view(world, 2, B, -1).permute(0, 2, 1, 3).reshape(Bg, 2, -1)
+        yv = y_g.view(world, 2, B)[:, 0].reshape(Bg)
+        r = lo // (2 * B)
+        assert (lo, hi) == (r * 2 * B, (r + 1) * 2 * B)
+        anchors = list(range(r * B, r * B + B)) + list(range(Bg + r * B, Bg + r * B + B))
+        l = O.rnc_loss(views, yv.unsqueeze(1), anchors=anchors)
         l.backward()
         loss += l.detach()
         dfeats += f.grad
@@ -54,7 +59,7 @@ def _worker(rank, world, port, B, q):
     ok = (abs(float(loss_g) - float(lr)) < 1e-12
           and torch.allclose(d_local, fr.grad[sl].permute(1, 0, 2), atol=1e-13)
           and abs(float(torch.sqrt(sums / a.numel())) - float(O.rmse_loss(a, b))) < 1e-13
-          and dp.anchor_ranges(B, world, rank) == [(rank * B, rank * B + B), (Bg + rank * B, Bg + rank * B + B)])
+          and dp.anchor_range(B, world, rank) == (rank * 2 * B, rank * 2 * B + 2 * B))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 

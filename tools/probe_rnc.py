@@ -1,4 +1,5 @@
-"""Times the RnC kernels at the data-parallel problem sizes: n = 2 * 512 * world rows, two anchor ranges of 512."""
+"""Times the RnC kernels at the data-parallel problem sizes: n = 2 * 512 * world rows, this rank's 1024 anchors
+(one contiguous row range in the rank-major row order of sdumc_b200/dp.py)."""
 import sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
@@ -16,7 +17,7 @@ if __name__ == "__main__":
     ws = torch.empty(ops.rnc_workspace_bytes(n, D), dtype=torch.uint8, device=dev)
     loss = torch.zeros(1, device=dev)
     df = torch.zeros(n, D, device=dev)
-    ranges = [(v * B * world, v * B * world + B) for v in range(2)] if world > 1 else [(0, n)]
+    ranges = [(0, 2 * B)]
 
     def go():
         for k, (lo, hi) in enumerate(ranges):
