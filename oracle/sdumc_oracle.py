@@ -462,3 +462,16 @@ def grad_fingerprint(g: torch.Tensor, n: int = 64) -> torch.Tensor:
     if samp.numel() < n:
         samp = torch.cat([samp, samp.new_zeros(n - samp.numel())])
     return torch.cat([torch.stack([flat.sum(), flat.abs().sum(), flat.norm()]), samp])
+
+
+# ----------------------------------------------------------------------------------------------
+# N4: EncoderProjectorConcat (feature_extraction/llm4wav/extract_wavlm_vicuna.py:162-185)
+# ----------------------------------------------------------------------------------------------
+def encoder_projector_concat(P: Params, x: torch.Tensor, k: int) -> torch.Tensor:
+    """x [B,T,dim] -> [B, T//k, llm_dim]: drop the T % k trailing frames (:177-179), concatenate k consecutive frames
+    (:183), Linear -> ReLU -> Linear (:184-186).  P holds linear1.weight/.bias, linear2.weight/.bias."""
+    B, T, dim = x.shape
+    T -= T % k
+    x = x[:, :T, :].contiguous().view(B, T // k, dim * k)
+    h = torch.relu(x @ P["linear1.weight"].t() + P["linear1.bias"])
+    return h @ P["linear2.weight"].t() + P["linear2.bias"]

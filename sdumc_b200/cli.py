@@ -271,6 +271,38 @@ def main_train(argv=None):
             "checkpoints": saved, "train_steps": n_steps, "graph_replays": n_replays}
 
 
+def gather_results(res: dict, order: np.ndarray, n_total: int, pg, device):
+    """All ranks' per-utterance result arrays -> the full arrays in dataset order on every rank.
+    `order` = dataset positions of this rank's rows (ranks hold whole reference batches, dealt round-robin).
+    One padded all_gather per key over NCCL (the payload of 100k utterances is ~1.1 GB in total)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(pg)
+    n_loc = torch.tensor([len(order)], dtype=torch.int64, device=device)
+    counts = [torch.zeros_like(n_loc) for _ in range(world)]
+    dist.all_gather(counts, n_loc, group=pg)
+    counts = [int(c.item()) for c in counts]
+    n_max = max(counts)
+
+    def gather(arr: np.ndarray) -> np.ndarray:
+        t = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+        pad = torch.zeros((n_max,) + tuple(t.shape[1:]), dtype=t.dtype, device=device)
+        pad[: t.shape[0]] = t
+        out = torch.empty((world,) + tuple(pad.shape), dtype=t.dtype, device=device)
+        dist.all_gather_into_tensor(out, pad, group=pg)
+        return out.cpu().numpy()
+    pos = gather(order.astype(np.int64))
+    full = {}
+    for k, v in res.items():
+        if not isinstance(v, np.ndarray):
+            continue
+        g = gather(v)
+        dst = np.zeros((n_total,) + v.shape[1:], dtype=v.dtype)
+        for r in range(world):
+            dst[pos[r, : counts[r]]] = g[r, : counts[r]]
+        full[k] = dst
+    return full
+
+
 def main_inference(argv=None):
     args = build_parser(True).parse_args(argv)
     args.test_sets = args.test_sets.split(',')
@@ -301,6 +333,14 @@ def main_inference(argv=None):
             names += nm
         res = {k: np.concatenate(v) for k, v in acc.items()}
         res["val_labels"], res["names"] = np.concatenate(labels), names
+        if world > 1:
+            # every rank scored whole reference batches (a sample's output depends on its batch's padding); put the
+            # rows back in dataset order on every rank, as main_frame_val_text_missing_inference.py:199-214 holds them
+            from .dataset import batch_chunks
+            order = np.array([i for c in batch_chunks(len(store), args.batch_size, rank, world) for i in c], dtype=np.int64)
+            all_names = list(store.names) if getattr(store, "_ids", None) is None else [store.names[i] for i in store._ids]
+            res = gather_results(res, order, len(store), pg, device)
+            res["names"] = all_names
         res["val_mse_full"] = float(np.mean((res["val_preds_full"].reshape(-1) - res["val_labels"]) ** 2))
         res["val_mse_missing"] = float(np.mean((res["val_preds_missing"].reshape(-1) - res["val_labels"]) ** 2))
         results[split_name] = res

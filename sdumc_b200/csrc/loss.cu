@@ -326,6 +326,41 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
       hi = min(max(th, rlo), rhi);
     }
   };
+  // The boundary on the element's OWN side of the anchor sits next to the element itself (labels within 1e-4 of its
+  // own): the predicate is known at the element, so a short walk finds the boundary - a binary search takes over
+  // only inside a large cluster of (nearly) tied labels.
+  //   walk_down: pred(m) holds; first index in [rlo, m] where the monotone (false -> true) predicate holds
+  //   walk_up  : first index in [m, rhi] where it holds (rhi = "nowhere")
+  auto walk_down = [&](int m, int rlo, auto pred) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (m > rlo && pred(m - 1)) --m; else return m;
+    }
+    if (m > rlo && pred(m - 1)) {
+      int lo = rlo, hi = m - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pred(mid)) hi = mid; else lo = mid + 1;
+      }
+      return lo;
+    }
+    return m;
+  };
+  auto walk_up = [&](int m, int rhi, auto pred) {
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+      if (m < rhi && !pred(m)) ++m; else return m;
+    }
+    if (m < rhi && !pred(m)) {
+      int lo = m + 1, hi = rhi;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (pred(mid)) hi = mid; else lo = mid + 1;
+      }
+      return lo;
+    }
+    return m;
+  };
   __shared__ float red[32];
   __shared__ double wsum[32];
   __shared__ float bcast;
@@ -377,22 +412,29 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
     float rinv = 0.f;
     if (s != pi) {
       const float thr = fabsf(yi - ys[s]) - 0.0001f;
-      int lo, hi;
-      bracket(yi - thr, 0, pi, lo, hi);  // first s' in [0,pi) with d < thr, i.e. label > y_i - thr
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (fabsf(yi - ys[mid]) >= thr) lo = mid + 1; else hi = mid;
+      auto in_neg = [&](int x) { return fabsf(yi - ys[x]) >= thr; };        // loss.py:303, verbatim
+      auto not_neg = [&](int x) { return !(fabsf(yi - ys[x]) >= thr); };
+      int left_end, right_begin, lo, hi;
+      if (s > pi) {
+        right_begin = walk_down(s, pi + 1, in_neg);   // first s' in (pi,n) with d >= thr: just below s
+        bracket(yi - thr, 0, pi, lo, hi);             // first s' in [0,pi) with d < thr, i.e. label > y_i - thr (mirror side)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (in_neg(mid)) lo = mid + 1; else hi = mid;
+        }
+        left_end = lo;
+      } else {
+        left_end = walk_up(s + 1, pi, not_neg);       // first s' in [0,pi) with d < thr: just above s
+        bracket(yi + thr, pi + 1, n, lo, hi);         // first s' in (pi,n) with d >= thr, i.e. label >= y_i + thr (mirror side)
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (in_neg(mid)) hi = mid; else lo = mid + 1;
+        }
+        right_begin = lo;
       }
-      const int left_end = lo;
-      bracket(yi + thr, pi + 1, n, lo, hi);  // first s' in (pi,n) with d >= thr, i.e. label >= y_i + thr
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (fabsf(yi - ys[mid]) >= thr) hi = mid; else lo = mid + 1;
-      }
-      const int right_begin = lo;
       const double Dk = (left_end > 0 ? pre[left_end - 1] : 0.0) + (total - pre[right_begin - 1]);
       lsum += logf((float)Dk) - (aux[s] - mx);
-      rinv = (float)(1.0 / Dk);
+      rinv = __frcp_rn((float)Dk);
     }
     aux[s] = rinv;  // the logit at s was consumed above by this thread only
   }
@@ -416,20 +458,28 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
     float c = 0.f;
     if (s != pi) {
       const float dij = fabsf(yi - ys[s]);
-      // left window: k in [a0, pi) with (d_ik - 1e-4) <= d_ij ; d_ik decreases towards pi
-      int lo, hi;
-      bracket(yi - (dij + 0.0001f), 0, pi, lo, hi);   // first k with label >= y_i - d_ij - 1e-4
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (dij >= fabsf(yi - ys[mid]) - 0.0001f) hi = mid; else lo = mid + 1;
+      // window of positives k whose negative set contains j: k in [a0, pi) and (pi, b1), where
+      // (d_ik - 1e-4) <= d_ij; d_ik decreases towards pi on the left and grows on the right
+      auto has_j = [&](int x) { return dij >= fabsf(yi - ys[x]) - 0.0001f; };
+      auto not_has_j = [&](int x) { return !(dij >= fabsf(yi - ys[x]) - 0.0001f); };
+      int a0, b1, lo, hi;
+      if (s < pi) {
+        a0 = walk_down(s, 0, has_j);                       // first k in [0,pi) with the predicate: just below s
+        bracket(yi + (dij + 0.0001f), pi + 1, n, lo, hi);  // first k in (pi,n) violating it: label > y_i + d_ij + 1e-4
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (has_j(mid)) lo = mid + 1; else hi = mid;
+        }
+        b1 = lo;  // window is (pi, b1)
+      } else {
+        b1 = walk_up(s + 1, n, not_has_j);                 // just above s
+        bracket(yi - (dij + 0.0001f), 0, pi, lo, hi);      // first k with label >= y_i - d_ij - 1e-4
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if (has_j(mid)) hi = mid; else lo = mid + 1;
+        }
+        a0 = lo;
       }
-      const int a0 = lo;
-      bracket(yi + (dij + 0.0001f), pi + 1, n, lo, hi);  // first k in (pi,n) violating the predicate: label > y_i + d_ij + 1e-4
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (dij >= fabsf(yi - ys[mid]) - 0.0001f) lo = mid + 1; else hi = mid;
-      }
-      const int b1 = lo;  // window is (pi, b1)
       const double Gj = (pre[pi] - (a0 > 0 ? pre[a0 - 1] : 0.0)) + (pre[b1 - 1] - pre[pi]);
       const float dl = cscale * (e[s] * (float)Gj - 1.f);  // d loss / d logit_ij
       // logit = -dist / t  ->  d loss / d dist = -dl / t ; direction (f_i - f_j) / dist
@@ -560,12 +610,13 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
                     "rnc: feats / dfeats must be 16-byte aligned");
     const int sms = num_sms();
     const int dt = (a.D + 63) / 64;
-    // reduction splits: ~2 CTAs per SM in total, at least 64 reduction steps per CTA
+    // reduction splits: ~5 resident CTAs per SM (the loads of a chunk are not double-buffered: other CTAs hide them),
+    // at least 64 reduction steps per CTA
     const int rt = (rows + 63) / 64, ct = (a.n + 63) / 64;
-    const int rsplit = std::max(1, std::min(a.n / 64, (2 * sms + rt * dt - 1) / (rt * dt)));
+    const int rsplit = std::max(1, std::min(a.n / 64, (5 * sms + rt * dt - 1) / (rt * dt)));
     rnc_grad_kernel<false><<<dim3(rt, rsplit, dt), 256, 0, stream>>>(a, Cmat);
     SDUMC_CUDA(cudaGetLastError());
-    const int csplit = std::max(1, std::min(rows / 64, (2 * sms + ct * dt - 1) / (ct * dt)));
+    const int csplit = std::max(1, std::min(rows / 64, (5 * sms + ct * dt - 1) / (ct * dt)));
     rnc_grad_kernel<true><<<dim3(ct, csplit, dt), 256, 0, stream>>>(a, Cmat);
     SDUMC_CUDA(cudaGetLastError());
   }

@@ -182,6 +182,26 @@ class DeviceStore4F:
             self.offsets[s] = off.to(self.device)
         self.vals = store.vals.to(self.device)
 
+    @classmethod
+    def from_device_batch(cls, batch: Dict[str, torch.Tensor], vals: torch.Tensor, names: Optional[List[str]] = None):
+        """Store over fixed-length utterances that already sit on the device as [N, L, D] tensors (synthetic data
+        generated in HBM): the packed layout is a view of the batch, no host round trip."""
+        self = cls.__new__(cls)
+        n = int(vals.shape[0])
+        self._ids = None
+        self.names = names or [f"synthetic_{i:06d}" for i in range(n)]
+        self.vals_host = vals.detach().float().cpu()
+        self.device = vals.device
+        self.dims = tuple(int(batch[s].shape[2]) for s in STREAMS)
+        self.max_frames = tuple(int(batch[s].shape[1]) for s in STREAMS)
+        self.lengths = {s: [int(batch[s].shape[1])] * n for s in STREAMS}
+        self.packed = {s: batch[s].to(torch.bfloat16).reshape(n * batch[s].shape[1], batch[s].shape[2]).contiguous()
+                       for s in STREAMS}
+        self.offsets = {s: (torch.arange(n + 1, dtype=torch.int64, device=self.device) * int(batch[s].shape[1]))
+                        for s in STREAMS}
+        self.vals = vals.detach().float().to(self.device)
+        return self
+
     def __len__(self):
         return len(self.names) if self._ids is None else len(self._ids)
 

@@ -157,3 +157,25 @@ def test_rnc_kernels_at_data_parallel_size():
     loss8, df8 = run(feats, slices=8)
     assert abs(float(loss8) - float(loss)) <= 1e-5 * abs(float(loss))
     assert float((df8 - df).abs().max()) <= 1e-5 * float(df.abs().max()) + 1e-9
+
+
+def test_encoder_projector_concat_matches_oracle():
+    """N4 drop-in (feature_extraction/llm4wav/extract_wavlm_vicuna.py:162-185) at the reference's real shape
+    EncoderProjectorConcat(5, 1024, 4096): bf16 tcgen05 GEMMs vs the fp64 oracle (itself pinned to the reference class by
+    tests/golden/projector_small.npz), max|err| / max|ref| <= 1e-2; trailing frames that do not fill a group of 5 are
+    discarded; the state_dict keys are the reference's."""
+    from oracle import sdumc_oracle as O
+    from sdumc_b200.projector import EncoderProjectorConcat
+    torch.manual_seed(3)
+    dev = torch.device("cuda", 0)
+    net = EncoderProjectorConcat(5, 1024, 4096).to(dev)
+    assert list(net.state_dict()) == ["linear1.weight", "linear1.bias", "linear2.weight", "linear2.bias"]
+    x = torch.randn(3, 203, 1024, device=dev)                       # 203 % 5 = 3 frames discarded
+    y = net(x)
+    assert y.shape == (3, 40, 4096)
+    P = {k: v.double().cpu() for k, v in net.state_dict().items()}
+    ref = O.encoder_projector_concat(P, x.double().cpu(), 5)
+    err = float((y.double().cpu() - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-2, err
+    with pytest.raises(Exception):
+        net.cpu()(x.cpu())

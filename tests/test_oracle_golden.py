@@ -203,3 +203,13 @@ def test_relu_flips_between_two_cpu_evaluations_move_gradients_as_much():
     pin_err = max(l2err(gc[k], ga[k]) for k in ga)
     assert free_err > 3 * pin_err and free_err > 5e-2, (free_err, pin_err)   # ... and move the gradients by >= 5 %
     assert pin_err < 7.5e-2, pin_err
+
+
+def test_encoder_projector_concat_matches_reference_golden():
+    """oracle.encoder_projector_concat against the output of the reference class (oracle/make_golden_projector.py)."""
+    from pathlib import Path
+    z = np.load(Path(__file__).parent / "golden" / "projector_small.npz")
+    P = {k[len("param/"):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("param/")}
+    y = O.encoder_projector_concat(P, torch.from_numpy(z["x"]), int(z["k"]))
+    assert y.shape == z["y"].shape
+    assert float((y - torch.from_numpy(z["y"])).abs().max()) < 1e-12
