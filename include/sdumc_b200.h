@@ -155,7 +155,7 @@ typedef struct sdumc_attn_bwd_args {
 int sdumc_attn_bwd(const sdumc_attn_bwd_args* a, void* stream);
 
 int sdumc_cast_bf16(const float* src, SDUMC_BF16* dst, int64_t n, void* stream);
-int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, float* out256, void* stream);
+int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, int32_t cols, float* out, void* stream);
 
 /* Collate of a device-resident feature store: the right-zero-padding batch builder of
  * toolkit/utils/read_data.py:223-248 (pad_to_maxlen_pre_modality_tensor_4) as a gather.

@@ -102,8 +102,8 @@ SDUMC_FWD(sdumc_adam, sdumc_adam_args, launch_adam)
 int sdumc_cast_bf16(const float* src, SDUMC_BF16* dst, int64_t n, void* stream) {
   return launch_cast_bf16(src, dst, n, static_cast<cudaStream_t>(stream));
 }
-int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, float* out256, void* stream) {
-  return launch_colsum_bf16(X, ld, rows, out256, static_cast<cudaStream_t>(stream));
+int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, int32_t cols, float* out, void* stream) {
+  return launch_colsum_bf16(X, ld, rows, cols, out, static_cast<cudaStream_t>(stream));
 }
 int sdumc_collate_pad(const SDUMC_BF16* packed, const int64_t* row_offset, const int32_t* idx, int32_t b,
                       int32_t Lpad, int32_t D, SDUMC_BF16* out, void* stream) {

@@ -698,30 +698,37 @@ int launch_collate_pad(const __nv_bfloat16* packed, const long long* row_offset,
   return 0;
 }
 
-// column sums of a bf16 matrix [rows, 256] -> atomicAdd into out[256]   (bias gradient of the in-projection)
-__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long ld, long rows,
+// column sums of a bf16 matrix [rows, cols] -> atomicAdd into out[cols]   (bias gradients: the in-projections',
+// and those of the MLP layers whose dZ comes straight out of a GEMM epilogue); cols % 8 == 0, cols <= 1024
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long ld, long rows, int cols,
                                                            float* __restrict__ out) {
-  __shared__ float red[G];
+  __shared__ float red[1024];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid < G) red[tid] = 0.f;
+  for (int i = tid; i < cols; i += 256) red[i] = 0.f;
   __syncthreads();
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (long r = (long)blockIdx.x * 8 + warp; r < rows; r += (long)gridDim.x * 8) {
-    float x[8];
-    unpack8(__ldg(reinterpret_cast<const uint4*>(X + r * ld + lane * 8)), x);
+  for (int cb = 0; cb < cols; cb += 256) {
+    const int c = cb + lane * 8;
+    if (c >= cols) continue;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (long r = (long)blockIdx.x * 8 + warp; r < rows; r += (long)gridDim.x * 8) {
+      float x[8];
+      unpack8(__ldg(reinterpret_cast<const uint4*>(X + r * ld + c)), x);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] += x[j];
+      for (int j = 0; j < 8; ++j) acc[j] += x[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&red[c + j], acc[j]);
   }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) atomicAdd(&red[lane * 8 + j], acc[j]);
   __syncthreads();
-  if (tid < G) atomicAdd(out + tid, red[tid]);
+  for (int i = tid; i < cols; i += 256) atomicAdd(out + i, red[i]);
 }
-int launch_colsum_bf16(const __nv_bfloat16* X, long ld, long rows, float* out, cudaStream_t stream) {
-  SDUMC_CHECK_ARG(X && out && rows > 0 && ld % 8 == 0, "colsum_bf16: bad arguments");
+int launch_colsum_bf16(const __nv_bfloat16* X, long ld, long rows, int cols, float* out, cudaStream_t stream) {
+  SDUMC_CHECK_ARG(X && out && rows > 0 && ld % 8 == 0 && cols > 0 && cols % 8 == 0 && cols <= 1024 &&
+                      (reinterpret_cast<uintptr_t>(X) & 15u) == 0,
+                  "colsum_bf16: bad arguments (cols %% 8 == 0, cols <= 1024, ld %% 8 == 0, 16-byte aligned)");
   long blocks = (rows + 63) / 64;
   if (blocks > (long)num_sms() * 8) blocks = (long)num_sms() * 8;
-  colsum_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, ld, rows, out);
+  colsum_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, ld, rows, cols, out);
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

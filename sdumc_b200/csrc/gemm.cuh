@@ -120,10 +120,15 @@ struct GemmCfg {
   static constexpr int kBBytes = kBlockN * kRowBytes;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (kBlockN == 256) ? 4 : (kBlockN == 128 ? 6 : 8);
+  static constexpr int kMaxStages = 8;                       // barrier slots (the resident-B ring may be deeper than kStages)
+  // ring area: kStages full (A + B) stages; for N = 256 one extra A tile, so that a resident 256 x 256 weight (128 KB)
+  // leaves a 5-deep A ring: the K = 256 frame GEMMs are bound by DRAM latency x ring depth (one 128-row tile = 4
+  // k-blocks = the whole 4-stage ring: the loads of tile i+1 could only start as tile i's MMAs retired)
+  static constexpr int kRingBytes = kStages * kStageBytes + (kBlockN == 256 ? kABytes : 0);
   static constexpr int kTmemCols = (2 * kBlockN < 32) ? 32 : 2 * kBlockN;
   static constexpr int kEpiWarps = 8;                        // two groups of 4, alternating tiles
   static constexpr int kVecBytes = 2 /*groups*/ * 2 /*bias, ctx*/ * kBlockN * 4;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kRingBytes + kVecBytes + 1024 /*align slack*/ + 256 /*barriers*/;
   static constexpr int kThreads = 384;
 };
 
@@ -142,11 +147,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const uint32_t raw = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw & 1023u)) & 1023u);
   uint8_t* stage_base = smem;
-  float* vec_s = reinterpret_cast<float*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes + Cfg::kVecBytes);
-  uint64_t* full_bar = bars;                       // [kStages]
-  uint64_t* empty_bar = bars + Cfg::kStages;       // [kStages]
-  uint64_t* tfull_bar = bars + 2 * Cfg::kStages;   // [2]
+  float* vec_s = reinterpret_cast<float*>(smem + Cfg::kRingBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kRingBytes + Cfg::kVecBytes);
+  uint64_t* full_bar = bars;                          // [kMaxStages]
+  uint64_t* empty_bar = bars + Cfg::kMaxStages;       // [kMaxStages]
+  uint64_t* tfull_bar = bars + 2 * Cfg::kMaxStages;   // [2]
   uint64_t* tempty_bar = tfull_bar + 2;            // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint64_t* bres_bar = tempty_bar + 3;             // resident-B mode: B loaded once per CTA
@@ -162,13 +167,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int n_tiles = (sh.N + kBlockN - 1) / kBlockN;
   const int nkb = (sh.K + kBlockK - 1) / kBlockK;
   const int num_tiles = m_tiles * n_tiles * sh.k_splits;
+  // ring depth: full stages, or - with B resident - as many A tiles as fit behind it
+  const int nst = b_res ? min(Cfg::kMaxStages, (Cfg::kRingBytes - nkb * Cfg::kBBytes) / Cfg::kABytes) : Cfg::kStages;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int i = 0; i < Cfg::kStages; ++i) {
+    for (int i = 0; i < Cfg::kMaxStages; ++i) {
       mbar_init(&full_bar[i], 1);
       mbar_init(&empty_bar[i], 1);
     }
@@ -235,7 +242,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
               tma_load_2d(sb + p * (kBlockK * 128), &tmB, n_blk * kBlockN + p * kPanel, kb * kBlockK,
                           &full_bar[stage]);
           }
-          if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+          if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
       }
     }
@@ -280,7 +287,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
-        if (++stage == Cfg::kStages) { stage = 0; phase ^= 1u; }
+        if (++stage == nst) { stage = 0; phase ^= 1u; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }

@@ -24,7 +24,7 @@ using AdamArgs = sdumc_adam_args;
 int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream);
 int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream);
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t stream);
-int launch_colsum_bf16(const __nv_bfloat16* X, long ld, long rows, float* out, cudaStream_t stream);
+int launch_colsum_bf16(const __nv_bfloat16* X, long ld, long rows, int cols, float* out, cudaStream_t stream);
 int launch_collate_pad(const __nv_bfloat16* packed, const long long* row_offset, const int* idx, int b, int Lpad, int D,
                        __nv_bfloat16* out, cudaStream_t stream);
 // chain.cu

@@ -142,6 +142,35 @@ class Engine:
         for i in range(n):
             main.wait_stream(self._streams[i])
 
+    def _side(self, fn, *keep):
+        """Run fn() on an auxiliary stream forked from the current one; joined by _join_side().  For work that is off the
+        critical path of the backward pass (weight / bias gradients: nothing downstream reads them before the
+        optimizer).  `keep` tensors are held until the join so that their memory is not reused while fn still reads it."""
+        if not self.multi_stream:
+            fn()
+            return
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_aux"):
+            self._aux, self._aux_rr, self._aux_pending, self._aux_keep = [], 0, [], []
+        if len(self._aux) < 4:
+            self._aux.append(torch.cuda.Stream(device=self.device))
+        aux = self._aux[self._aux_rr % len(self._aux)]
+        self._aux_rr += 1
+        aux.wait_stream(cur)
+        with torch.cuda.stream(aux):
+            fn()
+        self._aux_pending.append(aux)
+        self._aux_keep.extend(keep)
+
+    def _join_side(self):
+        if not getattr(self, "_aux_pending", None):
+            return
+        cur = torch.cuda.current_stream()
+        for aux in dict.fromkeys(self._aux_pending):
+            cur.wait_stream(aux)
+        self._aux_pending.clear()
+        self._aux_keep.clear()
+
     def _new(self, st: State, name: str, shape, dtype=torch.float32, zero=False):
         fn = torch.zeros if zero else torch.empty
         t = fn(shape, dtype=dtype, device=self.device)
@@ -159,22 +188,55 @@ class Engine:
                  act=ops.ACT_RELU if relu else ops.ACT_NONE, drop_p=p, drop_site=drop_site, out_f32=y,
                  out_bf16=y_bf16, seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev)
 
-    def _linear_bwd(self, W: Weights, st: State, lname: str, dY: torch.Tensor, x_bf16: torch.Tensor, *,
+    def _linear_bwd(self, W: Weights, st: State, lname: str, dY: Optional[torch.Tensor], x_bf16: torch.Tensor, *,
                     Y: Optional[torch.Tensor], dropped: bool, dX: Optional[torch.Tensor], dX_mode=ops.OUT_STORE,
-                    dY2: Optional[torch.Tensor] = None):
-        """Backward of y = [drop(relu(]x W^T + b[))]: bias/weight gradients accumulate into W.grads."""
+                    dY2: Optional[torch.Tensor] = None, dZ: Optional[torch.Tensor] = None,
+                    below: Optional[Tuple[torch.Tensor, bool]] = None) -> Optional[torch.Tensor]:
+        """Backward of y = [drop(relu(]x W^T + b[))]: bias/weight gradients accumulate into W.grads.
+
+        Critical path: act_bwd (dY -> bf16 dZ, bias gradient) -> dX = dZ W.  The weight gradient dW += dZ^T x runs on a
+        side stream (nothing reads it before the optimizer).  With `dZ` given (the layer above already produced it, see
+        `below`) act_bwd is skipped and the bias gradient is a column sum on the side stream.  With
+        below = (Y_below, dropped_below) the input x of this layer is the output of another Linear+ReLU(+dropout):
+        the dX GEMM applies that layer's ReLU / dropout gate in its epilogue and returns its dZ (bf16) directly -
+        one kernel on the critical path per layer instead of three."""
         cfg = st.cfg
-        rows, N = dY.shape
-        K = W.f32(lname + ".weight").shape[1]
-        dZ = torch.empty(rows, N, dtype=torch.bfloat16, device=self.device)
-        scale = 1.0 / (1.0 - MLP_P) if (dropped and cfg.dropout) else 1.0
-        ops.act_bwd(dY, dZ, rows=rows, cols=N, Y=Y, scale=scale, db=W.grad(lname + ".bias"), dY2=dY2)
-        # dW[N,K] += dZ^T x : both operands MN-major (reduction over the rows), split-K with fp32 atomics
-        ops.gemm(dZ, x_bf16, M=N, N=K, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, N, K),
-                 out_f32=W.grad(lname + ".weight"), f32_mode=ops.OUT_ATOMIC)
+        N, K = W.f32(lname + ".weight").shape
+        if dZ is None:
+            rows = dY.shape[0]
+            dZ = torch.empty(rows, N, dtype=torch.bfloat16, device=self.device)
+            scale = 1.0 / (1.0 - MLP_P) if (dropped and cfg.dropout) else 1.0
+            ops.act_bwd(dY, dZ, rows=rows, cols=N, Y=Y, scale=scale, db=W.grad(lname + ".bias"), dY2=dY2)
+            self._side(lambda: self._dw(W, lname, dZ, x_bf16), dZ)
+        else:
+            def grads():
+                ops.colsum_bf16(dZ, W.grad(lname + ".bias"))
+                self._dw(W, lname, dZ, x_bf16)
+            self._side(grads, dZ)
+        rows = dZ.shape[0]
+        if below is not None:
+            Yb, dropped_b = below
+            dZb = torch.empty(rows, K, dtype=torch.bfloat16, device=self.device)
+            sc = 1.0 / (1.0 - MLP_P) if (dropped_b and cfg.dropout) else 1.0
+            ops.gemm(dZ, W.bf16(lname + ".weight"), M=rows, N=K, K=N, b_mn=True, gate=Yb, gate_scale=sc, out_bf16=dZb)
+            return dZb
         if dX is not None:
             # dX[rows,K] = dZ W : A K-major, B = W[N,K] read MN-major
             ops.gemm(dZ, W.bf16(lname + ".weight"), M=rows, N=K, K=N, b_mn=True, out_f32=dX, f32_mode=dX_mode)
+        return None
+
+    def _dw(self, W: Weights, lname: str, dZ: torch.Tensor, x_bf16: torch.Tensor):
+        # dW[N,K] += dZ^T x : both operands MN-major (reduction over the rows), split-K with fp32 atomics
+        rows, N = dZ.shape
+        K = x_bf16.shape[1]
+        ops.gemm(dZ, x_bf16, M=N, N=K, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, N, K),
+                 out_f32=W.grad(lname + ".weight"), f32_mode=ops.OUT_ATOMIC)
+
+    def _mlp2_bwd(self, W: Weights, st: State, name: str, dY: torch.Tensor, *, Y_hi, x_hi_bf16, Y_lo, x_lo_bf16, dX,
+                  dX_mode=ops.OUT_STORE):
+        """Backward of the two-layer MLP() blocks (reference :264-273): name.3 (above) then name.0 (below)."""
+        dZ_lo = self._linear_bwd(W, st, name + ".3", dY, x_hi_bf16, Y=Y_hi, dropped=True, dX=None, below=(Y_lo, True))
+        self._linear_bwd(W, st, name + ".0", None, x_lo_bf16, Y=None, dropped=True, dX=dX, dX_mode=dX_mode, dZ=dZ_lo)
 
     # ------------------------------------------------------------------ forward
     def forward(self, W: Weights, inputs: Dict[str, torch.Tensor], cfg: Cfg) -> State:
@@ -383,11 +445,10 @@ class Engine:
         # B1. RnC head  rnc = Linear(64,64)(relu(Linear(128,64)(f)))
         df = d_fused.reshape(R, 128).clone() if d_fused is not None else z(R, 128)
         if d_rnc is not None:
-            d_o1 = e(R, 64)
-            self._linear_bwd(W, st, "orgin_linear_change.2", d_rnc.reshape(R, 64), t["o1_bf16"], Y=None, dropped=False,
-                             dX=d_o1)
-            self._linear_bwd(W, st, "orgin_linear_change.0", d_o1, t["f_bf16"], Y=t["o1"], dropped=False, dX=df,
-                             dX_mode=ops.OUT_ADD)
+            dZ_o1 = self._linear_bwd(W, st, "orgin_linear_change.2", d_rnc.reshape(R, 64), t["o1_bf16"], Y=None,
+                                     dropped=False, dX=None, below=(t["o1"], False))
+            self._linear_bwd(W, st, "orgin_linear_change.0", None, t["f_bf16"], Y=None, dropped=False, dX=df,
+                             dX_mode=ops.OUT_ADD, dZ=dZ_o1)
         # B2. head + query gate
         dWc = e(R, NQ * 128)
         dx2 = e(R, 128)
@@ -396,10 +457,8 @@ class Engine:
                       R=R, dWc=dWc, dx2=dx2, dWr=W.grad("cross_fc_att.weight"), dbr=W.grad("cross_fc_att.bias"),
                       dWv=W.grad("fc_out_v.weight"), dbv=W.grad("fc_out_v.bias"))
         # B3. cross_attention_mlp
-        dx1 = e(R, 256)
-        self._linear_bwd(W, st, "cross_attention_mlp.3", dx2, t["x1_bf16"], Y=t["x2"], dropped=True, dX=dx1)
-        self._linear_bwd(W, st, "cross_attention_mlp.0", dx1, t["Wc_bf16"], Y=t["x1"], dropped=True, dX=dWc,
-                         dX_mode=ops.OUT_ADD)
+        self._mlp2_bwd(W, st, "cross_attention_mlp", dx2, Y_hi=t["x2"], x_hi_bf16=t["x1_bf16"], Y_lo=t["x1"],
+                       x_lo_bf16=t["Wc_bf16"], dX=dWc, dX_mode=ops.OUT_ADD)
         # B4. gate-weighted sum
         dc = [e(R * NQ, 128) for _ in range(3)]
         dg_extra = e(R, 4)
@@ -407,12 +466,10 @@ class Engine:
         ops.weight_bwd(dWc, [t[f"c.{m}"] for m in range(3)], t["g"], R=R, dc=dc, dg=dg_extra, dc_extra=extra)
         # B5. cross MLPs -> gradient of the (dropped) pooled cross-attention outputs
         dC = [e(R * NQ, G) for _ in range(3)]
-        dc1s = [e(R * NQ, 256) for _ in range(3)]
 
         def cross_mlp_bwd(m):
-            name = CROSS_MLPS[m]
-            self._linear_bwd(W, st, name + ".3", dc[m], t[f"c1_bf16.{m}"], Y=t[f"c.{m}"], dropped=True, dX=dc1s[m])
-            self._linear_bwd(W, st, name + ".0", dc1s[m], t[f"C_bf16.{m}"], Y=t[f"c1.{m}"], dropped=True, dX=dC[m])
+            self._mlp2_bwd(W, st, CROSS_MLPS[m], dc[m], Y_hi=t[f"c.{m}"], x_hi_bf16=t[f"c1_bf16.{m}"], Y_lo=t[f"c1.{m}"],
+                           x_lo_bf16=t[f"C_bf16.{m}"], dX=dC[m])
         self._parallel(3, cross_mlp_bwd)
         # B6. Cross_Attention blocks
         dH: Dict[str, torch.Tensor] = {}
@@ -430,10 +487,10 @@ class Engine:
                                      dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH, started=started)
         self._parallel(3, cross_attn_bwd)
         # B7. query projections -> dQ
-        dQ = e(R * NQ, G)
-        for m in range(3):
-            self._linear_bwd(W, st, f"cross_att_fra2utt_{m}.query_proj", dQp[m], t["Q_bf16"].view(R * NQ, G), Y=None,
-                             dropped=False, dX=dQ, dX_mode=ops.OUT_STORE if m == 0 else ops.OUT_ADD)
+        dQ = z(R * NQ, G)                            # the three blocks add their share side by side (fp32 reds)
+        self._parallel(3, lambda m: self._linear_bwd(W, st, f"cross_att_fra2utt_{m}.query_proj", dQp[m],
+                                                     t["Q_bf16"].view(R * NQ, G), Y=None, dropped=False, dX=dQ,
+                                                     dX_mode=ops.OUT_ATOMIC))
         dQ = dQ.view(R, NQ * G)
         # B8. 7 query MLPs
         dqin = e(4, R, G)
@@ -451,21 +508,17 @@ class Engine:
         da2 = e(R, G)
         ops.gate_bwd(dqin, dg_extra, t["g"], t["cat"], t["a2"], W.f32("fc_att.weight"), R=R, dh=dcat, da2=da2,
                      dWg=W.grad("fc_att.weight"), dbg=W.grad("fc_att.bias"))
-        da1 = e(R, G)
-        self._linear_bwd(W, st, "attention_mlp.3", da2, t["a1_bf16"], Y=t["a2"], dropped=True, dX=da1)
-        self._linear_bwd(W, st, "attention_mlp.0", da1, t["cat_bf16"], Y=t["a1"], dropped=True, dX=dcat,
-                         dX_mode=ops.OUT_ADD)
+        self._mlp2_bwd(W, st, "attention_mlp", da2, Y_hi=t["a2"], x_hi_bf16=t["a1_bf16"], Y_lo=t["a1"],
+                       x_lo_bf16=t["cat_bf16"], dX=dcat, dX_mode=ops.OUT_ADD)
         # B9. modality MLPs -> gradient of the (dropped) FRA2UTT outputs
         du = [e(R, G) for _ in range(3)]
-        dh1s = [e(R, G) for _ in range(3)]
 
         def modality_mlp_bwd(m):
-            name = MODALITY_MLPS[m]
-            self._linear_bwd(W, st, name + ".3", dcat[:, m * G:(m + 1) * G], t[f"h1_bf16.{m}"],
-                             Y=t["cat"][:, m * G:(m + 1) * G], dropped=True, dX=dh1s[m])
-            self._linear_bwd(W, st, name + ".0", dh1s[m], t[f"u_bf16.{m}"], Y=t[f"h1.{m}"], dropped=True, dX=du[m])
+            self._mlp2_bwd(W, st, MODALITY_MLPS[m], dcat[:, m * G:(m + 1) * G], Y_hi=t["cat"][:, m * G:(m + 1) * G],
+                           x_hi_bf16=t[f"h1_bf16.{m}"], Y_lo=t[f"h1.{m}"], x_lo_bf16=t[f"u_bf16.{m}"], dX=du[m])
         self._parallel(3, modality_mlp_bwd)
         if on_chain_grads_final is not None:
+            self._join_side()                         # the chain's weight gradients ran on side streams
             on_chain_grads_final()
         # B10. FRA2UTT_new blocks
         def fra2utt_bwd(m):
@@ -487,6 +540,7 @@ class Engine:
                      out_f32=W.grad(wname + ".weight"), f32_mode=ops.OUT_ATOMIC)
             ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
         self._parallel(len(items), inproj_bwd)
+        self._join_side()
 
     def _attn_block_bwd(self, W: Weights, st: State, p: int, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
                         dH: Dict[str, torch.Tensor], started: Dict[str, bool]):

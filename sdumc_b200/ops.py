@@ -83,9 +83,10 @@ def collate_pad(packed: torch.Tensor, row_offset: torch.Tensor, idx: torch.Tenso
 
 
 def colsum_bf16(X: torch.Tensor, out: torch.Tensor) -> None:
-    """out[256] += column sums of the bf16 matrix X [rows,256]."""
-    assert X.dtype == torch.bfloat16 and X.shape[1] == G and out.numel() == G
-    check(_lib.lib().sdumc_colsum_bf16(ptr(X), _ld(X), X.shape[0], ptr(out), current_stream()), "sdumc_colsum_bf16")
+    """out[cols] += column sums of the bf16 matrix X [rows,cols]."""
+    assert X.dtype == torch.bfloat16 and out.numel() == X.shape[1] and out.dtype == torch.float32
+    check(_lib.lib().sdumc_colsum_bf16(ptr(X), _ld(X), X.shape[0], X.shape[1], ptr(out), current_stream()),
+          "sdumc_colsum_bf16")
 
 
 def pool_fwd(X, S, *, B, L, nq, O_pre, out, out_stride_b, out_bf16=None, drop_p=0.0, site=0, seed=0, step=0,
