@@ -233,6 +233,52 @@ __device__ __forceinline__ void mma_1688(float (&c)[4], uint32_t a0, uint32_t a1
                : "=f"(c[0]), "=f"(c[1]), "=f"(c[2]), "=f"(c[3])
                : "r"(a0), "r"(a1), "r"(b0), "f"(0.f), "f"(0.f), "f"(0.f), "f"(0.f));
 }
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on one TPC share one UMMA; rank 0 is the leader ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the pair's even (leader) CTA
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of a pair; the transaction bytes are counted on the LEADER CTA's mbarrier
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar) & kPeerBitMask)
+      : "memory");
+}
+// arrive on the leader CTA's copy of `bar` (from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & kPeerBitMask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_result, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A * B with M = 256 (128 rows per CTA), B split along N between the CTAs; leader only
+__device__ __forceinline__ void umma_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// all previously issued pair MMAs arrive on `bar` (same offset) in BOTH CTAs when they complete
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
 }
@@ -309,9 +355,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t 
 }
 
 // UMMA instruction descriptor: fp32 accumulate, M = 128, N = n, A/B both `fmt` (1 = bf16, 2 = tf32)
-__host__ __device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, uint32_t a_mn, uint32_t b_mn, uint32_t n) {
+__host__ __device__ __forceinline__ uint32_t make_idesc(uint32_t fmt, uint32_t a_mn, uint32_t b_mn, uint32_t n,
+                                                        uint32_t m = 128u) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) |
-         ((128u >> 4) << 24);
+         ((m >> 4) << 24);
 }
 
 __device__ __forceinline__ float tanh_fast(float x) {

@@ -1,6 +1,7 @@
 // sdumc_b200 — host side of the tcgen05 GEMM: TMA tensor-map construction (cached) and launch.
 #include "gemm.cuh"
 
+#include <algorithm>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -126,20 +127,44 @@ int num_sms() {
   return sms[dev];
 }
 
-template <int kBlockN, bool kTF32, int kKind>
+template <int kBlockN, bool kTF32, int kKind, bool kPair = false>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& sh, const GemmEpi& ep,
                        int grid, cudaStream_t stream) {
   using Cfg = GemmCfg<kBlockN>;
   static bool attr_done[kMaxDevices] = {false};
-  auto kern = gemm_tcgen05_kernel<kBlockN, kTF32, kKind>;
+  auto kern = gemm_tcgen05_kernel<kBlockN, kTF32, kKind, kPair>;
   const int dev = current_device();
   if (!attr_done[dev]) {
     SDUMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done[dev] = true;
   }
-  kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, sh, ep);
+  if constexpr (kPair) {
+    // clusters of two CTAs (one TPC): cta_group::2 MMAs
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SDUMC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, sh, ep));
+  } else {
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, sh, ep);
+  }
   SDUMC_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int kKind>
+static int launch_n256_bf16(bool pair, const CUtensorMap& ta, const CUtensorMap& tb, const GemmShape& sh,
+                            const GemmEpi& ep, int grid, cudaStream_t stream) {
+  if (pair) return launch_inst<256, false, kKind, true>(ta, tb, sh, ep, grid, stream);
+  return launch_inst<256, false, kKind, false>(ta, tb, sh, ep, grid, stream);
 }
 
 int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& shape, const GemmEpi& epi, bool tf32,
@@ -193,20 +218,28 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
                         epi.act == ACT_NONE,
                     "gemm: split-K requires a plain atomic fp32 epilogue");
 
+  const long n_tiles = (sh.N + block_n - 1) / block_n;
+  // CTA pairs (cta_group::2) for the large bf16 N-tile-256 problems: a deeper ring per byte of shared memory and B
+  // fetched once per pair.  Needs at least one full wave of work; `max_ctas` < 0 forces single-CTA mode (A/B timing).
+  const bool pair = !tf32 && block_n == 256 && m_tiles >= 2 && max_ctas >= 0 && (sms % 2 == 0) &&
+                    (long)m_tiles * n_tiles * sh.k_splits >= sms;
+  if (max_ctas < 0) max_ctas = 0;
   CUtensorMap ta, tb;
   if (!sh.a_mn) SDUMC_TRY(get_tmap(A.ptr, A.ld, sh.K, sh.M, block_k, 128, elem, &ta));
   else          SDUMC_TRY(get_tmap(A.ptr, A.ld, sh.M, sh.K, panel, block_k, elem, &ta));
-  if (!sh.b_mn) SDUMC_TRY(get_tmap(B.ptr, B.ld, sh.K, sh.N, block_k, block_n, elem, &tb));
+  if (!sh.b_mn) SDUMC_TRY(get_tmap(B.ptr, B.ld, sh.K, sh.N, block_k, pair ? block_n / 2 : block_n, elem, &tb));
   else          SDUMC_TRY(get_tmap(B.ptr, B.ld, sh.N, sh.K, panel, block_k, elem, &tb));
 
-  const long n_tiles = (sh.N + block_n - 1) / block_n;
-  long tiles = (long)m_tiles * n_tiles * sh.k_splits;
-  int grid = (int)(tiles < sms ? tiles : sms);
-  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  // scheduling units: tiles, or - for pairs - two neighbouring M tiles
+  long tiles = (long)(pair ? (m_tiles + 1) / 2 : m_tiles) * n_tiles * sh.k_splits;
+  const int slots = pair ? sms / 2 : sms;
+  int grid = (int)(tiles < slots ? tiles : slots);
+  if (max_ctas > 0 && grid > (pair ? max_ctas / 2 : max_ctas)) grid = std::max(1, pair ? max_ctas / 2 : max_ctas);
   // resident B: one N tile whose whole K extent fits beside an A-only ring, and at least two tiles per CTA to
   // amortise it
   const int stages = block_n == 256 ? 4 : (block_n == 128 ? 6 : 8);
   sh.b_res = (n_tiles == 1 && sh.k_splits == 1 && nkb <= stages && tiles >= 2L * grid) ? 1 : 0;
+  if (pair) grid *= 2;
 
   if (tf32) {
     SDUMC_CHECK_ARG(epi.kind == EPI_GENERIC, "gemm: tf32 operands support the generic epilogue only");
@@ -216,14 +249,14 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
   }
   if (epi.kind == EPI_INPROJ) {
     SDUMC_CHECK_ARG(block_n == 256, "gemm: in-proj epilogue is instantiated for block_n 256 (N = 256)");
-    return launch_inst<256, false, KIND_INPROJ>(ta, tb, sh, epi, grid, stream);
+    return launch_n256_bf16<KIND_INPROJ>(pair, ta, tb, sh, epi, grid, stream);
   }
-  if (epi.kind == EPI_KEYPROJ) return launch_inst<256, false, KIND_KEYPROJ>(ta, tb, sh, epi, grid, stream);
+  if (epi.kind == EPI_KEYPROJ) return launch_n256_bf16<KIND_KEYPROJ>(pair, ta, tb, sh, epi, grid, stream);
   // 'bf16 += acc * frame mask' without any other option: the dH accumulation of the attention backward
   const bool pure_rmw = block_n == 256 && epi.out_bf16 && epi.bf16_mode == OUT_ADD && !epi.out_f32 && !epi.bias &&
                         epi.act == ACT_NONE && !epi.gate && epi.drop_p == 0.f;
-  if (pure_rmw) return launch_inst<256, false, KIND_RMW>(ta, tb, sh, epi, grid, stream);
-  if (block_n == 256) return launch_inst<256, false, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
+  if (pure_rmw) return launch_n256_bf16<KIND_RMW>(pair, ta, tb, sh, epi, grid, stream);
+  if (block_n == 256) return launch_n256_bf16<KIND_GENERIC>(pair, ta, tb, sh, epi, grid, stream);
   if (block_n == 128) return launch_inst<128, false, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
   return launch_inst<64, false, KIND_GENERIC>(ta, tb, sh, epi, grid, stream);
 }

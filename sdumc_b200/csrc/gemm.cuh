@@ -132,11 +132,23 @@ struct GemmCfg {
   static constexpr int kThreads = 384;
 };
 
-template <int kBlockN, bool kTF32, int kKind>
+// kPair: the kernel runs as clusters of two CTAs on one TPC (cta_group::2).  One UMMA of M = 256 covers the pair's two
+// 128-row tiles; each CTA stages its own A tile but only HALF of the B tile (split along N), so a B stage costs half
+// the shared memory and the ring (or the A-only ring behind a resident weight) gets deeper: 6 instead of 4 full stages,
+// 8 instead of 5 A tiles behind a resident 256 x 256 weight - the frame-level GEMMs are bound by DRAM latency x ring
+// depth, not by the MMA.  The leader CTA (cluster rank 0) issues every MMA; TMA loads of both CTAs count their bytes on
+// the leader's barriers; tcgen05.commit multicasts "stage free" / "accumulator ready" to both CTAs; the epilogue warps
+// of both CTAs report "accumulator drained" to the leader.  B is also fetched once per pair instead of once per CTA.
+template <int kBlockN, bool kTF32, int kKind, bool kPair = false>
 __global__ void __launch_bounds__(384, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                     const GemmShape sh, const GemmEpi ep) {
   using Cfg = GemmCfg<kBlockN>;
+  static_assert(!kPair || (!kTF32 && kBlockN == 256), "CTA pairs: bf16, BLOCK_N = 256");
+  constexpr int kBCta = kPair ? Cfg::kBBytes / 2 : Cfg::kBBytes;      // bytes of B per k-block held by one CTA
+  constexpr int kNCta = kPair ? kBlockN / 2 : kBlockN;               // columns of the N tile staged by one CTA
+  const uint32_t crank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
   constexpr int kElem = kTF32 ? 4 : 2;
   constexpr int kBlockK = 128 / kElem;   // elements (K-major) == k rows (MN-major) per stage
   constexpr int kUmmaK = 32 / kElem;     // 16 (bf16) / 8 (tf32)
@@ -163,12 +175,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = (sh.M + 127) / 128;
+  // M tiles per scheduling unit: a pair works on two neighbouring M tiles (CTA rank r takes tile 2 * unit + r; with
+  // an odd tile count the last pair's second tile is out of range: TMA zero-fills it, the epilogue stores nothing)
+  const int m_tiles = kPair ? ((sh.M + 127) / 128 + 1) / 2 : (sh.M + 127) / 128;
   const int n_tiles = (sh.N + kBlockN - 1) / kBlockN;
   const int nkb = (sh.K + kBlockK - 1) / kBlockK;
   const int num_tiles = m_tiles * n_tiles * sh.k_splits;
+  const int cta0 = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;      // scheduling unit index / count
+  const int nctas = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   // ring depth: full stages, or - with B resident - as many A tiles as fit behind it
-  const int nst = b_res ? min(Cfg::kMaxStages, (Cfg::kRingBytes - nkb * Cfg::kBBytes) / Cfg::kABytes) : Cfg::kStages;
+  const int nst = b_res ? min(Cfg::kMaxStages, (Cfg::kRingBytes - nkb * kBCta) / Cfg::kABytes)
+                        : min(Cfg::kMaxStages, Cfg::kRingBytes / (Cfg::kABytes + kBCta));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -181,14 +198,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);  // one arrival per epilogue warp
+      mbar_init(&tempty_bar[i], kPair ? 8 : 4);  // one arrival per epilogue warp (of both CTAs of a pair)
     }
     mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 2) {
+    if constexpr (kPair) tmem_alloc_pair(tmem_slot, Cfg::kTmemCols);
+    else tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -198,57 +219,63 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      uint8_t* ring_base = stage_base + (b_res ? nkb * Cfg::kBBytes : 0);
-      const int stage_stride = b_res ? Cfg::kABytes : Cfg::kStageBytes;
-      if (b_res && blockIdx.x < num_tiles) {
-        mbar_expect_tx(bres_bar, (uint32_t)(nkb * Cfg::kBBytes));
+      uint8_t* ring_base = stage_base + (b_res ? nkb * kBCta : 0);
+      const int stage_stride = b_res ? Cfg::kABytes : Cfg::kABytes + kBCta;
+      // loads of a pair count on the leader's barrier; only the leader posts the expected byte count (of both CTAs)
+      auto load = [&](void* dst, const CUtensorMap* tm, int c0, int c1, uint64_t* bar) {
+        if constexpr (kPair) tma_load_2d_pair(dst, tm, c0, c1, bar);
+        else tma_load_2d(dst, tm, c0, c1, bar);
+      };
+      constexpr uint32_t kTxMul = kPair ? 2u : 1u;
+      const int n_half = (int)crank * kNCta;            // first column of this CTA's share of the N tile
+      if (b_res && cta0 < num_tiles) {
+        if (leader) mbar_expect_tx(bres_bar, kTxMul * (uint32_t)(nkb * kBCta));
         for (int kb = 0; kb < nkb; ++kb) {
-          uint8_t* sb = stage_base + kb * Cfg::kBBytes;
+          uint8_t* sb = stage_base + kb * kBCta;
           if (!sh.b_mn) {
-            tma_load_2d(sb, &tmB, kb * kBlockK, 0, bres_bar);
+            load(sb, &tmB, kb * kBlockK, n_half, bres_bar);
           } else {
 #pragma unroll
-            for (int p = 0; p < kBlockN / kPanel; ++p)
-              tma_load_2d(sb + p * (kBlockK * 128), &tmB, p * kPanel, kb * kBlockK, bres_bar);
+            for (int p = 0; p < kNCta / kPanel; ++p)
+              load(sb + p * (kBlockK * 128), &tmB, n_half + p * kPanel, kb * kBlockK, bres_bar);
           }
         }
       }
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int t = cta0; t < num_tiles; t += nctas) {
         const int ks = t / (m_tiles * n_tiles);
         const int mn = t - ks * (m_tiles * n_tiles);
-        const int m_blk = mn / n_tiles, n_blk = mn - m_blk * n_tiles;
+        const int mu = mn / n_tiles, n_blk = mn - mu * n_tiles;
+        const int m_blk = kPair ? 2 * mu + (int)crank : mu;
         const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
         const int kb1 = (int)(((long)(ks + 1) * nkb) / sh.k_splits);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           uint8_t* sa = ring_base + stage * stage_stride;
           uint8_t* sb = sa + Cfg::kABytes;
-          mbar_expect_tx(&full_bar[stage], b_res ? Cfg::kABytes : Cfg::kStageBytes);
+          if (leader) mbar_expect_tx(&full_bar[stage], kTxMul * (uint32_t)(b_res ? Cfg::kABytes : Cfg::kABytes + kBCta));
           if (!sh.a_mn) {
-            tma_load_2d(sa, &tmA, kb * kBlockK, m_blk * 128, &full_bar[stage]);
+            load(sa, &tmA, kb * kBlockK, m_blk * 128, &full_bar[stage]);
           } else {
 #pragma unroll
             for (int p = 0; p < 128 / kPanel; ++p)
-              tma_load_2d(sa + p * (kBlockK * 128), &tmA, m_blk * 128 + p * kPanel, kb * kBlockK,
-                          &full_bar[stage]);
+              load(sa + p * (kBlockK * 128), &tmA, m_blk * 128 + p * kPanel, kb * kBlockK, &full_bar[stage]);
           }
           if (b_res) {
             // B is resident
           } else if (!sh.b_mn) {
-            tma_load_2d(sb, &tmB, kb * kBlockK, n_blk * kBlockN, &full_bar[stage]);
+            load(sb, &tmB, kb * kBlockK, n_blk * kBlockN + n_half, &full_bar[stage]);
           } else {
 #pragma unroll
-            for (int p = 0; p < kBlockN / kPanel; ++p)
-              tma_load_2d(sb + p * (kBlockK * 128), &tmB, n_blk * kBlockN + p * kPanel, kb * kBlockK,
-                          &full_bar[stage]);
+            for (int p = 0; p < kNCta / kPanel; ++p)
+              load(sb + p * (kBlockK * 128), &tmB, n_blk * kBlockN + n_half + p * kPanel, kb * kBlockK, &full_bar[stage]);
           }
           if (++stage == nst) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    const uint32_t idesc = make_idesc(kFmt, (uint32_t)sh.a_mn, (uint32_t)sh.b_mn, (uint32_t)kBlockN);
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (one thread; the leader CTA of a pair) =====================
+    const uint32_t idesc = make_idesc(kFmt, (uint32_t)sh.a_mn, (uint32_t)sh.b_mn, (uint32_t)kBlockN, kPair ? 256u : 128u);
     const uint32_t mn_lbo = (uint32_t)(kBlockK * 128);
     const uint32_t mn_sbo = 1024u;
     const uint32_t a_lbo = sh.a_mn ? mn_lbo : 16u, a_sbo = sh.a_mn ? mn_sbo : 1024u;
@@ -260,10 +287,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t ring_u32 = smem_u32(stage_base) + (b_res ? (uint32_t)(nkb * Cfg::kBBytes) : 0u);
-    const uint32_t stage_stride = b_res ? (uint32_t)Cfg::kABytes : (uint32_t)Cfg::kStageBytes;
-    if (b_res && blockIdx.x < num_tiles) mbar_wait(bres_bar, 0u);
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const uint32_t ring_u32 = smem_u32(stage_base) + (b_res ? (uint32_t)(nkb * kBCta) : 0u);
+    const uint32_t stage_stride = b_res ? (uint32_t)Cfg::kABytes : (uint32_t)(Cfg::kABytes + kBCta);
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (kPair) umma_commit_pair(bar);
+      else umma_commit(bar);
+    };
+    if (b_res && cta0 < num_tiles) mbar_wait(bres_bar, 0u);
+    for (int t = cta0; t < num_tiles; t += nctas) {
       const int ks = t / (m_tiles * n_tiles);
       const int kb0 = (int)(((long)ks * nkb) / sh.k_splits);
       const int kb1 = (int)(((long)(ks + 1) * nkb) / sh.k_splits);
@@ -275,16 +306,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = ring_u32 + (uint32_t)stage * stage_stride;
-          const uint32_t sb = b_res ? smem_u32(stage_base) + (uint32_t)(kb * Cfg::kBBytes) : sa + Cfg::kABytes;
+          const uint32_t sb = b_res ? smem_u32(stage_base) + (uint32_t)(kb * kBCta) : sa + Cfg::kABytes;
           const uint64_t da = make_smem_desc(sa, a_lbo, a_sbo);
           const uint64_t db = make_smem_desc(sb, b_lbo, b_sbo);
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            umma_ss<kTF32>(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc,
+            if constexpr (kPair)
+              umma_ss_pair(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc,
                            (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_ss<kTF32>(tmem_d, da + (uint64_t)(k * a_kstep), db + (uint64_t)(k * b_kstep), idesc,
+                             (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);                 // smem slot free once these MMAs retire
-          if (kb == kb1 - 1) umma_commit(&tfull_bar[acc]);  // accumulator complete
+          commit(&empty_bar[stage]);                 // smem slot free (in both CTAs of a pair) once these MMAs retire
+          if (kb == kb1 - 1) commit(&tfull_bar[acc]);  // accumulator complete
         }
         __syncwarp();
         if (++stage == nst) { stage = 0; phase ^= 1u; }
@@ -307,11 +342,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool ctx_shared = kKind == KIND_KEYPROJ && ep.q_stride == 0 && ep.nq == 1;
     constexpr int NC = kBlockN / 32;
     int li = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++li) {
+    for (int t = cta0; t < num_tiles; t += nctas, ++li) {
       if ((li & 1) != grp) continue;
       const int acc = grp;
       const int mn = t % (m_tiles * n_tiles);
-      const int m_blk = mn / n_tiles, n_blk = mn - m_blk * n_tiles;
+      const int mu = mn / n_tiles, n_blk = mn - mu * n_tiles;
+      const int m_blk = kPair ? 2 * mu + (int)crank : mu;
       // stage the per-column vectors of this tile (group-local named barrier: 128 threads)
       for (int j = gtid; j < kBlockN; j += 128) {
         const int n = n_blk * kBlockN + j;
@@ -572,16 +608,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (kPair) mbar_arrive_leader(&tempty_bar[acc]);   // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(&tempty_bar[acc]);
+      }
       acc_phase ^= 1u;
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();   // neither CTA leaves (or frees TMEM) while the peer may still signal it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (kPair) tmem_dealloc_pair(tmem_base, Cfg::kTmemCols);
+    else tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 

@@ -198,8 +198,9 @@ class Engine:
         side stream (nothing reads it before the optimizer).  With `dZ` given (the layer above already produced it, see
         `below`) act_bwd is skipped and the bias gradient is a column sum on the side stream.  With
         below = (Y_below, dropped_below) the input x of this layer is the output of another Linear+ReLU(+dropout):
-        the dX GEMM applies that layer's ReLU / dropout gate in its epilogue and returns its dZ (bf16) directly -
-        one kernel on the critical path per layer instead of three."""
+        the dX GEMM applies that layer's ReLU / dropout gate in its epilogue and returns its dZ directly (bf16 for the
+        GEMMs + the unrounded fp32 values for the bias gradient) - one kernel on the critical path per layer
+        instead of three."""
         cfg = st.cfg
         N, K = W.f32(lname + ".weight").shape
         if dZ is None:
@@ -209,17 +210,22 @@ class Engine:
             ops.act_bwd(dY, dZ, rows=rows, cols=N, Y=Y, scale=scale, db=W.grad(lname + ".bias"), dY2=dY2)
             self._side(lambda: self._dw(W, lname, dZ, x_bf16), dZ)
         else:
+            dZ, dZ32 = dZ                             # bf16 for the GEMMs, fp32 (same values before rounding) for the bias
+
             def grads():
-                ops.colsum_bf16(dZ, W.grad(lname + ".bias"))
+                scratch = torch.empty_like(dZ)
+                ops.act_bwd(dZ32, scratch, rows=dZ.shape[0], cols=N, db=W.grad(lname + ".bias"))
                 self._dw(W, lname, dZ, x_bf16)
-            self._side(grads, dZ)
+            self._side(grads, dZ, dZ32)
         rows = dZ.shape[0]
         if below is not None:
             Yb, dropped_b = below
             dZb = torch.empty(rows, K, dtype=torch.bfloat16, device=self.device)
+            dZb32 = torch.empty(rows, K, dtype=torch.float32, device=self.device)
             sc = 1.0 / (1.0 - MLP_P) if (dropped_b and cfg.dropout) else 1.0
-            ops.gemm(dZ, W.bf16(lname + ".weight"), M=rows, N=K, K=N, b_mn=True, gate=Yb, gate_scale=sc, out_bf16=dZb)
-            return dZb
+            ops.gemm(dZ, W.bf16(lname + ".weight"), M=rows, N=K, K=N, b_mn=True, gate=Yb, gate_scale=sc, out_bf16=dZb,
+                     out_f32=dZb32)
+            return dZb, dZb32
         if dX is not None:
             # dX[rows,K] = dZ W : A K-major, B = W[N,K] read MN-major
             ops.gemm(dZ, W.bf16(lname + ".weight"), M=rows, N=K, K=N, b_mn=True, out_f32=dX, f32_mode=dX_mode)

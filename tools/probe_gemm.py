@@ -144,7 +144,7 @@ def run_case(name: str) -> dict:
 
         def go():
             ops.gemm(A, B, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, k_splits=ks, out_bf16=None if noout else outb,
-                     out_f32=None if noout else outf, block_n=bn,
+                     out_f32=None if noout else outf, block_n=bn, max_ctas=-1 if dbg == 1 else 0,   # -1: no CTA pairs
                      f32_mode=ops.OUT_ATOMIC if ks > 1 else ops.OUT_STORE)
         for _ in range(3):
             go()
@@ -275,7 +275,8 @@ def main():
     OUT.mkdir(exist_ok=True)
     log = open(OUT / "probe_gemm.jsonl", "w")
     n_bad = 0
-    for c in CASES:
+    cases = sys.argv[sys.argv.index("--cases") + 1].split(",") if "--cases" in sys.argv else CASES
+    for c in cases:
         t0 = time.time()
         try:
             p = subprocess.run([sys.executable, __file__, "--case", c], capture_output=True, text=True, timeout=180)
@@ -290,7 +291,7 @@ def main():
         print(s, flush=True)
         log.write(s + "\n")
         log.flush()
-    print(f"probe_gemm: {len(CASES) - n_bad}/{len(CASES)} ok")
+    print(f"probe_gemm: {len(cases) - n_bad}/{len(cases)} ok")
 
 
 if __name__ == "__main__":
