@@ -136,10 +136,11 @@ def run_case(name: str) -> dict:
         noout = len(rest) > 5 and rest[5] == "noout"
         bn = int(rest[6]) if len(rest) > 6 else 0
         dbg = int(rest[7]) if len(rest) > 7 else 0
-        A = mk((K, M) if a_mn else (M, K), torch.bfloat16)
-        B = mk((K, N) if b_mn else (N, K), torch.bfloat16)
+        dt = torch.float32 if (len(rest) > 8 and rest[8] == "f32") else torch.bfloat16   # f32: tf32 MMAs, fp32 + bf16 outputs
+        A = mk((K, M) if a_mn else (M, K), dt)
+        B = mk((K, N) if b_mn else (N, K), dt)
         outb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16) if ks == 1 else None
-        outf = torch.zeros(M, N, device=dev) if ks > 1 else None
+        outf = torch.zeros(M, N, device=dev) if (ks > 1 or dt == torch.float32) else None
         flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
         def go():
