@@ -172,13 +172,6 @@ int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sha
                 int block_n, int max_ctas, cudaStream_t stream) {
   GemmShape sh = shape;
   SDUMC_CHECK_ARG(sh.M > 0 && sh.N > 0 && sh.K > 0, "gemm: empty problem M=%d N=%d K=%d", sh.M, sh.N, sh.K);
-  // utterance-level (small-M) problems: the low-latency warp-MMA kernel, unless a tile width was asked for explicitly
-  // (block_n != 0 selects the tcgen05 kernel; SDUMC_SMALL_GEMM=0 disables the small kernel for A/B timing)
-  static const bool small_on = [] { const char* e = getenv("SDUMC_SMALL_GEMM"); return !(e && e[0] == '0'); }();
-  if (small_on && block_n == 0 && max_ctas == 0 && small_gemm_eligible(sh, epi, tf32, A.ld, B.ld)) {
-    if (epi.bias) SDUMC_CHECK_ARG((reinterpret_cast<uintptr_t>(epi.bias) & 3u) == 0, "gemm: bias misaligned");
-    return launch_small_gemm(A, B, sh, epi, tf32, stream);
-  }
   const int elem = tf32 ? 4 : 2;
   const int block_k = 128 / elem;
   const int panel = 128 / elem;

@@ -634,9 +634,4 @@ struct GemmOperand {
 // Launch C = op(A) op(B). `tf32` selects fp32 operands (else bf16). Returns 0 or an error code.
 int launch_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& shape, const GemmEpi& epi, bool tf32,
                 int block_n /*0 = auto*/, int max_ctas /*0 = all SMs*/, cudaStream_t stream);
-// small_gemm.cu: the low-latency warp-MMA kernel for the utterance-level chain (same operator, same epilogue)
-bool small_gemm_eligible(const GemmShape& sh, const GemmEpi& ep, bool tf32, long lda, long ldb);
-int launch_small_gemm(const GemmOperand& A, const GemmOperand& B, const GemmShape& sh, const GemmEpi& ep, bool tf32,
-                      cudaStream_t stream);
-
 }  // namespace sdumc

@@ -179,53 +179,3 @@ def test_encoder_projector_concat_matches_oracle():
     assert err <= 1e-2, err
     with pytest.raises(Exception):
         net.cpu()(x.cpu())
-
-
-def test_small_gemm_kernel_equals_the_tcgen05_kernel():
-    """The low-latency warp-MMA kernel of the utterance chain (csrc/small_gemm.cu; chosen for M <= 16384 when no tile
-    width is requested) serves the same operator as the tcgen05 kernel (block_n=64 forces it): identical dropout masks
-    and gates, values equal to accumulation-order noise, for the three operand layouts the chain uses and every
-    output mode; and both match a float64 matmul of the tf32- / bf16-rounded operands."""
-    from sdumc_b200 import ops
-    dev = torch.device("cuda", 0)
-    g = torch.Generator(device=dev).manual_seed(11)
-    rnd = lambda *s: torch.randn(*s, generator=g, device=dev)  # noqa: E731
-    tf32 = lambda x: (x.contiguous().view(torch.int32) & -8192).view(torch.float32)  # noqa: E731
-    for (M, N, K) in ((1000, 256, 256), (70, 64, 128), (7168, 128, 256), (1024, 256, 768)):
-        # (1) forward layer: fp32 operands as tf32, bias + ReLU + dropout, fp32 and bf16 outputs
-        A, W, b = rnd(M, K), rnd(N, K) * 0.1, rnd(N)
-        outs = []
-        for bn in (0, 64):
-            y, yb = torch.zeros(M, N, device=dev), torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-            ops.gemm(A, W, M=M, N=N, K=K, bias=b, act=ops.ACT_RELU, drop_p=0.3, drop_site=9, out_f32=y, out_bf16=yb,
-                     seed=77, step=5, block_n=bn)
-            outs.append((y, yb))
-        mask = ops.elem_mask(77, 5, 9, M * N, 0.3).view(M, N)
-        ref = torch.relu(tf32(A).double() @ tf32(W).double().t() + b.double()) * mask.double()
-        for y, yb in outs:
-            assert float((y.double() - ref).abs().max()) <= 2e-4 * float(ref.abs().max())
-            assert torch.equal(yb, y.bfloat16())
-        assert torch.equal(outs[0][0] == 0, outs[1][0] == 0)
-        # (2) dX = dZ W with the ReLU/dropout gate of the layer below, bf16 operands, W stored [K,N]; += and atomic modes
-        dZ, Wt = rnd(M, K).bfloat16(), (rnd(K, N) * 0.1).bfloat16()
-        gate, prev = rnd(M, N), rnd(M, N)
-        refx = (dZ.double() @ Wt.double()) * (gate > 0).double() / 0.7
-        for mode, base in ((ops.OUT_STORE, 0.0), (ops.OUT_ADD, 1.0), (ops.OUT_ATOMIC, 1.0)):
-            for bn in (0, 64):
-                o = prev.clone()
-                ob = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
-                ops.gemm(dZ, Wt, M=M, N=N, K=K, b_mn=True, gate=gate, gate_scale=1.0 / 0.7, out_f32=o, f32_mode=mode,
-                         out_bf16=ob if mode == ops.OUT_STORE else None, block_n=bn)
-                want = refx + base * prev.double()
-                assert float((o.double() - want).abs().max()) <= 1e-4 * float(want.abs().max()) + 1e-5, (M, N, K, mode, bn)
-                if mode == ops.OUT_STORE:
-                    assert torch.equal(ob, o.bfloat16())
-        # (3) bf16 operands, weight stored [N,K], bf16 += output
-        Ab, Wb = rnd(M, K).bfloat16(), (rnd(N, K) * 0.1).bfloat16()
-        prevb = rnd(M, N).bfloat16()
-        o0, o1 = prevb.clone(), prevb.clone()
-        ops.gemm(Ab, Wb, M=M, N=N, K=K, out_bf16=o0, bf16_mode=ops.OUT_ADD)
-        ops.gemm(Ab, Wb, M=M, N=N, K=K, out_bf16=o1, bf16_mode=ops.OUT_ADD, block_n=64)
-        refb = prevb.double() + Ab.double() @ Wb.double().t()
-        assert float((o0.double() - refb).abs().max()) <= 1e-2 * float(refb.abs().max())
-        assert float((o0.double() - o1.double()).abs().max()) <= 1e-2 * float(refb.abs().max())

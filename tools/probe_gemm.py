@@ -164,6 +164,63 @@ def run_case(name: str) -> dict:
         res["tflops"] = 2.0 * M * N * K / ms / 1e9
         res["gbs"] = (A.numel() * 2 + B.numel() * 2 + M * N * (2 if ks == 1 else 4)) / ms / 1e6
         res["ok"] = True
+    elif kind == "nullchain":
+        # 20 dependent trivial kernels (cast of 1 KB) replayed as a CUDA graph: the floor of a dependent launch
+        a = torch.zeros(256, device=dev)
+        b = torch.zeros(256, device=dev, dtype=torch.bfloat16)
+
+        def body():
+            for _ in range(20):
+                ops.cast_bf16(a, b)
+        body()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        ts = []
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        res["us_per_kernel"] = sorted(ts)[len(ts) // 2] * 1e3 / 20
+        res["ok"] = True
+    elif kind == "chain":
+        # chain:<M>:<N>:<K>:<bn>:<cold>  20 dependent tf32 linears (bias + ReLU + dropout) replayed as a CUDA graph
+        M, N, K, bn, cold = map(int, rest[0:5])
+        lvl = int(rest[5]) if len(rest) > 5 else 3     # epilogue level: 0 plain store, 1 +bias/ReLU, 2 +dropout, 3 +bf16 copy
+        Ws = [mk((N, K), torch.float32) * 0.1 for _ in range(20)]
+        bs_ = [torch.randn(N, device=dev) for _ in range(20)]
+        xs = [mk((M, K), torch.float32), mk((M, K), torch.float32)]
+        xb = torch.zeros(M, N, device=dev, dtype=torch.bfloat16)
+        flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+        def body():
+            for i in range(20):
+                ops.gemm(xs[i & 1], Ws[i], M=M, N=N, K=K, bias=bs_[i] if lvl >= 1 else None,
+                         act=ops.ACT_RELU if lvl >= 1 else ops.ACT_NONE, drop_p=0.3 if lvl >= 2 else 0.0, drop_site=3 + i,
+                         out_f32=xs[(i + 1) & 1], out_bf16=xb if lvl >= 3 else None, seed=5, step=1, block_n=bn)
+        body()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            body()
+        ts = []
+        for _ in range(10):
+            if cold:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        res["us_per_layer"] = sorted(ts)[len(ts) // 2] * 1e3 / 20
+        res["ok"] = True
     elif kind == "timeepi":
         # timeepi:inproj:<ntgt>:<K>  |  timeepi:keyproj:<nq>:<store_k>
         sub = rest[0]

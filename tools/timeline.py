@@ -20,7 +20,7 @@ from sdumc_b200.trainer import Trainer  # noqa: E402
 
 
 def short(name):
-    name = name.replace("void ", "").replace("sdumc::", "")
+    name = name.replace("void ", "").replace("sdumc::", "").replace("(anonymous namespace)::", "")
     return name.split("(")[0][:70]
 
 
