@@ -121,8 +121,10 @@ typedef struct sdumc_pool_fwd_args {
   sdumc_dropkey key;
   const SDUMC_BF16* Kt; /* optional tanh keys [B*L,256]: when set, the scores S = Kt Qp^T are computed here */
   int64_t ldk;
-  const float* Qp;      /* with Kt: projected queries [B,nq,256] (qp_stride_b = nq*256) or shared context (0) */
+  const float* Qp;      /* with Kt: projected queries [B,nq,G] (qp_stride_b = nq*G) or shared context (0) */
   int64_t qp_stride_b;
+  int32_t G;            /* general_dim: 0 or 256 (reference), or 1024 (BASELINE config 4); 256 in the comments above */
+  int32_t reserved;
 } sdumc_pool_fwd_args;
 int sdumc_pool_fwd(const sdumc_pool_fwd_args* a, void* stream);
 
@@ -149,8 +151,10 @@ typedef struct sdumc_attn_bwd_args {
   uint32_t fmask_site;  /* 0: no input dropout */
   float* dQp;           /* accumulated with atomicAdd (zero-fill first): [B,nq,256], or [nq,256] when qp_stride_b == 0 */
   int64_t dqp_stride_b;
-  float* db;            /* [256] atomicAdd */
+  float* db;            /* [G] atomicAdd */
   sdumc_dropkey key;
+  int32_t G;            /* general_dim: 0 or 256 (reference), or 1024 */
+  int32_t reserved;
 } sdumc_attn_bwd_args;
 int sdumc_attn_bwd(const sdumc_attn_bwd_args* a, void* stream);
 
@@ -187,6 +191,7 @@ typedef struct sdumc_gate_fwd_args {
   const float* Wg; const float* bg;/* fc_att [3,256], [3] */
   const float* h; int64_t ld_h;    /* [R,768] = (h_a|h_t|h_v) */
   int32_t R;
+  int32_t G;                       /* general_dim (256 in the shapes quoted here; a multiple of 256 up to 1024) */
   float* g;                        /* [R,4] (3 used): raw gate, not softmaxed (:303-304) */
   float* qin; int64_t qin_stride;  /* 4 x [R,256]: fused, audio+text, text+video, audio+video */
 } sdumc_gate_fwd_args;
@@ -200,6 +205,7 @@ typedef struct sdumc_gate_bwd_args {
   const float* a2; int64_t ld_a2;
   const float* Wg;
   int32_t R;
+  int32_t G;                       /* general_dim */
   float* dh; int64_t ld_dh;        /* [R,768] += */
   float* da2; int64_t ld_da2;      /* [R,256] store */
   float* dWg; float* dbg;          /* atomicAdd */
@@ -258,10 +264,11 @@ int sdumc_final_bwd(const sdumc_final_bwd_args* a, void* stream);
  * ------------------------------------------------------------------------------------------ */
 typedef struct sdumc_loss_sums_args {
   const float* v0; const float* v1; const float* y;  /* [B] */
-  const float* th0; const float* th1;                /* [B,256] */
+  const float* th0; const float* th1;                /* [B,G] (G = 256 in the reference) */
   const float* ct0; const float* ct1;                /* [B,896] */
   const float* f0; const float* f1;                  /* [B,128] */
   int32_t B;
+  int32_t G;                                         /* general_dim: width of th0 / th1; 0 = 256 */
   float* sums;                                       /* [8], atomicAdd of 5 sums of squares */
 } sdumc_loss_sums_args;
 int sdumc_loss_sums(const sdumc_loss_sums_args* a, void* stream);

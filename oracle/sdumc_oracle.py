@@ -92,7 +92,7 @@ def param_spec(input_dims: Sequence[int], general_dim: int = GENERAL_DIM) -> Lis
 
 
 def init_params(input_dims: Sequence[int], seed: int = 100, gain: float = 1.0,
-                dtype=torch.float32) -> Params:
+                dtype=torch.float32, general_dim: int = GENERAL_DIM) -> Params:
     """Deterministic, torch-RNG-independent parameters (numpy PCG64 keyed by the parameter name).
 
     Same distribution family as torch defaults (U(+-1/sqrt(fan_in)) for Linear, xavier-normal for
@@ -100,7 +100,7 @@ def init_params(input_dims: Sequence[int], seed: int = 100, gain: float = 1.0,
     makes the prediction input-dependent at init — SURVEY.md §7 'parity traps').
     """
     P: Params = {}
-    for name, shape, _live in param_spec(input_dims):
+    for name, shape, _live in param_spec(input_dims, general_dim):
         rng = np.random.default_rng([seed, zlib.crc32(name.encode())])
         if name == "prelu.weight":
             a = np.full(shape, 0.25)

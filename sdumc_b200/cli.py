@@ -69,6 +69,8 @@ def build_parser(inference: bool) -> argparse.ArgumentParser:
     p.add_argument('--synthetic_dims', type=str, default=None, help='Da,Dt,Dv,D4 of --synthetic (default S0: 1024,4096,1024,4096)')
     p.add_argument('--synthetic_label_scale', type=float, default=1.0,
                    help='multiplies the labels of --synthetic (the reference keeps a checkpoint only below a test MAE of 1.0, :299)')
+    p.add_argument('--general_dim', type=int, default=256,
+                   help='model width (the reference hard-codes general_dim = 256, :191); 1024 = the "hidden 1024" stress config')
     p.add_argument('--no_dropout', action='store_true', help='train without dropout (deterministic parity runs)')
     p.add_argument('--checkpoint', type=str, default=None,
                    help='checkpoint with ["state_dict"] (inference; the reference hard-codes its path, ..._inference.py:341)')
@@ -165,7 +167,8 @@ def make_trainer(args, stores, device, pg, state_dict=None):
     merge = any(len(s) > args.batch_size and len(s) % args.batch_size == 1 for s in stores)
     cap = max(args.batch_size + (1 if merge else 0), 2)
     tr = Trainer(store.dims, cap, max_frames, device, lr=args.lr, weight_decay=args.l2, loss_w=w,
-                 seed=args.seed, process_group=pg, state_dict=state_dict, use_graph=True)
+                 seed=args.seed, process_group=pg, state_dict=state_dict, use_graph=True,
+                 general_dim=getattr(args, "general_dim", 256))
     tr.train_dropout = not getattr(args, "no_dropout", False)
     return tr
 

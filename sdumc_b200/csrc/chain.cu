@@ -9,7 +9,6 @@
 
 namespace sdumc {
 
-static constexpr int G = 256;
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) act_bwd_kernel(ActBwdArgs a) {
@@ -66,134 +65,128 @@ int launch_act_bwd(const ActBwdArgs& a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------
-// gate forward: warp per utterance row, lane owns 8 of the 256 columns
+// gate forward: warp per utterance row; a lane owns 8 columns of every 256-column block (G = 256: one block)
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ld8(const float* p, float (&x)[8]) {
+  const float4 u = *reinterpret_cast<const float4*>(p), v = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+}
+__device__ __forceinline__ void st8(float* p, const float (&x)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+}
+
 __global__ void __launch_bounds__(256) gate_fwd_kernel(GateFwdArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= a.R) return;
-  const int c0 = lane * 8;
-  float x[8];
-  {
-    const float4 u = *reinterpret_cast<const float4*>(a.a2 + (long)r * a.ld_a2 + c0);
-    const float4 v = *reinterpret_cast<const float4*>(a.a2 + (long)r * a.ld_a2 + c0 + 4);
-    x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
+  const int G = a.G;
+  float s[3] = {0.f, 0.f, 0.f};
+  for (int c0 = lane * 8; c0 < G; c0 += 256) {
+    float x[8];
+    ld8(a.a2 + (long)r * a.ld_a2 + c0, x);
+#pragma unroll
+    for (int m = 0; m < 3; ++m)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[m] = fmaf(x[j], __ldg(a.Wg + m * G + c0 + j), s[m]);
   }
   float g[3];
 #pragma unroll
-  for (int m = 0; m < 3; ++m) {
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s = fmaf(x[j], __ldg(a.Wg + m * G + c0 + j), s);
-    g[m] = warp_sum(s) + __ldg(a.bg + m);
-  }
+  for (int m = 0; m < 3; ++m) g[m] = warp_sum(s[m]) + __ldg(a.bg + m);
   if (lane < 4) a.g[(long)r * 4 + lane] = lane == 0 ? g[0] : (lane == 1 ? g[1] : (lane == 2 ? g[2] : 0.f));
-  float h[3][8];
+  for (int c0 = lane * 8; c0 < G; c0 += 256) {
+    float h[3][8];
 #pragma unroll
-  for (int m = 0; m < 3; ++m) {
-    const float4 u = *reinterpret_cast<const float4*>(a.h + (long)r * a.ld_h + m * G + c0);
-    const float4 v = *reinterpret_cast<const float4*>(a.h + (long)r * a.ld_h + m * G + c0 + 4);
-    h[m][0] = u.x; h[m][1] = u.y; h[m][2] = u.z; h[m][3] = u.w;
-    h[m][4] = v.x; h[m][5] = v.y; h[m][6] = v.z; h[m][7] = v.w;
-  }
-  float o[4][8];
+    for (int m = 0; m < 3; ++m) ld8(a.h + (long)r * a.ld_h + m * G + c0, h[m]);
+    float o[4][8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const float pa = g[0] * h[0][j], pt = g[1] * h[1][j], pv = g[2] * h[2][j];
-    // same association order as torch.matmul over the stacked modalities: (a + t) + v
-    o[0][j] = (pa + pt) + pv;  // fused
-    o[1][j] = pa + pt;         // audio+text
-    o[2][j] = pt + pv;         // text+video
-    o[3][j] = pa + pv;         // audio+video
-  }
+    for (int j = 0; j < 8; ++j) {
+      const float pa = g[0] * h[0][j], pt = g[1] * h[1][j], pv = g[2] * h[2][j];
+      // same association order as torch.matmul over the stacked modalities: (a + t) + v
+      o[0][j] = (pa + pt) + pv;  // fused
+      o[1][j] = pa + pt;         // audio+text
+      o[2][j] = pt + pv;         // text+video
+      o[3][j] = pa + pv;         // audio+video
+    }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float* dst = a.qin + (long)i * a.qin_stride + (long)r * G + c0;
-    *reinterpret_cast<float4*>(dst) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(o[i][4], o[i][5], o[i][6], o[i][7]);
+    for (int i = 0; i < 4; ++i) st8(a.qin + (long)i * a.qin_stride + (long)r * G + c0, o[i]);
   }
 }
 int launch_gate_fwd(const GateFwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.a2 && a.Wg && a.bg && a.h && a.g && a.qin && a.R > 0, "gate_fwd: bad arguments");
+  SDUMC_CHECK_ARG(a.G > 0 && a.G % 256 == 0 && a.G <= 1024, "gate: general_dim %d unsupported", a.G);
   gate_fwd_kernel<<<(a.R + 7) / 8, 256, 0, stream>>>(a);
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void __launch_bounds__(256) gate_bwd_kernel(GateBwdArgs a) {
-  __shared__ float sW[3][G];
+  __shared__ float sW[3 * 1024];
   __shared__ float sb[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < 3 * G; i += 256) (&sW[0][0])[i] = 0.f;
+  const int G = a.G;
+  for (int i = threadIdx.x; i < 3 * G; i += 256) sW[i] = 0.f;
   if (threadIdx.x < 4) sb[threadIdx.x] = 0.f;
   __syncthreads();
   const int r = blockIdx.x * 8 + warp;
   if (r < a.R) {
-    const int c0 = lane * 8;
-    float d[4][8], h[3][8];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float* src = a.dqin + (long)i * a.dqin_stride + (long)r * G + c0;
-      const float4 u = *reinterpret_cast<const float4*>(src);
-      const float4 v = *reinterpret_cast<const float4*>(src + 4);
-      d[i][0] = u.x; d[i][1] = u.y; d[i][2] = u.z; d[i][3] = u.w;
-      d[i][4] = v.x; d[i][5] = v.y; d[i][6] = v.z; d[i][7] = v.w;
-    }
-#pragma unroll
-    for (int m = 0; m < 3; ++m) {
-      const float4 u = *reinterpret_cast<const float4*>(a.h + (long)r * a.ld_h + m * G + c0);
-      const float4 v = *reinterpret_cast<const float4*>(a.h + (long)r * a.ld_h + m * G + c0 + 4);
-      h[m][0] = u.x; h[m][1] = u.y; h[m][2] = u.z; h[m][3] = u.w;
-      h[m][4] = v.x; h[m][5] = v.y; h[m][6] = v.z; h[m][7] = v.w;
-    }
     const float g0 = a.g[(long)r * 4 + 0], g1 = a.g[(long)r * 4 + 1], g2 = a.g[(long)r * 4 + 2];
     float dg[3] = {0.f, 0.f, 0.f};
-    float dh[3][8];
+    // pass 1: dh += g * (sum of the consumers' gradients), dg = <h, ...> over all G columns
+    for (int c0 = lane * 8; c0 < G; c0 += 256) {
+      float d[4][8], h[3][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float ua = d[0][j] + d[1][j] + d[3][j];  // consumers of g_a h_a: fused, at, av
-      const float ut = d[0][j] + d[1][j] + d[2][j];  // fused, at, tv
-      const float uv = d[0][j] + d[2][j] + d[3][j];  // fused, tv, av
-      dh[0][j] = g0 * ua; dh[1][j] = g1 * ut; dh[2][j] = g2 * uv;
-      dg[0] = fmaf(h[0][j], ua, dg[0]);
-      dg[1] = fmaf(h[1][j], ut, dg[1]);
-      dg[2] = fmaf(h[2][j], uv, dg[2]);
+      for (int i = 0; i < 4; ++i) ld8(a.dqin + (long)i * a.dqin_stride + (long)r * G + c0, d[i]);
+#pragma unroll
+      for (int m = 0; m < 3; ++m) ld8(a.h + (long)r * a.ld_h + m * G + c0, h[m]);
+      float dh[3][8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float ua = d[0][j] + d[1][j] + d[3][j];  // consumers of g_a h_a: fused, at, av
+        const float ut = d[0][j] + d[1][j] + d[2][j];  // fused, at, tv
+        const float uv = d[0][j] + d[2][j] + d[3][j];  // fused, tv, av
+        dh[0][j] = g0 * ua; dh[1][j] = g1 * ut; dh[2][j] = g2 * uv;
+        dg[0] = fmaf(h[0][j], ua, dg[0]);
+        dg[1] = fmaf(h[1][j], ut, dg[1]);
+        dg[2] = fmaf(h[2][j], uv, dg[2]);
+      }
+#pragma unroll
+      for (int m = 0; m < 3; ++m) {
+        float* dst = a.dh + (long)r * a.ld_dh + m * G + c0;
+        float old[8];
+        ld8(dst, old);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) old[j] += dh[m][j];
+        st8(dst, old);
+      }
     }
 #pragma unroll
     for (int m = 0; m < 3; ++m) {
       dg[m] = warp_sum(dg[m]);
       if (a.dg_extra) dg[m] += a.dg_extra[(long)r * 4 + m];
-      float* dst = a.dh + (long)r * a.ld_dh + m * G + c0;
-      float4 u = *reinterpret_cast<float4*>(dst), v = *reinterpret_cast<float4*>(dst + 4);
-      u.x += dh[m][0]; u.y += dh[m][1]; u.z += dh[m][2]; u.w += dh[m][3];
-      v.x += dh[m][4]; v.y += dh[m][5]; v.z += dh[m][6]; v.w += dh[m][7];
-      *reinterpret_cast<float4*>(dst) = u;
-      *reinterpret_cast<float4*>(dst + 4) = v;
     }
-    float x[8], da[8];
-    {
-      const float4 u = *reinterpret_cast<const float4*>(a.a2 + (long)r * a.ld_a2 + c0);
-      const float4 v = *reinterpret_cast<const float4*>(a.a2 + (long)r * a.ld_a2 + c0 + 4);
-      x[0] = u.x; x[1] = u.y; x[2] = u.z; x[3] = u.w; x[4] = v.x; x[5] = v.y; x[6] = v.z; x[7] = v.w;
-    }
+    // pass 2: through fc_att
+    for (int c0 = lane * 8; c0 < G; c0 += 256) {
+      float x[8], da[8];
+      ld8(a.a2 + (long)r * a.ld_a2 + c0, x);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      da[j] = dg[0] * __ldg(a.Wg + c0 + j) + dg[1] * __ldg(a.Wg + G + c0 + j) + dg[2] * __ldg(a.Wg + 2 * G + c0 + j);
+      for (int j = 0; j < 8; ++j) {
+        da[j] = dg[0] * __ldg(a.Wg + c0 + j) + dg[1] * __ldg(a.Wg + G + c0 + j) + dg[2] * __ldg(a.Wg + 2 * G + c0 + j);
 #pragma unroll
-      for (int m = 0; m < 3; ++m) atomicAdd(&sW[m][c0 + j], dg[m] * x[j]);
+        for (int m = 0; m < 3; ++m) atomicAdd(&sW[m * G + c0 + j], dg[m] * x[j]);
+      }
+      st8(a.da2 + (long)r * a.ld_da2 + c0, da);
     }
-    float* dst = a.da2 + (long)r * a.ld_da2 + c0;
-    *reinterpret_cast<float4*>(dst) = make_float4(da[0], da[1], da[2], da[3]);
-    *reinterpret_cast<float4*>(dst + 4) = make_float4(da[4], da[5], da[6], da[7]);
     if (lane < 3) atomicAdd(&sb[lane], lane == 0 ? dg[0] : (lane == 1 ? dg[1] : dg[2]));
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * G; i += 256) atomicAdd(a.dWg + i, (&sW[0][0])[i]);
+  for (int i = threadIdx.x; i < 3 * G; i += 256) atomicAdd(a.dWg + i, sW[i]);
   if (threadIdx.x < 3) atomicAdd(a.dbg + threadIdx.x, sb[threadIdx.x]);
 }
 int launch_gate_bwd(const GateBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.dqin && a.g && a.h && a.a2 && a.Wg && a.dh && a.da2 && a.dWg && a.dbg && a.R > 0,
                   "gate_bwd: bad arguments");
+  SDUMC_CHECK_ARG(a.G > 0 && a.G % 256 == 0 && a.G <= 1024, "gate: general_dim %d unsupported", a.G);
   gate_bwd_kernel<<<(a.R + 7) / 8, 256, 0, stream>>>(a);
   SDUMC_CUDA(cudaGetLastError());
   return 0;

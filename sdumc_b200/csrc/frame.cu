@@ -13,7 +13,21 @@
 
 namespace sdumc {
 
-static constexpr int G = 256;  // general_dim of the model (reference :191)
+// general_dim of the model: 256 in the reference (:191); 1024 is BASELINE config 4 ("hidden 1024" stress).  A stage of
+// the frame rings always holds 16 K-rows' worth of bytes per warp-row-slab, so the tile shapes scale with G:
+//   G = 256 : 64 frame rows per stage = 4 slabs of 16 rows x (2 | 4) column groups of warps
+//   G = 1024: 16 frame rows per stage = 1 slab            x (8 | 16) column groups
+// and every warp keeps the same fragment loops: 128 columns (forward) / 64 columns (backward) of its slab.
+template <int G>
+struct FrameCfg {
+  static_assert(G == 256 || G == 1024, "general_dim 256 (reference) or 1024 (stress configuration)");
+  static constexpr int kRows = 64 * 256 / G;           // frame rows per stage
+  static constexpr int kSlabs = kRows / 16;            // 16-row slabs per stage
+  static constexpr int kPitch = G + 8;                 // bf16 elements per padded shared-memory row
+  static constexpr int kTile = kRows * kPitch * 2;     // bytes of one padded bf16 [kRows, G] tile
+  static constexpr int kFwdColWarps = 8 / kSlabs;      // pool_fwd: 8 warps, 128 columns each
+  static constexpr int kBwdColWarps = 16 / kSlabs;     // attn_bwd: 16 warps, 64 columns each
+};
 
 __device__ __forceinline__ void unpack8(const uint4& v, float (&x)[8]) {
   x[0] = __uint_as_float(v.x << 16); x[1] = __uint_as_float(v.x & 0xffff0000u);
@@ -42,13 +56,13 @@ __device__ __forceinline__ uint4 pack8(const float (&x)[8]) {
 // inference path that never materialises K).  P is written back to S for the backward pass.
 // ------------------------------------------------------------------------------------------
 constexpr int kFwdStages = 2;
-constexpr int kFwdRows = 64;
-constexpr int kFwdPitch = G + 8;
-constexpr int kFwdTile = kFwdRows * kFwdPitch * 2;
 constexpr int kFwdThreads = 256;
 
-template <int NQ>
+template <int NQ, int G>
 __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a) {
+  using FC = FrameCfg<G>;
+  constexpr int kFwdRows = FC::kRows, kFwdPitch = FC::kPitch, kFwdTile = FC::kTile, kSlabs = FC::kSlabs;
+  constexpr int kCW = FC::kFwdColWarps, kWCols = G / kCW;   // 128 columns per warp
   extern __shared__ __align__(128) unsigned char dyn[];
   // layout: ring [2][tile] | QpB hi, lo [2][8][264] bf16 | S_s [L][8] f32
   // (queries and probabilities enter the tensor-core products as bf16 hi + lo pairs: ~16 mantissa bits for
@@ -63,7 +77,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (uniform-register bulk copies)
   const int gid = lane >> 2, tq = lane & 3;
-  const int rw = warp & 3, hc = (warp >> 2) * (G / 2);
+  const int rw = warp % kSlabs, cw = warp / kSlabs, hc = cw * kWCols;   // row slab / column group of this warp
   const int L = a.L;
   const int n_iter = (L + kFwdRows - 1) / kFwdRows;
   const bool has_k = a.Kt != nullptr;
@@ -73,7 +87,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
   const __nv_bfloat16* Kb = has_k ? a.Kt + (long)b * L * G : nullptr;
   float* Sg = a.S + (long)b * L * NQ;
 
-  auto issue_stage = [&](int j) {                           // lane 0 of warp w: rows 8w..8w+7
+  auto issue_stage = [&](int j) {                           // lane 0 of warp w: rows w*rpw .. w*rpw + rpw - 1
+    constexpr int rpw = kFwdRows / 8;
     const int slot = j % kFwdStages;
     const bool kphase = has_k && j < n_iter;
     const int it = kphase ? j : j - (has_k ? n_iter : 0);
@@ -82,8 +97,8 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
     unsigned char* dst = ring + slot * kFwdTile;
     if (lane == 0) {
       if (warp == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2);
-      const int r1 = min(rows, warp * 8 + 8);
-      for (int r = warp * 8; r < r1; ++r) bulk_load(dst + r * kFwdPitch * 2, src + (long)r * G, G * 2, &full_bar[slot]);
+      const int r1 = min(rows, warp * rpw + rpw);
+      for (int r = warp * rpw; r < r1; ++r) bulk_load(dst + r * kFwdPitch * 2, src + (long)r * G, G * 2, &full_bar[slot]);
     }
   };
   if (tid == 0) {
@@ -100,7 +115,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
     const float4* Qg = reinterpret_cast<const float4*>(a.Qp + (long)b * a.qp_stride_b);
     for (int i = tid; i < 8 * G / 4; i += kFwdThreads) {
       const float4 v = i < kV4 ? __ldg(Qg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      const int q = (i * 4) >> 8, g = (i * 4) & (G - 1);
+      const int q = (i * 4) / G, g = (i * 4) & (G - 1);
       const uint32_t h0 = pack2(v.x, v.y), h1 = pack2(v.z, v.w);
       *reinterpret_cast<uint2*>(QpB + q * kFwdPitch + g) = make_uint2(h0, h1);
       *reinterpret_cast<uint2*>(QpL + q * kFwdPitch + g) =
@@ -159,12 +174,12 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
     const int valid = min(16, L - l0);
     if (valid > 0) {
       if (kphase) {
-        // scores of this warp's 16 rows: partial over its 128 columns, then add the partner warp's half
+        // scores of this warp's 16 rows: partial over its 128 columns, then add the other column groups' partials
         float sc[4] = {0.f, 0.f, 0.f, 0.f};
         const __nv_bfloat16* arow = Ts + ((lane & 7) + ((lane >> 3) & 1) * 8) * kFwdPitch + (lane >> 4) * 8;
         const __nv_bfloat16* brow = QpB + gid * kFwdPitch + hc + 2 * tq;
 #pragma unroll
-        for (int kk = 0; kk < G / 32; ++kk) {
+        for (int kk = 0; kk < kWCols / 16; ++kk) {
           uint32_t af[4];
           ldsm_x4(af, arow + kk * 16);
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + kk * 16);
@@ -175,15 +190,20 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
           mma_16816(sc, af, c0, c1);
         }
         sp_x[tid] = make_float4(sc[0], sc[1], sc[2], sc[3]);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + rw) : "memory");
-        const float4 o = sp_x[tid ^ 128];
-        // the lower-half warp writes rows gid, its partner rows gid+8 (rows past L hold garbage: skipped)
-        if (hc == 0) { if (gid < valid) *reinterpret_cast<float2*>(&S_s[(l0 + gid) * 8 + 2 * tq]) = make_float2(sc[0] + o.x, sc[1] + o.y); }
-        else if (gid + 8 < valid) *reinterpret_cast<float2*>(&S_s[(l0 + gid + 8) * 8 + 2 * tq]) = make_float2(sc[2] + o.z, sc[3] + o.w);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + rw), "n"(kCW * 32) : "memory");
+        float4 o = sp_x[rw * 32 + lane];                           // column groups summed in a fixed order
+#pragma unroll
+        for (int c = 1; c < kCW; ++c) {
+          const float4 x = sp_x[(c * kSlabs + rw) * 32 + lane];
+          o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+        }
+        // column group 0 writes rows gid, group 1 rows gid+8 (rows past L hold garbage: skipped)
+        if (cw == 0) { if (gid < valid) *reinterpret_cast<float2*>(&S_s[(l0 + gid) * 8 + 2 * tq]) = make_float2(o.x, o.y); }
+        else if (cw == 1 && gid + 8 < valid) *reinterpret_cast<float2*>(&S_s[(l0 + gid + 8) * 8 + 2 * tq]) = make_float2(o.z, o.w);
       } else {
         if (valid < 16) {                             // rows past L: zero so 0 * garbage cannot produce NaN
-          for (int i = lane; i < 16 * (G / 16); i += 32) {
-            const int r = i / (G / 16), c = (i % (G / 16)) * 8;
+          for (int i = lane; i < 16 * (kWCols / 8); i += 32) {
+            const int r = i / (kWCols / 8), c = (i % (kWCols / 8)) * 8;
             if (r >= valid) *reinterpret_cast<uint4*>(Ts + r * kFwdPitch + c) = make_uint4(0, 0, 0, 0);
           }
           __syncwarp();
@@ -212,7 +232,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
 
   // O: fragments of the four row-slab warps -> per-slab partials in the (now idle) ring -> summed in a fixed
   // order (bitwise reproducible, unlike shared-memory atomics) -> global (+ output dropout)
-  float* part = reinterpret_cast<float*>(ring);            // [4 slabs][8 q][256]: 32 KB of the 66 KB ring
+  float* part = reinterpret_cast<float*>(ring);            // [kSlabs][8 q][G]: 32 KB of the 66 KB ring
 #pragma unroll
   for (int mt = 0; mt < 8; ++mt) {
     const int c = hc + mt * 16 + gid, q = 2 * tq;
@@ -224,7 +244,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
   const uint32_t thr = drop_threshold(a.drop_p);
   const float scale = a.drop_p > 0.f ? 1.f / (1.f - a.drop_p) : 1.f;
   for (int i = tid; i < NQ * G; i += kFwdThreads) {
-    const float o = (part[i] + part[8 * G + i]) + (part[2 * 8 * G + i] + part[3 * 8 * G + i]);
+    float o;
+    if constexpr (kSlabs == 4) o = (part[i] + part[8 * G + i]) + (part[2 * 8 * G + i] + part[3 * 8 * G + i]);
+    else o = part[i];
     a.O_pre[(long)b * NQ * G + i] = o;
     float y = o;
     if (a.drop_p > 0.f) {
@@ -239,26 +261,36 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
 int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.X && a.S && a.O_pre && a.out, "pool_fwd: null pointer");
   SDUMC_CHECK_ARG(a.B > 0 && a.L > 0 && (a.nq == 1 || a.nq == 7), "pool_fwd: bad shape B=%d L=%d nq=%d", a.B, a.L, a.nq);
+  const int G = a.G > 0 ? a.G : 256;
+  SDUMC_CHECK_ARG(G == 256 || G == 1024, "pool_fwd: general_dim %d unsupported (256 or 1024)", G);
   SDUMC_CHECK_ARG(a.ldx == G && (reinterpret_cast<uintptr_t>(a.X) & 15u) == 0,
-                  "pool_fwd: X must be dense [B*L,256] and 16-byte aligned (bulk-copy staging)");
+                  "pool_fwd: X must be dense [B*L,G] and 16-byte aligned (bulk-copy staging)");
   if (a.Kt) {
     SDUMC_CHECK_ARG(a.ldk == G && (reinterpret_cast<uintptr_t>(a.Kt) & 15u) == 0,
-                    "pool_fwd: Kt must be dense [B*L,256] and 16-byte aligned");
+                    "pool_fwd: Kt must be dense [B*L,G] and 16-byte aligned");
     SDUMC_CHECK_ARG(a.Qp && (reinterpret_cast<uintptr_t>(a.Qp) & 15u) == 0 && a.qp_stride_b % 4 == 0,
                     "pool_fwd: Qp is required with Kt (16-byte aligned, stride a multiple of 4)");
   }
-  const size_t smem = (size_t)kFwdStages * kFwdTile + (size_t)2 * 8 * kFwdPitch * 2 + (size_t)a.L * 8 * 4;
+  const size_t tile = G == 256 ? FrameCfg<256>::kTile : FrameCfg<1024>::kTile;
+  const size_t smem = (size_t)kFwdStages * tile + (size_t)2 * 8 * (G + 8) * 2 + (size_t)a.L * 8 * 4;
   constexpr size_t kMaxDyn = 216 * 1024;
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "pool_fwd: L=%d too long for the shared-memory softmax", a.L);
   static bool attr_done[kMaxDevices] = {false};
   const int dev = current_device();
   if (!attr_done[dev]) {
-    SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
-    SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(pool_fwd_kernel<7, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
     attr_done[dev] = true;
   }
-  if (a.nq == 1) pool_fwd_kernel<1><<<a.B, kFwdThreads, smem, stream>>>(a);
-  else           pool_fwd_kernel<7><<<a.B, kFwdThreads, smem, stream>>>(a);
+  if (G == 256) {
+    if (a.nq == 1) pool_fwd_kernel<1, 256><<<a.B, kFwdThreads, smem, stream>>>(a);
+    else           pool_fwd_kernel<7, 256><<<a.B, kFwdThreads, smem, stream>>>(a);
+  } else {
+    if (a.nq == 1) pool_fwd_kernel<1, 1024><<<a.B, kFwdThreads, smem, stream>>>(a);
+    else           pool_fwd_kernel<7, 1024><<<a.B, kFwdThreads, smem, stream>>>(a);
+  }
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -287,13 +319,15 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
 // stores; the "+= old dH" of the accumulate mode is a bulk reduce-add performed at L2, so the old
 // gradient is never read by the SM.
 constexpr int kBwdStages = 2;
-constexpr int kBwdRows = 64;                       // rows per stage (16 per warp)
-constexpr int kBwdPitch = G + 8;                   // bf16 elements per padded shared-memory row (528 B)
-constexpr int kBwdTile = kBwdRows * kBwdPitch * 2; // bytes of one padded bf16 [64,256] tile
 constexpr int kBwdThreads = 512;
 
-template <int NQ>
+template <int NQ, int G>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a) {
+  using FC = FrameCfg<G>;
+  constexpr int kBwdRows = FC::kRows;      // rows per stage (16 per slab)
+  constexpr int kBwdPitch = FC::kPitch;    // bf16 elements per padded shared-memory row
+  constexpr int kBwdTile = FC::kTile;      // bytes of one padded bf16 [kBwdRows, G] tile
+  constexpr int kSlabs = FC::kSlabs, kCW = FC::kBwdColWarps;   // row slabs / column groups (64 columns per warp)
   extern __shared__ __align__(128) unsigned char dyn[];
   // layout: ring [2 stages][X' tile, K tile] | dO_b [8][264] | dOT [256][8] | QpT [256][8] | dqp_s [8][256] f32 | P_s [L][8] f32
   unsigned char* ring = dyn;
@@ -309,8 +343,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   // uniform registers (no per-lane serialisation loop around UBLKCP)
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int gid = lane >> 2, tq = lane & 3;           // fragment coordinates: row group / column pair
-  const int rw = warp & 3, qc = warp >> 2;             // row slab of the stage / column quarter
-  const int hc = qc * (G / 4);                        // first column of this warp's quarter
+  const int rw = warp % kSlabs, qc = warp / kSlabs;     // row slab of the stage / column group
+  const int hc = qc * 64;                              // first column of this warp's 64-column group
   __shared__ float4 dp_x[kBwdThreads];                // partial dP exchange inside a warp quartet
   const int L = a.L;
   const int n_iter = (L + kBwdRows - 1) / kBwdRows;
@@ -324,7 +358,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   const int u_begin = (int)(((long)n_units * blockIdx.x) / gridDim.x);
   const int my_units = (int)(((long)n_units * (blockIdx.x + 1)) / gridDim.x) - u_begin;
 
-  auto issue_stage = [&](int k) {                     // lane 0 of warp w: rows 4w..4w+3 of X' and of K of unit k
+  auto issue_stage = [&](int k) {                     // lane 0 of warp w: rows w*rpw.. of X' and of K of unit k
+    constexpr int rpw = kBwdRows / 16;
     const int u = u_begin + k;
     const int ub = u / n_iter, it = u - ub * n_iter;
     const int slot = k % kBwdStages;
@@ -332,8 +367,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
     unsigned char* dst = ring + slot * 2 * kBwdTile;
     if (lane == 0) {
       if (warp == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2 * 2);
-      const int r1 = min(rows, warp * 4 + 4);
-      for (int r = warp * 4; r < r1; ++r) {
+      const int r1 = min(rows, warp * rpw + rpw);
+      for (int r = warp * rpw; r < r1; ++r) {
         const long src = (((long)ub * L + (long)it * kBwdRows) + r) * G;   // host guarantees dense [B*L,256] tensors
         bulk_load(dst + r * kBwdPitch * 2, a.X + src, G * 2, &full_bar[slot]);
         bulk_load(dst + kBwdTile + r * kBwdPitch * 2, a.Kt + src, G * 2, &full_bar[slot]);
@@ -386,7 +421,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       const int i = tid + j * kBwdThreads;
       dpart[j] = 0.f;
       if (i < kV4) {
-        const int q = (i * 4) >> 8, g = (i * 4) & (G - 1);
+        const int q = (i * 4) / G, g = (i * 4) & (G - 1);
         float d[4] = {dv[j].x, dv[j].y, dv[j].z, dv[j].w};
         if (a.out_drop_p > 0.f) {
           // four consecutive elements share one Philox counter (elem_rand: counter e >> 2, word e & 3)
@@ -421,9 +456,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   // a float4 group lies inside one query row (64 groups per query): warp-reduce, then one atomic per warp and query
 #pragma unroll
   for (int j = 0; j < kPer; ++j) {
-    const int i = tid + j * kBwdThreads;           // warp-uniform q: 32 consecutive groups never straddle a row of 64
+    const int i = tid + j * kBwdThreads;           // warp-uniform q: 32 consecutive groups never straddle a row of G/4
     const float s = warp_sum(dpart[j]);
-    if (lane == 0 && i < kV4) atomicAdd(&delta_s[(i * 4) >> 8], s);
+    if (lane == 0 && i < kV4) atomicAdd(&delta_s[(i * 4) / G], s);
   }
   __syncthreads();
   dl0 = delta_s[2 * tq];
@@ -475,8 +510,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
     const int l0 = it * kBwdRows + rw * 16;           // first frame of this warp's slab
     const int valid = min(16, L - l0);                // may be <= 0 for a trailing warp
     if (valid < 16) {                                 // rows past L: zero so they add nothing to dQp / db
-      for (int i = lane; i < 16 * (G / 32); i += 32) {
-        const int r = i / (G / 32), c = (i % (G / 32)) * 8;
+      for (int i = lane; i < 16 * 8; i += 32) {          // this warp's 16 rows x 64 columns, 8 columns at a time
+        const int r = i / 8, c = (i % 8) * 8;
         if (r >= valid) {
           *reinterpret_cast<uint4*>(Xs + r * kBwdPitch + c) = make_uint4(0, 0, 0, 0);
           *reinterpret_cast<uint4*>(Ks + r * kBwdPitch + c) = make_uint4(0, 0, 0, 0);
@@ -485,13 +520,13 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       __syncwarp();
     }
     if (valid > 0) {
-      // (1) dP = X' * dO^T: this warp's 64 columns, then add the partials of the other three quarters
+      // (1) dP = X' * dO^T: this warp's 64 columns, then add the partials of the other column groups
       float dP[4] = {0.f, 0.f, 0.f, 0.f};
       {
         const __nv_bfloat16* arow = Xs + ((lane & 7) + ((lane >> 3) & 1) * 8) * kBwdPitch + (lane >> 4) * 8;
         const __nv_bfloat16* brow = dO_b + gid * kBwdPitch + hc + 2 * tq;
 #pragma unroll
-        for (int kk = 0; kk < G / 64; ++kk) {
+        for (int kk = 0; kk < 4; ++kk) {
           uint32_t af[4];
           ldsm_x4(af, arow + kk * 16);
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + kk * 16);
@@ -499,12 +534,22 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
           mma_16816(dP, af, b0, b1);
         }
         dp_x[tid] = make_float4(dP[0], dP[1], dP[2], dP[3]);
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + rw) : "memory");
-        // all four quarters add the partials in the same order: identical dS in every warp of the quartet
-        const float4 o0 = dp_x[(rw << 5) + lane], o1 = dp_x[128 + (rw << 5) + lane];
-        const float4 o2 = dp_x[256 + (rw << 5) + lane], o3 = dp_x[384 + (rw << 5) + lane];
-        dP[0] = (o0.x + o1.x) + (o2.x + o3.x); dP[1] = (o0.y + o1.y) + (o2.y + o3.y);
-        dP[2] = (o0.z + o1.z) + (o2.z + o3.z); dP[3] = (o0.w + o1.w) + (o2.w + o3.w);
+        asm volatile("bar.sync %0, %1;" ::"r"(1 + rw), "n"(kCW * 32) : "memory");
+        // every column group adds the partials in the same order: identical dS in every warp of the slab
+        if constexpr (kCW == 4) {
+          const float4 o0 = dp_x[(rw << 5) + lane], o1 = dp_x[128 + (rw << 5) + lane];
+          const float4 o2 = dp_x[256 + (rw << 5) + lane], o3 = dp_x[384 + (rw << 5) + lane];
+          dP[0] = (o0.x + o1.x) + (o2.x + o3.x); dP[1] = (o0.y + o1.y) + (o2.y + o3.y);
+          dP[2] = (o0.z + o1.z) + (o2.z + o3.z); dP[3] = (o0.w + o1.w) + (o2.w + o3.w);
+        } else {
+          float4 o = dp_x[rw * 32 + lane];
+#pragma unroll
+          for (int c = 1; c < kCW; ++c) {
+            const float4 x = dp_x[(c * kSlabs + rw) * 32 + lane];
+            o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
+          }
+          dP[0] = o.x; dP[1] = o.y; dP[2] = o.z; dP[3] = o.w;
+        }
       }
       // (2) dS = alpha * P * (dP - delta) on the accumulator layout: rows gid / gid+8, queries 2tq / 2tq+1
       const bool v0 = gid < valid, v1 = gid + 8 < valid;
@@ -528,8 +573,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       U4 ma, mb;
       if (a.fmask_site) {
         const uint32_t r0 = (uint32_t)((long)b * L + l0 + gid);
-        ma = frame_mask_words(key, a.fmask_site, r0, (uint32_t)(qc >> 1));
-        mb = frame_mask_words(key, a.fmask_site, r0 + 8, (uint32_t)(qc >> 1));
+        ma = frame_mask_words(key, a.fmask_site, r0, (uint32_t)(hc >> 7));
+        mb = frame_mask_words(key, a.fmask_site, r0 + 8, (uint32_t)(hc >> 7));
       }
       // (3) dK = dS * Qp, dXv = P * dO, eight columns at a time; dZ and the masked dXv replace K and X' in place
 #pragma unroll
@@ -552,7 +597,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
         *k0p = pack2(z00, z01);
         *k1p = pack2(z10, z11);
         if (a.fmask_site) {
-          const int w = ((qc & 1) * 2 + (nt >> 2)) & 3;   // 32-column word inside the 128-column block
+          const int w = (((hc & 127) >> 5) + (nt >> 2)) & 3;   // 32-column word inside the 128-column block
           const uint32_t wa = (w == 0 ? ma.x : (w == 1 ? ma.y : (w == 2 ? ma.z : ma.w))) >> ((nt & 3) * 8 + 2 * tq);
           const uint32_t wb = (w == 0 ? mb.x : (w == 1 ? mb.y : (w == 2 ? mb.z : mb.w))) >> ((nt & 3) * 8 + 2 * tq);
           dX[0] = (wa & 1u) ? 2.f * dX[0] : 0.f; dX[1] = (wa & 2u) ? 2.f * dX[1] : 0.f;
@@ -561,14 +606,15 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
         *reinterpret_cast<uint32_t*>(Xs + gid * kBwdPitch + col) = pack2(dX[0], dX[1]);
         *reinterpret_cast<uint32_t*>(Xs + (gid + 8) * kBwdPitch + col) = pack2(dX[2], dX[3]);
       }
-      // tiles -> global: the quartet's 16 finished rows leave as full 512-byte rows, four per warp
+      // tiles -> global: the slab's 16 finished rows leave as full rows, 16 / kCW per warp
       fence_proxy_async();
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + rw) : "memory");
+      asm volatile("bar.sync %0, %1;" ::"r"(1 + rw), "n"(kCW * 32) : "memory");
       if (lane == 0) {
+        constexpr int spw = 16 / kCW;                  // rows stored per warp
         const __nv_bfloat16* Kr = Ks - hc;             // row starts of this slab
         const __nv_bfloat16* Xr = Xs - hc;
-        const int r1 = min(valid, qc * 4 + 4);
-        for (int r = qc * 4; r < r1; ++r) {
+        const int r1 = min(valid, qc * spw + spw);
+        for (int r = qc * spw; r < r1; ++r) {
           const long dst = (long)(l0 + r) * G;
           bulk_store(Zb + dst, Kr + r * kBwdPitch, G * 2);
           if (rmw) bulk_reduce_add_bf16(Hb + dst, Xr + r * kBwdPitch, G * 2);
@@ -595,7 +641,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       db_acc[nt][j] = v;
     }
   }
-  __shared__ float db_s[G];
+  float* db_s = dqp_s;                                // the dQp staging buffer is idle now (flushed and re-zeroed)
   for (int i = tid; i < G; i += kBwdThreads) db_s[i] = 0.f;
   __syncthreads();
   if (gid == 0) {
@@ -610,8 +656,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   bulk_wait_all();
 }
 
-static size_t attn_bwd_smem(int L) {
-  return (size_t)kBwdStages * 2 * kBwdTile + (size_t)8 * kBwdPitch * 2 + (size_t)2 * G * 8 * 2 + (size_t)8 * G * 4 +
+static size_t attn_bwd_smem(int L, int G) {
+  const size_t tile = G == 256 ? FrameCfg<256>::kTile : FrameCfg<1024>::kTile;
+  return (size_t)kBwdStages * 2 * tile + (size_t)8 * (G + 8) * 2 + (size_t)2 * G * 8 * 2 + (size_t)8 * G * 4 +
          (size_t)L * 8 * 4;
 }
 
@@ -619,27 +666,37 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.X && a.Kt && a.P && a.dOut && a.O_pre && a.Qp && a.dZ && a.dH && a.dQp && a.db,
                   "attn_bwd: null pointer");
   SDUMC_CHECK_ARG(a.B > 0 && a.L > 0 && (a.nq == 1 || a.nq == 7), "attn_bwd: bad shape");
+  const int G = a.G > 0 ? a.G : 256;
+  SDUMC_CHECK_ARG(G == 256 || G == 1024, "attn_bwd: general_dim %d unsupported (256 or 1024)", G);
   SDUMC_CHECK_ARG(a.ldx == G && a.ldk == G && a.lddz == G && a.lddh == G,
-                  "attn_bwd: frame tensors must be dense [B*L,256] (bulk-copy staging)");
+                  "attn_bwd: frame tensors must be dense [B*L,G] (bulk-copy staging)");
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.X) | reinterpret_cast<uintptr_t>(a.Kt) | reinterpret_cast<uintptr_t>(a.dH) |
                     reinterpret_cast<uintptr_t>(a.dZ)) & 15u) == 0, "attn_bwd: frame tensors must be 16-byte aligned");
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.dOut) | reinterpret_cast<uintptr_t>(a.Qp) | reinterpret_cast<uintptr_t>(a.O_pre)) & 15u) == 0 &&
                   a.dout_stride_b % 4 == 0 && a.qp_stride_b % 4 == 0,
                   "attn_bwd: dOut / Qp / O_pre must be 16-byte aligned with strides that are multiples of 4");
-  const size_t smem = attn_bwd_smem(a.L);
-  constexpr size_t kMaxDyn = 216 * 1024;   // + 9.1 KB static (dP exchange, db) stays under the 227 KB per-CTA limit
+  const size_t smem = attn_bwd_smem(a.L, G);
+  constexpr size_t kMaxDyn = 218 * 1024;   // + 8.3 KB static (dP exchange, barriers) stays under the 227 KB per-CTA limit
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
   static bool attr_done[kMaxDevices] = {false};
   const int dev = current_device();
   if (!attr_done[dev]) {
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
     attr_done[dev] = true;
   }
-  const long n_units = (long)a.B * ((a.L + kBwdRows - 1) / kBwdRows);
+  const int rows_per_stage = G == 256 ? FrameCfg<256>::kRows : FrameCfg<1024>::kRows;
+  const long n_units = (long)a.B * ((a.L + rows_per_stage - 1) / rows_per_stage);
   const int grid = (int)std::min<long>(n_units, num_sms());   // one resident CTA per SM (shared-memory bound)
-  if (a.nq == 1) attn_bwd_kernel<1><<<grid, kBwdThreads, smem, stream>>>(a);
-  else           attn_bwd_kernel<7><<<grid, kBwdThreads, smem, stream>>>(a);
+  if (G == 256) {
+    if (a.nq == 1) attn_bwd_kernel<1, 256><<<grid, kBwdThreads, smem, stream>>>(a);
+    else           attn_bwd_kernel<7, 256><<<grid, kBwdThreads, smem, stream>>>(a);
+  } else {
+    if (a.nq == 1) attn_bwd_kernel<1, 1024><<<grid, kBwdThreads, smem, stream>>>(a);
+    else           attn_bwd_kernel<7, 1024><<<grid, kBwdThreads, smem, stream>>>(a);
+  }
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

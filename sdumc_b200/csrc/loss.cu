@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) loss_sums_kernel(LossSumsArgs a) {
     s[0] += d0 * d0;
     s[1] += d1 * d1;
   }
-  s[2] = sqdiff_range(a.th1, a.th0, (long)a.B * 256);
+  s[2] = sqdiff_range(a.th1, a.th0, (long)a.B * (a.G > 0 ? a.G : 256));
   s[3] = sqdiff_range(a.ct1, a.ct0, (long)a.B * 896);
   s[4] = sqdiff_range(a.f1, a.f0, (long)a.B * 128);
 #pragma unroll
@@ -77,7 +77,8 @@ int launch_loss_sums(const LossSumsArgs& a, cudaStream_t stream) {
 __global__ void __launch_bounds__(256) loss_finish_kernel(LossFinishArgs a) {
   const float Bg = (float)a.B_global;
   const float mse0 = a.sums[0] / Bg, mse1 = a.sums[1] / Bg;
-  const float n2 = Bg * 256.f, n3 = Bg * 896.f, n4 = Bg * 128.f;
+  const int Gd = a.in.G > 0 ? a.in.G : 256;
+  const float n2 = Bg * (float)Gd, n3 = Bg * 896.f, n4 = Bg * 128.f;
   const float r2 = sqrtf(a.sums[2] / n2), r3 = sqrtf(a.sums[3] / n3), r4 = sqrtf(a.sums[4] / n4);
   const float rnc = a.rnc ? a.rnc[0] : 0.f;
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(256) loss_finish_kernel(LossFinishArgs a) {
     a.d_v0[i] = a.w[0] * 2.f * (in.v0[i] - y) / Bg;
     a.d_v1[i] = a.w[1] * 2.f * (in.v1[i] - y) / Bg;
   }
-  for (long i = t0; i < (long)in.B * 256; i += stride) a.d_th1[i] = c2 * (in.th1[i] - in.th0[i]);
+  for (long i = t0; i < (long)in.B * Gd; i += stride) a.d_th1[i] = c2 * (in.th1[i] - in.th0[i]);
   for (long i = t0; i < (long)in.B * 896; i += stride) a.d_ct1[i] = c3 * (in.ct1[i] - in.ct0[i]);
   for (long i = t0; i < (long)in.B * 128; i += stride) {
     const float g = c4 * (in.f1[i] - in.f0[i]);

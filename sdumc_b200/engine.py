@@ -26,7 +26,6 @@ import torch
 from . import ops
 from .params import CROSS_MLPS, MODALITY_MLPS, QUERY_MLPS, ParamLayout
 
-G = 256
 NQ = 7
 FRAME_P = 0.5   # nn.Dropout(0.5) inside FRA2UTT_new / Cross_Attention (reference :54, :77)
 MLP_P = 0.3     # MLP() dropout (reference :187, :270)
@@ -116,6 +115,7 @@ def _ksplits(rows_k: int, m_gemm: int, n_gemm: int) -> int:
 class Engine:
     def __init__(self, layout: ParamLayout, device, multi_stream: bool = True):
         self.layout = layout
+        self.G = layout.G
         self.device = device
         self.multi_stream = multi_stream
         self._streams: List[torch.cuda.Stream] = []
@@ -247,6 +247,7 @@ class Engine:
     # ------------------------------------------------------------------ forward
     def forward(self, W: Weights, inputs: Dict[str, torch.Tensor], cfg: Cfg) -> State:
         st = State(cfg)
+        G = self.G
         B, NP = cfg.B, cfg.n_pass
         R = NP * B
         dev = self.device
@@ -305,14 +306,24 @@ class Engine:
             S = st.t[f"Sf.{p}.{m}"]
             Kt = st.t[f"Kf.{p}.{m}"] if keep else None
             pre = f"fra2utt_{m}"
-            # one query: the score is a single dot product per row, free in the GEMM epilogue (K is stored only
-            # when the backward pass needs it), and the pooling kernel reads X' alone
-            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                     act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt,
-                     qv=W.f32(pre + ".attention_context_vector"), q_stride=0, nq=1, L=L, scores=S)
+            ctx = W.f32(pre + ".attention_context_vector")
+            if G == 256:
+                # one query: the score is a single dot product per row, free in the GEMM epilogue (K is stored only
+                # when the backward pass needs it), and the pooling kernel reads X' alone
+                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                         act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=ctx, q_stride=0, nq=1, L=L, scores=S)
+                Kp, Qc = None, None
+            else:
+                # wider models: a row spans several N tiles of the key projection, so the scores come from the pooling
+                # kernel's tensor-core product over the stored K (like the 7-query blocks)
+                Kp = Kt if keep else torch.empty(B * L, G, dtype=torch.bfloat16, device=dev)
+                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                         act=ops.ACT_TANH, out_bf16=Kp)
+                Qc = ctx
             ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=st.t[f"Of_pre.{p}.{m}"], out=u_pool[m][p * B:(p + 1) * B],
                          out_stride_b=G, out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
-                         site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev)
+                         site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev, Kt=Kp, Qp=Qc,
+                         qp_stride_b=0)
         self._parallel(len(units), fra2utt_unit)
 
         # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
@@ -426,6 +437,7 @@ class Engine:
         cfg = st.cfg
         NP, B = cfg.n_pass, cfg.B
         t = st.t
+        G = t["Q"].shape[1] // NQ
         return (t["vals"].view(NP, B, 1), t["f"].view(NP, B, 128), t["rnc"].view(NP, B, 64),
                 t["Q"].view(NP, B, NQ, G)[:, :, 5, :], t["c.1"].view(NP, B, NQ, 128))
 
@@ -437,6 +449,7 @@ class Engine:
         every gradient except those of the in-projections and the FRA2UTT_new blocks has been issued - the
         data-parallel trainer starts their all-reduce there, under the rest of the backward pass."""
         cfg = st.cfg
+        G = self.G
         assert cfg.need_grad, "forward was run without need_grad"
         B, NP = cfg.B, cfg.n_pass
         R = NP * B
@@ -551,6 +564,7 @@ class Engine:
     def _attn_block_bwd(self, W: Weights, st: State, p: int, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
                         dH: Dict[str, torch.Tensor], started: Dict[str, bool]):
         cfg = st.cfg
+        G = self.G
         t = st.t
         B = cfg.B
         s = _unit_stream(p, m)

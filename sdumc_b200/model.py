@@ -62,7 +62,8 @@ class WengnetMOSEIMultViewsTextMissing(nn.Module):
             # the reference CLI never reaches these arguments (models/__init__.py:67 passes args only)
             raise NotImplementedError("sdumc_b200 implements the configuration the reference trains: "
                                       "layers='256,128', output dims 1, dropout 0.3")
-        self.layout = ParamLayout(args.input_dims)
+        # `general_dim` is hard-coded to 256 in the reference (:191); args.general_dim is an additive knob
+        self.layout = ParamLayout(args.input_dims, int(getattr(args, "general_dim", 256)))
         self.dropout_seed = int(getattr(args, "seed", 100))
         self._step = 0
         self.keep_last_state = False

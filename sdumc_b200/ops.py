@@ -13,7 +13,6 @@ from . import _lib
 from ._lib import (ACT_NONE, ACT_RELU, ACT_TANH, EPI_GENERIC, EPI_INPROJ, EPI_KEYPROJ, OUT_ADD, OUT_ATOMIC,
                    OUT_STORE, STRUCTS, GemmDesc, call, check, current_stream, dropkey, ptr)
 
-G = 256  # general_dim of the model
 
 
 def _ld(t: torch.Tensor) -> int:
@@ -99,6 +98,7 @@ def pool_fwd(X, S, *, B, L, nq, O_pre, out, out_stride_b, out_bf16=None, drop_p=
     a.B, a.L, a.nq, a.alpha = B, L, nq, alpha
     a.O_pre, a.out, a.out_stride_b, a.out_bf16 = ptr(O_pre), ptr(out), out_stride_b, ptr(out_bf16)
     a.drop_p, a.site, a.key = drop_p, site, dropkey(seed, step, step_dev)
+    a.G = X.shape[1]
     call("sdumc_pool_fwd", a)
 
 
@@ -113,6 +113,7 @@ def attn_bwd(X, Kt, P, dOut, *, dout_stride_b, O_pre, Qp, qp_stride_b, B, L, nq,
     a.dZ, a.lddz, a.dH, a.lddh, a.dh_mode, a.fmask_site = ptr(dZ), _ld(dZ), ptr(dH), _ld(dH), dh_mode, fmask_site
     a.dQp, a.dqp_stride_b, a.db = ptr(dQp), dqp_stride_b, ptr(db)
     a.key = dropkey(seed, step, step_dev)
+    a.G = X.shape[1]
     call("sdumc_attn_bwd", a)
 
 
@@ -129,7 +130,7 @@ def act_bwd(dY, dZ, *, rows, cols, Y=None, scale=1.0, db=None, dY2=None) -> None
 def gate_fwd(a2, Wg, bg, h, *, R, g, qin) -> None:
     a = STRUCTS["sdumc_gate_fwd_args"]()
     a.a2, a.ld_a2, a.Wg, a.bg = ptr(a2), _ld(a2), ptr(Wg), ptr(bg)
-    a.h, a.ld_h, a.R = ptr(h), _ld(h), R
+    a.h, a.ld_h, a.R, a.G = ptr(h), _ld(h), R, a2.shape[1]
     a.g, a.qin, a.qin_stride = ptr(g), ptr(qin), qin.stride(0)
     call("sdumc_gate_fwd", a)
 
@@ -137,7 +138,7 @@ def gate_fwd(a2, Wg, bg, h, *, R, g, qin) -> None:
 def gate_bwd(dqin, dg_extra, g, h, a2, Wg, *, R, dh, da2, dWg, dbg) -> None:
     a = STRUCTS["sdumc_gate_bwd_args"]()
     a.dqin, a.dqin_stride, a.dg_extra, a.g = ptr(dqin), dqin.stride(0), ptr(dg_extra), ptr(g)
-    a.h, a.ld_h, a.a2, a.ld_a2, a.Wg, a.R = ptr(h), _ld(h), ptr(a2), _ld(a2), ptr(Wg), R
+    a.h, a.ld_h, a.a2, a.ld_a2, a.Wg, a.R, a.G = ptr(h), _ld(h), ptr(a2), _ld(a2), ptr(Wg), R, a2.shape[1]
     a.dh, a.ld_dh, a.da2, a.ld_da2 = ptr(dh), _ld(dh), ptr(da2), _ld(da2)
     a.dWg, a.dbg = ptr(dWg), ptr(dbg)
     call("sdumc_gate_bwd", a)
@@ -181,6 +182,7 @@ def final_bwd(dvals, df_ext, x2, Wr, W, r, f, Wv, *, R, dWc, dx2, dWr, dbr, dWv,
 def _loss_in(a, v0, v1, y, th0, th1, ct0, ct1, f0, f1, B):
     a.v0, a.v1, a.y = ptr(v0), ptr(v1), ptr(y)
     a.th0, a.th1, a.ct0, a.ct1, a.f0, a.f1, a.B = ptr(th0), ptr(th1), ptr(ct0), ptr(ct1), ptr(f0), ptr(f1), B
+    a.G = th0.shape[-1]
 
 
 def loss_sums(v0, v1, y, th0, th1, ct0, ct1, f0, f1, *, B, sums) -> None:

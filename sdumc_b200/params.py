@@ -27,8 +27,12 @@ DEAD_PREFIXES = ("missing_text_imagination_mlp.", "missing_cross_text_query_imag
                  "fc_out_ev.", "prelu.", "layer_normali.")
 
 
-def param_spec(input_dims: Sequence[int]) -> List[Tuple[str, Tuple[int, ...]]]:
-    G = GENERAL_DIM
+def param_spec(input_dims: Sequence[int], general_dim: int = GENERAL_DIM) -> List[Tuple[str, Tuple[int, ...]]]:
+    """general_dim = 256 is the reference (`general_dim = 256`, `fused_layer = '256,256'`, :191, :199).  Other values
+    are the additive `args.general_dim` knob (BASELINE config 4, "hidden 1024"): every dimension the reference ties
+    to general_dim OR to fused_layer scales together - the reference's own forward only type-checks when the two are
+    equal (fc_att is Linear(general_dim, 3) on the fused_layer-wide attention_mlp output, :222-223, :303)."""
+    G = general_dim
     spec: List[Tuple[str, Tuple[int, ...]]] = []
 
     def lin(name, out_f, in_f):
@@ -87,12 +91,15 @@ class Entry:
 
 
 class ParamLayout:
-    def __init__(self, input_dims: Sequence[int]):
+    def __init__(self, input_dims: Sequence[int], general_dim: int = GENERAL_DIM):
         self.input_dims = tuple(int(d) for d in input_dims[:3])
+        self.G = int(general_dim)
+        if self.G not in (256, 1024):
+            raise ValueError(f"general_dim must be 256 (reference) or 1024 (stress configuration), got {self.G}")
         for d in self.input_dims:
             if d % 8 != 0:
                 raise ValueError(f"input feature dims must be multiples of 8 for the bf16 TMA path, got {self.input_dims}")
-        self.spec = param_spec(self.input_dims)
+        self.spec = param_spec(self.input_dims, self.G)
         self.entries: Dict[str, Entry] = {}
         off = 0
         for live_pass in (True, False):

@@ -51,12 +51,13 @@ class Trainer:
 
     def __init__(self, input_dims: Sequence[int], B: int, frames: Sequence[int], device, *, lr=1e-4,
                  weight_decay=1e-5, loss_w: Sequence[float] = DEFAULT_LOSS_W, seed: int = 100,
-                 state_dict: Optional[Dict[str, torch.Tensor]] = None, process_group=None, use_graph: bool = True):
+                 state_dict: Optional[Dict[str, torch.Tensor]] = None, process_group=None, use_graph: bool = True,
+                 general_dim: int = 256):
         _lib.lib()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.SdumcError("sdumc_b200.Trainer needs a CUDA (sm_100a) device; there is no CPU fallback")
-        self.layout = ParamLayout(input_dims)
+        self.layout = ParamLayout(input_dims, general_dim)   # general_dim: additive knob, 256 = the reference (:191)
         self.dims = tuple(int(d) for d in input_dims)          # (Da, Dt, Dv[, D4 == Dt])
         self.B = int(B)
         self.frames = dict(zip(("a", "t0", "v", "t1"), (int(f) for f in frames)))   # (La, Lt, Lv, L4)
@@ -101,7 +102,8 @@ class Trainer:
         self.rnc_val = z(1)
         R = 2 * B
         self.d_vals, self.d_f, self.d_rnc = z(R), z(R * 128).view(R, 128), z(R * 64).view(R, 64)
-        self.d_th, self.d_ct = z(R * 256).view(R, 256), z(R * 896).view(R, 896)
+        Gd = self.layout.G
+        self.d_th, self.d_ct = z(R * Gd).view(R, Gd), z(R * 896).view(R, 896)
         self.y2 = z(R)
         n_g = 2 * B * self.world
         self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64), dtype=torch.uint8, device=dev)

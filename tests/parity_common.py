@@ -77,7 +77,7 @@ def l2err(got: torch.Tensor, ref: torch.Tensor, floor: float = 1e-12) -> float:
 def cuda_relu_gates(net):
     """ReLU(+dropout) on/off pattern of every MLP layer in the forward that just ran, keyed like the oracle."""
     t = net._last_state.t
-    G = 256
+    G = net.layout.G
     B = t["a2"].shape[0]
     g = {}
     for m, name in enumerate(("audio_mlp", "text_mlp", "video_mlp")):
@@ -98,7 +98,7 @@ def state_relu_gates(st, pass_idx: int):
     """ReLU on/off pattern of pass `pass_idx` of a fused two-pass forward (Trainer: rows [p*B, (p+1)*B) of every
     utterance-level buffer belong to pass p), keyed like the oracle."""
     t = st.t
-    G = 256
+    G = t["a2"].shape[1]
     B = st.cfg.B
     rows = slice(pass_idx * B, (pass_idx + 1) * B)
     rows7 = slice(pass_idx * B * 7, (pass_idx + 1) * B * 7)
@@ -138,9 +138,9 @@ def make_relu_from_gates(gates, masks=None, stats=None, pin=True):
     return relu
 
 
-def build_model(dims, P: Dict[str, torch.Tensor], seed=100, device="cuda"):
+def build_model(dims, P: Dict[str, torch.Tensor], seed=100, device="cuda", general_dim=256):
     from sdumc_b200.model import WengnetMOSEIMultViewsTextMissing
-    net = WengnetMOSEIMultViewsTextMissing(types.SimpleNamespace(input_dims=dims, seed=seed))
+    net = WengnetMOSEIMultViewsTextMissing(types.SimpleNamespace(input_dims=dims, seed=seed, general_dim=general_dim))
     net.load_state_dict({k: v.float() for k, v in P.items()}, strict=True)
     return net.to(device)
 
@@ -151,6 +151,7 @@ def kernel_masks(net, B, frames_amv, pass_idx: int):
     from sdumc_b200 import ops
     from sdumc_b200.engine import FRAME_P, MLP_P, dropout_site_names, site_id
     seed, step = net.dropout_seed, net._step
+    G = net.layout.G
     La, Lt, Lv = frames_amv
     Ls = (La, Lt, Lv)
     masks = {}
@@ -159,17 +160,17 @@ def kernel_masks(net, B, frames_amv, pass_idx: int):
         sid = site_id(name, 0)
         if name.endswith(".in"):
             m = int(name.split(".")[0][-1])
-            masks[name] = ops.frame_mask(seed, step, sid, B * Ls[m], 256).view(B, Ls[m], 256)
+            masks[name] = ops.frame_mask(seed, step, sid, B * Ls[m], G).view(B, Ls[m], G)
         elif name.endswith(".out"):
             nq = 1 if name.startswith("fra2utt") else 7
-            mk = ops.elem_mask(seed, step, sid, B * nq * 256, FRAME_P).view(B, nq, 256)
+            mk = ops.elem_mask(seed, step, sid, B * nq * G, FRAME_P).view(B, nq, G)
             masks[name] = mk[:, 0] if nq == 1 else mk
         else:
             base, idx = name.rsplit(".", 1)
             seven = base.startswith("cross_") and base.endswith("_mlp") and base not in ("cross_attention_mlp",) \
                 and "query" not in base
             width = {"cross_audio_mlp": (256, 128), "cross_text_mlp": (256, 128), "cross_video_mlp": (256, 128),
-                     "cross_attention_mlp": (256, 128)}.get(base, (256, 256))[int(idx)]
+                     "cross_attention_mlp": (256, 128)}.get(base, (G, G))[int(idx)]
             rows = B * 7 if seven else B
             mk = ops.elem_mask(seed, step, sid, rows * width, MLP_P).view(rows, width)
             masks[name] = mk.view(B, 7, width) if seven else mk
@@ -177,19 +178,19 @@ def kernel_masks(net, B, frames_amv, pass_idx: int):
 
 
 def run_parity(dims, frames, B, gain, train: bool, data_seed=4321, device="cuda", loss_w=None, emulate=False,
-               cotangent=False, count_flips=False, pin=None):
+               cotangent=False, count_flips=False, pin=None, general_dim=256):
     """Returns dict of normalised errors: outputs of both passes, the 6 loss terms, every live gradient.
 
     cotangent=True replaces the distillation loss by sum_p <output_p, C_p> with fixed random cotangents C:
     the vector-Jacobian product of the model alone (the RMSE / RnC terms are direction-like functions of
     differences of nearly equal features at initialisation and amplify forward rounding noise)."""
     from sdumc_b200.losses import MSELoss, RMSELoss, RnCLoss
-    P = O.init_params(dims, seed=100, gain=gain, dtype=torch.float64)
+    P = O.init_params(dims, seed=100, gain=gain, dtype=torch.float64, general_dim=general_dim)
     batch = O.synth_batch(B, dims, frames, seed=data_seed)
     # the CUDA path stores its inputs as bf16: hand the oracle the same rounded values
     b64 = {k: (v.bfloat16().double() if k != "vals" else v.double()) for k, v in batch.items()}
     P_bf = {k: v for k, v in P.items()}
-    net = build_model(dims, P, device=device)
+    net = build_model(dims, P, device=device, general_dim=general_dim)
     net.keep_last_state = True
     net.train(train)
     dev = {k: v.bfloat16().float().to(device) if k != "vals" else v.to(device) for k, v in batch.items()}

@@ -84,3 +84,24 @@ def test_distillation_loss_and_gradients(train):
     l2 = {k: v for k, v in res.items() if k.startswith("gradl2/")}
     bad = {k: v for k, v in l2.items() if not (v <= (3e-2 if k == "gradl2/orgin_linear_change.0.bias" else 2e-2))}
     assert not bad, "gradient L2 error: " + ", ".join(f"{k}={v:.3g}" for k, v in sorted(bad.items()))
+
+
+# ---- BASELINE config 4: "hidden 1024" (general_dim knob; the reference hard-codes 256 at :191) --------------------
+G1024 = dict(dims=(128, 160, 96, 160), frames=(40, 9, 33, 12), B=8)
+
+
+@pytest.mark.parametrize("train", [False, True], ids=["eval", "train"])
+def test_general_dim_1024_forward_and_vjp(train):
+    """The frame kernels at G = 1024 (16-row stages, 8 / 16 column groups of warps, N-tiled key projections with the
+    scores computed in the pooling kernel) and the widened utterance chain against the oracle built with the same
+    general_dim: outputs vs the exact fp64 oracle, gradients vs the oracle with the CUDA path's rounding points and
+    ReLU pattern - same criteria as the G = 256 tests (toy input dimensions: 3e-2)."""
+    cfg = G1024
+    res = run_parity(cfg["dims"], cfg["frames"], cfg["B"], gain=1.0, train=train, cotangent=True, emulate=True,
+                     general_dim=1024)
+    _check_outputs(res, "small")
+    _check_grads(res, "small")
+    if not train:
+        res = run_parity(cfg["dims"], cfg["frames"], cfg["B"], gain=1.0, train=False, cotangent=True, emulate=False,
+                         general_dim=1024)
+        _check_outputs(res, "small")
