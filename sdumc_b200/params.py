@@ -41,11 +41,12 @@ def param_spec(input_dims: Sequence[int], general_dim: int = GENERAL_DIM) -> Lis
 
     for i in range(3):
         lin(f"frame_dim_reshape_{i}", G, int(input_dims[i]))
-    for pre, d in (("missing_text_imagination_mlp", G), ("missing_cross_text_query_imagination_mlp", 128)):
+    # ResidualAE(layers=[mid], n_blocks=1, input_dim=d) (:202-203): the bottleneck widths 128 / 64 are literals
+    for pre, d, mid in (("missing_text_imagination_mlp", G, 128), ("missing_cross_text_query_imagination_mlp", 128, 64)):
         lin(f"{pre}.transition.0", d, 3 * d)
         lin(f"{pre}.transition.2", d, d)
-        lin(f"{pre}.encoder_0.0", d // 2, d)
-        lin(f"{pre}.decoder_0.0", d, d // 2)
+        lin(f"{pre}.encoder_0.0", mid, d)
+        lin(f"{pre}.decoder_0.0", d, mid)
     for i in range(3):
         spec.append((f"fra2utt_{i}.attention_context_vector", (1, G)))
         lin(f"fra2utt_{i}.input_proj", G, G)
