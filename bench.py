@@ -358,6 +358,36 @@ def run_ours(args):
         for extra in bench_kernel_probes(tr, ops, torch, dev, B, La, Da, rows, X, Wt, bias, time_alone, entry):
             roof_extra.append(extra)
 
+    # ---- BASELINE config 4 "S1": attention-heavy stress - 256 frames per modality, general_dim 1024, batch 1024 per run
+    #      split over the GPUs (strong scaling of a fixed job) ----
+    s1 = None
+    if not args.no_stress:
+        F_S1 = 30.77e9                                  # algorithmic FLOPs / sample
+        Bs1 = 1024 // world
+        tr.close()
+        tr1 = Trainer(S0_DIMS, Bs1, (256, 256, 256, 256), dev, lr=1e-4, weight_decay=1e-5, seed=100, process_group=pg,
+                      general_dim=1024)
+        b1 = synth_batch(Bs1, S0_DIMS, (256, 256, 256, 256), seed=777 + rank, device=dev)
+        tr1.load_batch(b1["audio"], b1["text"], b1["video"], b1["feat4"], b1["vals"])
+        for _ in range(3):
+            tr1.train_step()
+        barrier()
+        n1 = max(3, args.steps // 2)
+        e0.record()
+        for _ in range(n1):
+            tr1.train_step()
+        e1.record()
+        barrier()
+        ms1 = max_over_ranks(e0.elapsed_time(e1)) / n1
+        v1 = 1024 / (ms1 * 1e-3)
+        s1 = {"value": v1, "unit": "samples/s", "ms_per_step": ms1, "global_batch": 1024, "batch_per_gpu": Bs1,
+              "general_dim": 1024, "frames": [256, 256, 256, 256], "scaling": "strong", "steps": n1,
+              "loss_total": float(tr1.terms[6].item()),
+              "roofline": {"bound": "tensor", "achieved": v1 / world * F_S1 / 1e12, "peak": peaks["tc_sustained"],
+                           "unit": "TFLOP/s", "frac": v1 / world * F_S1 / 1e12 / peaks["tc_sustained"]}}
+        tr1.close()
+        del tr1, b1
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         Bc, times = cpu_reference_steps(n_steps=8, warmup=1, B=32)
@@ -393,6 +423,7 @@ def run_ours(args):
                                           "peak": peaks["tc_sustained"], "unit": "TFLOP/s",
                                           "frac": Bs / (ms_score128 * 1e-3) * F_INFER_PER_SAMPLE / 1e12 / peaks["tc_sustained"]}},
             "inference_100k": inf,
+            "stress_s1": s1,
             "roofline": roof,
             "roofline_extra": roof_extra,
             "cpu_baseline": cpu,
@@ -453,6 +484,7 @@ def main():
     ap.add_argument("--batch", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-inference", dest="no_inference", action="store_true", help="skip the config-5 inference leg")
+    ap.add_argument("--no-stress", dest="no_stress", action="store_true", help="skip the config-4 (G = 1024) stress leg")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

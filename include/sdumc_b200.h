@@ -154,7 +154,8 @@ typedef struct sdumc_attn_bwd_args {
   float* db;            /* [G] atomicAdd */
   sdumc_dropkey key;
   int32_t G;            /* general_dim: 0 or 256 (reference), or 1024 */
-  int32_t reserved;
+  int32_t max_ctas;     /* 0 = one persistent CTA per SM; > 0: at most this many (a share of the GPU, so that the
+                           blocks of several modalities run side by side) */
 } sdumc_attn_bwd_args;
 int sdumc_attn_bwd(const sdumc_attn_bwd_args* a, void* stream);
 

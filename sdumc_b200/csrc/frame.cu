@@ -689,7 +689,8 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   }
   const int rows_per_stage = G == 256 ? FrameCfg<256>::kRows : FrameCfg<1024>::kRows;
   const long n_units = (long)a.B * ((a.L + rows_per_stage - 1) / rows_per_stage);
-  const int grid = (int)std::min<long>(n_units, num_sms());   // one resident CTA per SM (shared-memory bound)
+  int grid = (int)std::min<long>(n_units, num_sms());   // one resident CTA per SM (shared-memory bound)
+  if (a.max_ctas > 0) grid = std::min(grid, a.max_ctas);
   if (G == 256) {
     if (a.nq == 1) attn_bwd_kernel<1, 256><<<grid, kBwdThreads, smem, stream>>>(a);
     else           attn_bwd_kernel<7, 256><<<grid, kBwdThreads, smem, stream>>>(a);

@@ -106,14 +106,34 @@ def _stream_mod(s: str) -> int:
     return {"a": 0, "t": 1, "v": 2}[s[0]]
 
 
-def _ksplits(rows_k: int, m_gemm: int, n_gemm: int) -> int:
+def _ksplits(rows_k: int, m_gemm: int, n_gemm: int, ctas: int = NUM_SMS) -> int:
     tiles = ((m_gemm + 127) // 128) * ((n_gemm + 255) // 256)
     nkb = max(1, (rows_k + 63) // 64)
-    return max(1, min(nkb, (NUM_SMS + tiles - 1) // tiles))
+    return max(1, min(nkb, (ctas + tiles - 1) // tiles))
+
+
+def _shares(weights: Dict, total: int = NUM_SMS, even: bool = True) -> Dict:
+    """Splits the SMs among kernels that run side by side, proportionally to their work; even counts (CTA pairs)."""
+    tot = float(sum(weights.values()))
+    unit = 2 if even else 1
+    out = {k: max(unit, int(total * w / tot) // unit * unit) for k, w in weights.items()}
+    # hand the remainder to the largest shares
+    left = total - sum(out.values())
+    for k in sorted(weights, key=lambda k: -weights[k]):
+        if left < unit:
+            break
+        out[k] += unit
+        left -= unit
+    return out
 
 
 class Engine:
     def __init__(self, layout: ParamLayout, device, multi_stream: bool = True):
+        import os
+        # SDUMC_SM_SHARES=1: the frame-level kernels of the modalities / units that run side by side on parallel
+        # streams each get a share of the SMs proportional to their rows (persistent kernels sized for the whole GPU
+        # serialise with a ramp-up / ramp-down gap between every two of them)
+        self.sm_shares = os.environ.get("SDUMC_SM_SHARES", "1") != "0" and multi_stream
         self.layout = layout
         self.G = layout.G
         self.device = device
@@ -256,7 +276,9 @@ class Engine:
         streams = ["a", "v"] + [f"t{p}" for p in range(NP)]
         units = [(p, m) for p in range(NP) for m in range(3)]
 
-        # 1. inputs -> bf16, in-projection (+ the dropped copies each attention block consumes)
+        # 1. inputs -> bf16, in-projection (+ the dropped copies each attention block consumes); the streams run side by
+        #    side, each on a share of the SMs proportional to its FLOPs (outputs are allocated before the fork)
+        plan = []
         for s in streams:
             x = inputs[s]
             L, D = cfg.frames[s], x.shape[-1]
@@ -271,23 +293,31 @@ class Engine:
             st.t[f"X.{s}"] = xb
             mod = _stream_mod(s)
             users = [(p, m) for (p, m) in units if _unit_stream(p, m) == s]
-            wname = INPROJ[mod]
             if drop:
                 tg, sites = [], []
                 for (p, m) in users:
                     for blk in ("fra2utt", "cross_att_fra2utt"):
-                        t = self._new(st, f"X{blk[0]}.{p}.{m}", (B * L, G), torch.bfloat16)
-                        tg.append(t)
+                        tg.append(self._new(st, f"X{blk[0]}.{p}.{m}", (B * L, G), torch.bfloat16))
                         sites.append(site_id(f"{blk}_{m}.in", p))
-                ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
-                         epi_kind=ops.EPI_INPROJ, targets=tg, target_sites=sites, seed=seed, step=step, step_dev=cfg.step_dev)
+                plan.append((s, xb, L, D, INPROJ[mod], tg, sites, None))
             else:
                 H = self._new(st, f"H.{s}", (B * L, G), torch.bfloat16)
-                ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
-                         epi_kind=ops.EPI_INPROJ, out_bf16=H)
                 for (p, m) in users:
                     st.t[f"Xf.{p}.{m}"] = H
                     st.t[f"Xc.{p}.{m}"] = H
+                plan.append((s, xb, L, D, INPROJ[mod], None, None, H))
+        in_share = _shares({i: pl[2] * pl[3] for i, pl in enumerate(plan)}) if self.sm_shares else {}
+
+        def inproj(i):
+            s, xb, L, D, wname, tg, sites, H = plan[i]
+            if tg is not None:
+                ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
+                         epi_kind=ops.EPI_INPROJ, targets=tg, target_sites=sites, seed=seed, step=step,
+                         step_dev=cfg.step_dev, max_ctas=in_share.get(i, 0))
+            else:
+                ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
+                         epi_kind=ops.EPI_INPROJ, out_bf16=H, max_ctas=in_share.get(i, 0))
+        self._parallel(len(plan), inproj)
 
         # 2. FRA2UTT_new per unit: key projection + scores (GEMM epilogue), softmax + pooling
         u_pool = [self._new(st, f"u.{m}", (R, G)) for m in range(3)]
@@ -299,9 +329,12 @@ class Engine:
                 self._new(st, f"Kf.{p}.{m}", (B * L, G), torch.bfloat16)
             self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
 
+        unit_share = _shares({i: cfg.frames[_unit_stream(p, m)] for i, (p, m) in enumerate(units)}) if self.sm_shares else {}
+
         def fra2utt_unit(i):
             p, m = units[i]
             L = cfg.frames[_unit_stream(p, m)]
+            mc = unit_share.get(i, 0)
             X = st.t[f"Xf.{p}.{m}"]
             S = st.t[f"Sf.{p}.{m}"]
             Kt = st.t[f"Kf.{p}.{m}"] if keep else None
@@ -311,14 +344,15 @@ class Engine:
                 # one query: the score is a single dot product per row, free in the GEMM epilogue (K is stored only
                 # when the backward pass needs it), and the pooling kernel reads X' alone
                 ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                         act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=ctx, q_stride=0, nq=1, L=L, scores=S)
+                         act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=ctx, q_stride=0, nq=1, L=L, scores=S,
+                         max_ctas=mc)
                 Kp, Qc = None, None
             else:
                 # wider models: a row spans several N tiles of the key projection, so the scores come from the pooling
                 # kernel's tensor-core product over the stored K (like the 7-query blocks)
                 Kp = Kt if keep else torch.empty(B * L, G, dtype=torch.bfloat16, device=dev)
                 ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                         act=ops.ACT_TANH, out_bf16=Kp)
+                         act=ops.ACT_TANH, out_bf16=Kp, max_ctas=mc)
                 Qc = ctx
             ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=st.t[f"Of_pre.{p}.{m}"], out=u_pool[m][p * B:(p + 1) * B],
                          out_stride_b=G, out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
@@ -385,7 +419,7 @@ class Engine:
             # epilogue - writing and re-reading K costs less than those FMAs
             Kt = st.t[f"Kc.{p}.{m}"] if keep else torch.empty(B * L, G, dtype=torch.bfloat16, device=dev)
             ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                     act=ops.ACT_TANH, out_bf16=Kt)
+                     act=ops.ACT_TANH, out_bf16=Kt, max_ctas=unit_share.get(i, 0))
             ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=st.t[f"Oc_pre.{p}.{m}"], out=C[m][p * B * NQ:(p + 1) * B * NQ],
                          out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
                          drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step,
@@ -498,12 +532,15 @@ class Engine:
                 dH[s_] = torch.empty(B * cfg.frames[s_], G, dtype=torch.bfloat16, device=dev)
         started: Dict[str, bool] = {}
         dQp = [z(R * NQ, G) for _ in range(3)]     # attn_bwd accumulates (a sample may be split over CTAs)
+        # the three modalities' blocks run side by side, each on a share of the SMs proportional to its frames
+        mod_share = _shares({m: cfg.frames[_unit_stream(0, m)] for m in range(3)}) if self.sm_shares else {}
 
         def cross_attn_bwd(m):                     # passes of one modality accumulate into the same dH: in order
             for p in range(NP):
                 self._attn_block_bwd(W, st, p, m, "cross_att_fra2utt", NQ, dOut=dC[m][p * B * NQ:(p + 1) * B * NQ],
                                      Qp=t[f"Qp.{m}"][p * B * NQ:(p + 1) * B * NQ], qp_stride=NQ * G,
-                                     dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH, started=started)
+                                     dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH, started=started,
+                                     max_ctas=mod_share.get(m, 0))
         self._parallel(3, cross_attn_bwd)
         # B7. query projections -> dQ
         dQ = z(R * NQ, G)                            # the three blocks add their share side by side (fp32 reds)
@@ -545,24 +582,27 @@ class Engine:
             for p in range(NP):
                 self._attn_block_bwd(W, st, p, m, "fra2utt", 1, dOut=du[m][p * B:(p + 1) * B],
                                      Qp=W.f32(pre + ".attention_context_vector"), qp_stride=0,
-                                     dQp=W.grad(pre + ".attention_context_vector"), dH=dH, started=started)
+                                     dQp=W.grad(pre + ".attention_context_vector"), dH=dH, started=started,
+                                     max_ctas=mod_share.get(m, 0))
         self._parallel(3, fra2utt_bwd)
         # B11. in-projection weight / bias gradients (inputs carry no gradient)
         items = list(dH.items())
+        dw_share = _shares({i: t[f"X.{s_}"].numel() for i, (s_, _) in enumerate(items)}) if self.sm_shares else {}
 
         def inproj_bwd(i):
             s, dHs = items[i]
             wname = INPROJ[_stream_mod(s)]
             X = t[f"X.{s}"]
             rows, D = X.shape
-            ops.gemm(dHs, X, M=G, N=D, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, G, D),
-                     out_f32=W.grad(wname + ".weight"), f32_mode=ops.OUT_ATOMIC)
+            mc = dw_share.get(i, 0)
+            ops.gemm(dHs, X, M=G, N=D, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, G, D, mc or NUM_SMS),
+                     out_f32=W.grad(wname + ".weight"), f32_mode=ops.OUT_ATOMIC, max_ctas=mc)
             ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
         self._parallel(len(items), inproj_bwd)
         self._join_side()
 
     def _attn_block_bwd(self, W: Weights, st: State, p: int, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
-                        dH: Dict[str, torch.Tensor], started: Dict[str, bool]):
+                        dH: Dict[str, torch.Tensor], started: Dict[str, bool], max_ctas: int = 0):
         cfg = st.cfg
         G = self.G
         t = st.t
@@ -582,10 +622,12 @@ class Engine:
         ops.attn_bwd(X, Kt, P, dOut, dout_stride_b=nq * G, O_pre=Opre, Qp=Qp, qp_stride_b=qp_stride, B=B, L=L, nq=nq,
                      out_drop_p=FRAME_P if cfg.dropout else 0.0, out_site=site_id(pre + ".out", p), dZ=dZ, dH=dH[s],
                      dh_mode=0 if first else 1, fmask_site=fmask, dQp=dQp, dqp_stride_b=nq * G,
-                     db=W.grad(pre + ".input_proj.bias"), seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev)
+                     db=W.grad(pre + ".input_proj.bias"), seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev,
+                     max_ctas=max_ctas)
         # dH += (dZ W_in) * M_in
         ops.gemm(dZ, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, b_mn=True, fmask_site=fmask,
-                 out_bf16=dH[s], bf16_mode=ops.OUT_ADD, seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev)
+                 out_bf16=dH[s], bf16_mode=ops.OUT_ADD, seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev,
+                 max_ctas=max_ctas)
         # dW_in += dZ^T X'
-        ops.gemm(dZ, X, M=G, N=G, K=B * L, a_mn=True, b_mn=True, k_splits=_ksplits(B * L, G, G),
-                 out_f32=W.grad(pre + ".input_proj.weight"), f32_mode=ops.OUT_ATOMIC)
+        ops.gemm(dZ, X, M=G, N=G, K=B * L, a_mn=True, b_mn=True, k_splits=_ksplits(B * L, G, G, max_ctas or NUM_SMS),
+                 out_f32=W.grad(pre + ".input_proj.weight"), f32_mode=ops.OUT_ATOMIC, max_ctas=max_ctas)

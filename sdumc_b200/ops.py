@@ -103,7 +103,7 @@ def pool_fwd(X, S, *, B, L, nq, O_pre, out, out_stride_b, out_bf16=None, drop_p=
 
 
 def attn_bwd(X, Kt, P, dOut, *, dout_stride_b, O_pre, Qp, qp_stride_b, B, L, nq, out_drop_p, out_site, dZ, dH,
-             dh_mode, fmask_site, dQp, dqp_stride_b, db, seed=0, step=0, step_dev=None, alpha=0.3) -> None:
+             dh_mode, fmask_site, dQp, dqp_stride_b, db, seed=0, step=0, step_dev=None, alpha=0.3, max_ctas=0) -> None:
     a = STRUCTS["sdumc_attn_bwd_args"]()
     a.X, a.ldx, a.Kt, a.ldk, a.P = ptr(X), _ld(X), ptr(Kt), _ld(Kt), ptr(P)
     a.dOut, a.dout_stride_b, a.O_pre = ptr(dOut), dout_stride_b, ptr(O_pre)
@@ -114,6 +114,7 @@ def attn_bwd(X, Kt, P, dOut, *, dout_stride_b, O_pre, Qp, qp_stride_b, B, L, nq,
     a.dQp, a.dqp_stride_b, a.db = ptr(dQp), dqp_stride_b, ptr(db)
     a.key = dropkey(seed, step, step_dev)
     a.G = X.shape[1]
+    a.max_ctas = max_ctas
     call("sdumc_attn_bwd", a)
 
 
