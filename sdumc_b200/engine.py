@@ -130,10 +130,11 @@ def _shares(weights: Dict, total: int = NUM_SMS, even: bool = True) -> Dict:
 class Engine:
     def __init__(self, layout: ParamLayout, device, multi_stream: bool = True):
         import os
-        # SDUMC_SM_SHARES=1: the frame-level kernels of the modalities / units that run side by side on parallel
-        # streams each get a share of the SMs proportional to their rows (persistent kernels sized for the whole GPU
-        # serialise with a ramp-up / ramp-down gap between every two of them)
-        self.sm_shares = os.environ.get("SDUMC_SM_SHARES", "1") != "0" and multi_stream
+        # SDUMC_SM_SHARES=1 (experiment, off): the frame-level kernels of the units that run side by side on parallel
+        # streams each get a share of the SMs proportional to their rows instead of a grid sized for the whole GPU.
+        # Measured 5.17 vs 3.99 ms per step (profiles/r2_experiments.md): the non-persistent kernels of a unit only find
+        # the SMs its own predecessor frees, so the short (text) pipelines become the long pole.
+        self.sm_shares = os.environ.get("SDUMC_SM_SHARES", "0") == "1" and multi_stream
         self.layout = layout
         self.G = layout.G
         self.device = device
