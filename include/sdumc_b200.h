@@ -125,6 +125,16 @@ typedef struct sdumc_pool_fwd_args {
   int64_t qp_stride_b;
   int32_t G;            /* general_dim: 0 or 256 (reference), or 1024 (BASELINE config 4); 256 in the comments above */
   int32_t reserved;
+  /* Length-aware (varlen) eval execution with the reference's padding semantics.  The reference
+   * right-zero-pads every batch and has NO mask (read_data.py:223-248; `pads` ignored, feat_data.py:239,253): a padded
+   * frame still takes part in the softmax with h_pad = in-projection bias, k_pad = tanh(W_in h_pad + b_in).  With
+   * row_off set, X / Kt / S hold only the VALID frames, packed: sample b owns rows [row_off[b], row_off[b+1]); L is the
+   * padded length the reference would see, and the (L - T_b) padded frames enter in closed form: the denominator gains
+   * (L - T_b) exp(alpha s_pad,q) and the pooled value (L - T_b) p_pad,q h_pad.  Eval mode only (input dropout makes
+   * padded rows differ in train mode: those batches run padded).  Qp is required (s_pad,q = k_pad . Qp_q). */
+  const int32_t* row_off;   /* [B+1] device, or NULL = dense padded layout */
+  const SDUMC_BF16* Hpad;   /* [G] */
+  const SDUMC_BF16* Kpad;   /* [G] */
 } sdumc_pool_fwd_args;
 int sdumc_pool_fwd(const sdumc_pool_fwd_args* a, void* stream);
 
@@ -168,9 +178,11 @@ int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, int32_t col
  *   row_offset  [n_utt + 1] first row of each utterance (device, int64)
  *   idx         [b] utterances of the batch (device, int32)
  *   out         bf16 [b, Lpad, D]: out[i, l] = packed[row_offset[idx[i]] + l] for l < T_i, else 0
+ *   out_off     NULL, or [b + 1] device int32: PACKED output for the varlen path - only the valid rows are written,
+ *               utterance i at rows [out_off[i], out_off[i+1]) of out (no padding rows at all)
  * D % 8 == 0, 16-byte aligned pointers; utterances longer than Lpad are an error the caller rules out. */
 int sdumc_collate_pad(const SDUMC_BF16* packed, const int64_t* row_offset, const int32_t* idx, int32_t b,
-                      int32_t Lpad, int32_t D, SDUMC_BF16* out, void* stream);
+                      int32_t Lpad, int32_t D, SDUMC_BF16* out, const int32_t* out_off, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * 4. Utterance-level glue between the MLP GEMMs (reference :301-320, :346-364) and the

@@ -106,8 +106,8 @@ int sdumc_colsum_bf16(const SDUMC_BF16* X, int64_t ld, int64_t rows, int32_t col
   return launch_colsum_bf16(X, ld, rows, cols, out, static_cast<cudaStream_t>(stream));
 }
 int sdumc_collate_pad(const SDUMC_BF16* packed, const int64_t* row_offset, const int32_t* idx, int32_t b,
-                      int32_t Lpad, int32_t D, SDUMC_BF16* out, void* stream) {
-  return launch_collate_pad(packed, reinterpret_cast<const long long*>(row_offset), idx, b, Lpad, D, out,
+                      int32_t Lpad, int32_t D, SDUMC_BF16* out, const int32_t* out_off, void* stream) {
+  return launch_collate_pad(packed, reinterpret_cast<const long long*>(row_offset), idx, b, Lpad, D, out, out_off,
                             static_cast<cudaStream_t>(stream));
 }
 int sdumc_sqdiff_sum(const float* a, const float* b, int64_t n, float* out_sum, void* stream) {

@@ -78,14 +78,23 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform (uniform-register bulk copies)
   const int gid = lane >> 2, tq = lane & 3;
   const int rw = warp % kSlabs, cw = warp / kSlabs, hc = cw * kWCols;   // row slab / column group of this warp
-  const int L = a.L;
+  // dense layout: sample b owns rows [b*L, (b+1)*L).  Varlen (row_off): only its T_b valid frames exist, packed at
+  // rows [row_off[b], row_off[b+1]); the a.L - T_b padded frames of the reference's batch enter in closed form below.
+  long row0 = (long)b * a.L;
+  int L = a.L;
+  if (a.row_off) {
+    row0 = __ldg(a.row_off + b);
+    L = __ldg(a.row_off + b + 1) - (int)row0;
+  }
+  const int n_pad = a.L - L;
+  __shared__ float ppad_s[8];                                // probability mass of the padded frames per query
   const int n_iter = (L + kFwdRows - 1) / kFwdRows;
   const bool has_k = a.Kt != nullptr;
   const int n_total = has_k ? 2 * n_iter : n_iter;
   const DropKey key = resolve_key(a.key);
-  const __nv_bfloat16* Xb = a.X + (long)b * L * G;          // host guarantees dense [B*L,256]
-  const __nv_bfloat16* Kb = has_k ? a.Kt + (long)b * L * G : nullptr;
-  float* Sg = a.S + (long)b * L * NQ;
+  const __nv_bfloat16* Xb = a.X + row0 * G;                  // host guarantees dense [rows,G]
+  const __nv_bfloat16* Kb = has_k ? a.Kt + row0 * G : nullptr;
+  float* Sg = a.S + row0 * NQ;
 
   auto issue_stage = [&](int j) {                           // lane 0 of warp w: rows w*rpw .. w*rpw + rpw - 1
     constexpr int rpw = kFwdRows / 8;
@@ -149,7 +158,14 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
       // (every score of the sample is in S_s: the K phase ended with a __syncthreads, or the prologue did)
       for (int q = warp; q < 8; q += kFwdThreads / 32) {
         if (q < NQ) {
-          float m = -INFINITY;
+          // score of a padded frame of this sample: s_pad = k_pad . Qp_q (the same for all its padded frames)
+          float sp = 0.f;
+          if (n_pad > 0) {
+            const float* Qg = a.Qp + (long)b * a.qp_stride_b + (long)q * G;
+            for (int g = lane; g < G; g += 32) sp = fmaf(__bfloat162float(a.Kpad[g]), __ldg(Qg + g), sp);
+            sp = warp_sum(sp);
+          }
+          float m = n_pad > 0 ? sp : -INFINITY;
           for (int l = lane; l < L; l += 32) m = fmaxf(m, S_s[l * 8 + q]);
           m = warp_max(m);
           float ssum = 0.f;
@@ -159,10 +175,13 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
             ssum += e;
           }
           ssum = warp_sum(ssum);
-          const float inv = 1.f / ssum;
+          const float epad = n_pad > 0 ? (float)n_pad * __expf(a.alpha * (sp - m)) : 0.f;
+          const float inv = 1.f / (ssum + epad);
           for (int l = lane; l < L; l += 32) S_s[l * 8 + q] *= inv;
+          if (lane == 0) ppad_s[q] = epad * inv;
         } else {
           for (int l = lane; l < L; l += 32) S_s[l * 8 + q] = 0.f;
+          if (lane == 0) ppad_s[q] = 0.f;
         }
       }
       __syncthreads();
@@ -247,6 +266,7 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
     float o;
     if constexpr (kSlabs == 4) o = (part[i] + part[8 * G + i]) + (part[2 * 8 * G + i] + part[3 * 8 * G + i]);
     else o = part[i];
+    if (n_pad > 0) o = fmaf(ppad_s[i / G], __bfloat162float(a.Hpad[i % G]), o);   // the padded frames' pooled share
     a.O_pre[(long)b * NQ * G + i] = o;
     float y = o;
     if (a.drop_p > 0.f) {
@@ -261,6 +281,9 @@ __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a)
 int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.X && a.S && a.O_pre && a.out, "pool_fwd: null pointer");
   SDUMC_CHECK_ARG(a.B > 0 && a.L > 0 && (a.nq == 1 || a.nq == 7), "pool_fwd: bad shape B=%d L=%d nq=%d", a.B, a.L, a.nq);
+  if (a.row_off)
+    SDUMC_CHECK_ARG(a.Hpad && a.Kpad && a.Qp && a.drop_p == 0.f,
+                    "pool_fwd: the varlen layout needs Hpad, Kpad and Qp and is defined for eval mode only (no dropout)");
   const int G = a.G > 0 ? a.G : 256;
   SDUMC_CHECK_ARG(G == 256 || G == 1024, "pool_fwd: general_dim %d unsupported (256 or 1024)", G);
   SDUMC_CHECK_ARG(a.ldx == G && (reinterpret_cast<uintptr_t>(a.X) & 15u) == 0,
@@ -733,25 +756,27 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t 
 __global__ void __launch_bounds__(256) collate_pad_kernel(const __nv_bfloat16* __restrict__ packed,
                                                            const long long* __restrict__ row_offset,
                                                            const int* __restrict__ idx, int b, int Lpad, int D,
-                                                           __nv_bfloat16* __restrict__ out) {
+                                                           __nv_bfloat16* __restrict__ out,
+                                                           const int* __restrict__ out_off) {
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long)b * Lpad) return;
   const int i = (int)(row / Lpad), l = (int)(row - (long)i * Lpad);
   const int u = __ldg(idx + i);
   const long long r0 = __ldg(row_offset + u), r1 = __ldg(row_offset + u + 1);
   const bool live = l < (int)(r1 - r0);
+  if (out_off && !live) return;                       // packed output: padding rows do not exist
   const uint4* src = reinterpret_cast<const uint4*>(packed + (r0 + l) * (long long)D);
-  uint4* dst = reinterpret_cast<uint4*>(out + row * D);
+  uint4* dst = reinterpret_cast<uint4*>(out + (out_off ? (long)(__ldg(out_off + i) + l) : row) * D);
   for (int c = threadIdx.x & 31; c < D / 8; c += 32) dst[c] = live ? __ldg(src + c) : make_uint4(0, 0, 0, 0);
 }
 int launch_collate_pad(const __nv_bfloat16* packed, const long long* row_offset, const int* idx, int b, int Lpad, int D,
-                       __nv_bfloat16* out, cudaStream_t stream) {
+                       __nv_bfloat16* out, const int* out_off, cudaStream_t stream) {
   SDUMC_CHECK_ARG(packed && row_offset && idx && out, "collate_pad: null pointer");
   SDUMC_CHECK_ARG(b > 0 && Lpad > 0 && D > 0 && D % 8 == 0, "collate_pad: bad shape b=%d Lpad=%d D=%d", b, Lpad, D);
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
                   "collate_pad: pointers must be 16-byte aligned");
   const long rows = (long)b * Lpad;
-  collate_pad_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(packed, row_offset, idx, b, Lpad, D, out);
+  collate_pad_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(packed, row_offset, idx, b, Lpad, D, out, out_off);
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -26,7 +26,7 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream);
 int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t stream);
 int launch_colsum_bf16(const __nv_bfloat16* X, long ld, long rows, int cols, float* out, cudaStream_t stream);
 int launch_collate_pad(const __nv_bfloat16* packed, const long long* row_offset, const int* idx, int b, int Lpad, int D,
-                       __nv_bfloat16* out, cudaStream_t stream);
+                       __nv_bfloat16* out, const int* out_off, cudaStream_t stream);
 // chain.cu
 int launch_act_bwd(const ActBwdArgs& a, cudaStream_t stream);
 int launch_gate_fwd(const GateFwdArgs& a, cudaStream_t stream);

@@ -87,6 +87,10 @@ class Cfg:
     seed: int = 0
     step: int = 0
     step_dev: Optional[torch.Tensor] = None   # device uint32 counter added to step (CUDA-graph replay)
+    # varlen (eval only): per stream an int32 device tensor [B+1] of cumulative valid-frame counts.
+    # The inputs then hold only the valid frames, packed ([sum_T, D]); `frames` stays the padded length the
+    # reference's collater would produce (the padded frames enter the softmaxes in closed form, ops.pool_fwd).
+    row_off: Optional[Dict[str, torch.Tensor]] = None
 
 
 @dataclass
@@ -280,11 +284,20 @@ class Engine:
         # 1. inputs -> bf16, in-projection (+ the dropped copies each attention block consumes); the streams run side by
         #    side, each on a share of the SMs proportional to its FLOPs (outputs are allocated before the fork)
         plan = []
+        varlen = cfg.row_off is not None
+        if varlen:
+            assert not drop and not keep, "the varlen layout is defined for eval mode (no dropout, no backward)"
+        nrows: Dict[str, int] = {}
         for s in streams:
             x = inputs[s]
             L, D = cfg.frames[s], x.shape[-1]
-            assert x.shape[0] == B and x.shape[1] == L, f"stream {s}: expected [{B},{L},D], got {tuple(x.shape)}"
-            x2 = x.reshape(B * L, D)
+            if varlen:
+                assert x.dim() == 2, f"stream {s}: packed [sum_T, D] expected"
+                x2 = x
+            else:
+                assert x.shape[0] == B and x.shape[1] == L, f"stream {s}: expected [{B},{L},D], got {tuple(x.shape)}"
+                x2 = x.reshape(B * L, D)
+            nrows[s] = x2.shape[0]
             if x2.dtype == torch.float32:
                 xb = torch.empty(B * L, D, dtype=torch.bfloat16, device=dev)
                 ops.cast_bf16(x2.contiguous(), xb)
@@ -302,7 +315,7 @@ class Engine:
                         sites.append(site_id(f"{blk}_{m}.in", p))
                 plan.append((s, xb, L, D, INPROJ[mod], tg, sites, None))
             else:
-                H = self._new(st, f"H.{s}", (B * L, G), torch.bfloat16)
+                H = self._new(st, f"H.{s}", (nrows[s], G), torch.bfloat16)
                 for (p, m) in users:
                     st.t[f"Xf.{p}.{m}"] = H
                     st.t[f"Xc.{p}.{m}"] = H
@@ -316,18 +329,31 @@ class Engine:
                          epi_kind=ops.EPI_INPROJ, targets=tg, target_sites=sites, seed=seed, step=step,
                          step_dev=cfg.step_dev, max_ctas=in_share.get(i, 0))
             else:
-                ops.gemm(xb, W.bf16(wname + ".weight"), M=B * L, N=G, K=D, bias=W.f32(wname + ".bias"),
+                ops.gemm(xb, W.bf16(wname + ".weight"), M=xb.shape[0], N=G, K=D, bias=W.f32(wname + ".bias"),
                          epi_kind=ops.EPI_INPROJ, out_bf16=H, max_ctas=in_share.get(i, 0))
         self._parallel(len(plan), inproj)
+
+        # varlen: the constants of a padded frame per modality / block: h_pad = in-projection bias (as stored: bf16),
+        # k_pad = tanh(W_in h_pad + b_in)
+        pad_c: Dict[Tuple[str, int], Tuple[torch.Tensor, torch.Tensor]] = {}
+        if varlen:
+            for m in range(3):
+                hp = W.bf16(INPROJ[m] + ".bias").reshape(1, G)
+                for blk in ("fra2utt", "cross_att_fra2utt"):
+                    kp = torch.empty(1, G, dtype=torch.bfloat16, device=dev)
+                    ops.gemm(hp, W.bf16(f"{blk}_{m}.input_proj.weight"), M=1, N=G, K=G,
+                             bias=W.f32(f"{blk}_{m}.input_proj.bias"), act=ops.ACT_TANH, out_bf16=kp)
+                    pad_c[(blk, m)] = (hp, kp)
 
         # 2. FRA2UTT_new per unit: key projection + scores (GEMM epilogue), softmax + pooling
         u_pool = [self._new(st, f"u.{m}", (R, G)) for m in range(3)]
         u_pool_b = [self._new(st, f"u_bf16.{m}", (R, G), torch.bfloat16) for m in range(3)]
         for (p, m) in units:
             L = cfg.frames[_unit_stream(p, m)]
-            self._new(st, f"Sf.{p}.{m}", (B * L, 1))
+            nr = nrows[_unit_stream(p, m)]
+            self._new(st, f"Sf.{p}.{m}", (nr, 1))
             if keep:
-                self._new(st, f"Kf.{p}.{m}", (B * L, G), torch.bfloat16)
+                self._new(st, f"Kf.{p}.{m}", (nr, G), torch.bfloat16)
             self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
 
         unit_share = _shares({i: cfg.frames[_unit_stream(p, m)] for i, (p, m) in enumerate(units)}) if self.sm_shares else {}
@@ -335,6 +361,9 @@ class Engine:
         def fra2utt_unit(i):
             p, m = units[i]
             L = cfg.frames[_unit_stream(p, m)]
+            nr = nrows[_unit_stream(p, m)]
+            vl = dict(row_off=cfg.row_off[_unit_stream(p, m)], Hpad=pad_c[("fra2utt", m)][0],
+                      Kpad=pad_c[("fra2utt", m)][1]) if varlen else {}
             mc = unit_share.get(i, 0)
             X = st.t[f"Xf.{p}.{m}"]
             S = st.t[f"Sf.{p}.{m}"]
@@ -344,21 +373,21 @@ class Engine:
             if G == 256:
                 # one query: the score is a single dot product per row, free in the GEMM epilogue (K is stored only
                 # when the backward pass needs it), and the pooling kernel reads X' alone
-                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=nr, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
                          act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kt, qv=ctx, q_stride=0, nq=1, L=L, scores=S,
                          max_ctas=mc)
-                Kp, Qc = None, None
+                Kp, Qc = None, (ctx if varlen else None)      # varlen: the pooling kernel scores the padded frame itself
             else:
                 # wider models: a row spans several N tiles of the key projection, so the scores come from the pooling
                 # kernel's tensor-core product over the stored K (like the 7-query blocks)
-                Kp = Kt if keep else torch.empty(B * L, G, dtype=torch.bfloat16, device=dev)
-                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+                Kp = Kt if keep else torch.empty(nr, G, dtype=torch.bfloat16, device=dev)
+                ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=nr, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
                          act=ops.ACT_TANH, out_bf16=Kp, max_ctas=mc)
                 Qc = ctx
             ops.pool_fwd(X, S, B=B, L=L, nq=1, O_pre=st.t[f"Of_pre.{p}.{m}"], out=u_pool[m][p * B:(p + 1) * B],
                          out_stride_b=G, out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
                          site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev, Kt=Kp, Qp=Qc,
-                         qp_stride_b=0)
+                         qp_stride_b=0, **vl)
         self._parallel(len(units), fra2utt_unit)
 
         # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
@@ -403,9 +432,10 @@ class Engine:
         C_b = [self._new(st, f"C_bf16.{m}", (R * NQ, G), torch.bfloat16) for m in range(3)]
         for (p, m) in units:
             L = cfg.frames[_unit_stream(p, m)]
-            self._new(st, f"Sc.{p}.{m}", (B * L, NQ))
+            nr = nrows[_unit_stream(p, m)]
+            self._new(st, f"Sc.{p}.{m}", (nr, NQ))
             if keep:
-                self._new(st, f"Kc.{p}.{m}", (B * L, G), torch.bfloat16)
+                self._new(st, f"Kc.{p}.{m}", (nr, G), torch.bfloat16)
             self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
 
         def cross_unit(i):
@@ -418,13 +448,16 @@ class Engine:
             # K is materialised (kept for the backward pass when training, a temporary when scoring): the 7 scores
             # per row come from the pooling kernel's tensor-core product instead of 7 x 256 SIMT FMAs in the GEMM
             # epilogue - writing and re-reading K costs less than those FMAs
-            Kt = st.t[f"Kc.{p}.{m}"] if keep else torch.empty(B * L, G, dtype=torch.bfloat16, device=dev)
-            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=B * L, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
+            nr = nrows[_unit_stream(p, m)]
+            vl = dict(row_off=cfg.row_off[_unit_stream(p, m)], Hpad=pad_c[("cross_att_fra2utt", m)][0],
+                      Kpad=pad_c[("cross_att_fra2utt", m)][1]) if varlen else {}
+            Kt = st.t[f"Kc.{p}.{m}"] if keep else torch.empty(nr, G, dtype=torch.bfloat16, device=dev)
+            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=nr, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
                      act=ops.ACT_TANH, out_bf16=Kt, max_ctas=unit_share.get(i, 0))
             ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=st.t[f"Oc_pre.{p}.{m}"], out=C[m][p * B * NQ:(p + 1) * B * NQ],
                          out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
                          drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step,
-                         step_dev=cfg.step_dev, Kt=Kt, Qp=qp, qp_stride_b=NQ * G)
+                         step_dev=cfg.step_dev, Kt=Kt, Qp=qp, qp_stride_b=NQ * G, **vl)
         self._parallel(len(units), cross_unit)
 
         # 5. utterance chain B

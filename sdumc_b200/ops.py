@@ -71,14 +71,17 @@ def cast_bf16(src: torch.Tensor, dst: torch.Tensor) -> None:
     check(_lib.lib().sdumc_cast_bf16(ptr(src), ptr(dst), src.numel(), current_stream()), "sdumc_cast_bf16")
 
 
-def collate_pad(packed: torch.Tensor, row_offset: torch.Tensor, idx: torch.Tensor, Lpad: int, out: torch.Tensor) -> None:
-    """out[b, Lpad, D] = right-zero-padded utterances idx of the packed device store (read_data.py:223-248)."""
+def collate_pad(packed: torch.Tensor, row_offset: torch.Tensor, idx: torch.Tensor, Lpad: int, out: torch.Tensor,
+                out_off: torch.Tensor = None) -> None:
+    """out[b, Lpad, D] = right-zero-padded utterances idx of the packed device store (read_data.py:223-248); with
+    out_off ([b+1] int32, device) the output is PACKED: only the valid rows, utterance i at rows out_off[i].. of out."""
     assert packed.dtype == torch.bfloat16 and out.dtype == torch.bfloat16 and packed.is_contiguous() and out.is_contiguous()
     assert row_offset.dtype == torch.int64 and idx.dtype == torch.int32
     b, D = idx.numel(), packed.shape[1]
-    assert out.numel() == b * Lpad * D
-    check(_lib.lib().sdumc_collate_pad(ptr(packed), ptr(row_offset), ptr(idx), b, Lpad, D, ptr(out), current_stream()),
-          "sdumc_collate_pad")
+    assert out_off is not None or out.numel() == b * Lpad * D
+    assert out_off is None or (out_off.dtype == torch.int32 and out_off.numel() == b + 1)
+    check(_lib.lib().sdumc_collate_pad(ptr(packed), ptr(row_offset), ptr(idx), b, Lpad, D, ptr(out), ptr(out_off),
+                                       current_stream()), "sdumc_collate_pad")
 
 
 def colsum_bf16(X: torch.Tensor, out: torch.Tensor) -> None:
@@ -89,7 +92,7 @@ def colsum_bf16(X: torch.Tensor, out: torch.Tensor) -> None:
 
 
 def pool_fwd(X, S, *, B, L, nq, O_pre, out, out_stride_b, out_bf16=None, drop_p=0.0, site=0, seed=0, step=0,
-             step_dev=None, alpha=0.3, Kt=None, Qp=None, qp_stride_b=0) -> None:
+             step_dev=None, alpha=0.3, Kt=None, Qp=None, qp_stride_b=0, row_off=None, Hpad=None, Kpad=None) -> None:
     """softmax over frames + pooling; with Kt/Qp the scores are computed in the kernel (S is output only)."""
     a = STRUCTS["sdumc_pool_fwd_args"]()
     a.X, a.ldx, a.S = ptr(X), _ld(X), ptr(S)
@@ -99,6 +102,7 @@ def pool_fwd(X, S, *, B, L, nq, O_pre, out, out_stride_b, out_bf16=None, drop_p=
     a.O_pre, a.out, a.out_stride_b, a.out_bf16 = ptr(O_pre), ptr(out), out_stride_b, ptr(out_bf16)
     a.drop_p, a.site, a.key = drop_p, site, dropkey(seed, step, step_dev)
     a.G = X.shape[1]
+    a.row_off, a.Hpad, a.Kpad = ptr(row_off), ptr(Hpad), ptr(Kpad)
     call("sdumc_pool_fwd", a)
 
 

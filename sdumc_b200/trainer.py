@@ -467,12 +467,46 @@ class Trainer:
         return vals[0], vals[1]
 
     # ---- scoring (main_frame_val_text_missing_inference.py:158-175) --------------------------
-    def _score_body(self):
-        st = self._forward(dropout=False, need_grad=False)
+    @staticmethod
+    def _score_dict(st):
         vals, f, rnc, th, ct = Engine.outputs(st)
         return {"val_preds_full": vals[0], "val_preds_missing": vals[1], "full_rep": f[0], "missing_rep": f[1],
                 "full_rnc": rnc[0], "missing_rnc": rnc[1], "text_rep_query_full": th[0].contiguous(),
                 "text_rep_query_missing": th[1].contiguous(), "text_rep_full": ct[0], "text_rep_missing": ct[1]}
+
+    def _score_body(self):
+        return self._score_dict(self._forward(dropout=False, need_grad=False))
+
+    @torch.no_grad()
+    def score_varlen(self, store, idx):
+        """Scores the ragged batch `idx` of a DeviceStore4F WITHOUT touching padded frames, with the
+        reference's semantics: the reference pads every modality to the batch maximum and has no mask, so padded frames
+        (in-projection = bias) take part in both softmaxes (read_data.py:223-248; …text_missing.py:63, :90).  Here the
+        batch is gathered PACKED (valid frames only), every frame-level GEMM runs on sum_T rows instead of B * L_max,
+        and the pooling kernels add the padded frames' closed-form share.  Equal to score() on the padded batch up to
+        rounding (tests/test_trainer_gpu.py); eval mode only - train-mode input dropout makes padded rows differ."""
+        b = len(idx)
+        if b > self.B:
+            raise ValueError(f"batch of {b} exceeds the trainer's capacity {self.B}")
+        frames = store.batch_frames(idx)
+        idx_dev = torch.tensor(list(idx), dtype=torch.int32).to(self.device, non_blocking=True)
+        inputs, row_off = {}, {}
+        for key, sname, Lpad in zip(("a", "t0", "v", "t1"), ("audio", "text", "video", "feat4"), frames):
+            D = self.in_dims[key]
+            if store.packed[sname].shape[1] != D or Lpad > self.frames[key]:
+                raise ValueError(f"stream {key}: store has D={store.packed[sname].shape[1]}, batch needs {Lpad} frames; "
+                                 f"capacity [{self.B},{self.frames[key]},{D}]")
+            lens = [store.lengths[sname][i] for i in idx]
+            cum = [0]
+            for n in lens:
+                cum.append(cum[-1] + n)
+            off = torch.tensor(cum, dtype=torch.int32).to(self.device, non_blocking=True)
+            dst = self.in_flat[key][:cum[-1] * D].view(cum[-1], D)
+            ops.collate_pad(store.packed[sname], store.offsets[sname], idx_dev, Lpad, dst, out_off=off)
+            inputs[key], row_off[key] = dst, off
+        cfg = Cfg(B=b, n_pass=2, frames=dict(zip(("a", "t0", "v", "t1"), frames)), dropout=False, need_grad=False,
+                  seed=self.drop_seed, step=0, step_dev=self.step_dev, row_off=row_off)
+        return self._score_dict(self.engine.forward(self.W, inputs, cfg))
 
     @torch.no_grad()
     def score(self):

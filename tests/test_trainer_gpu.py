@@ -227,3 +227,41 @@ def test_collate_kernel_equals_reference_padding_golden():
     out = torch.empty(3 * L * 16, dtype=torch.bfloat16, device=dev)
     ops.collate_pad(ds.packed["audio"], ds.offsets["audio"], torch.tensor(ids, dtype=torch.int32, device=dev), L, out)
     assert np.array_equal(out.view(3, L, 16).float().cpu().numpy(), z["batch/audio"][[4, 2, 0], :L])
+
+
+def test_varlen_scoring_equals_padded_scoring_and_the_oracle():
+    """Trainer.score_varlen (packed valid frames + the closed-form share of the padded frames in the
+    pooling kernels) against (a) Trainer.score on the same ragged batch right-zero-padded to the batch maximum by the
+    collate kernel - the reference's semantics, padded frames inside both softmaxes - and (b) the exact fp64 oracle
+    forward on the padded batch.  Also with one utterance of a single frame and one of full length."""
+    from sdumc_b200.dataset import DeviceStore4F, Store4F
+    from sdumc_b200.trainer import Trainer
+    dev = torch.device("cuda", 0)
+    P = O.init_params(DIMS, seed=100, gain=1.0, dtype=torch.float64)
+    n = 14
+    store = Store4F.synthetic(n, DIMS, FRAMES, seed=21, ragged=True)
+    for s_, L in zip(("audio", "text", "video", "feat4"), FRAMES):          # edge lengths
+        store.feats[s_][3] = store.feats[s_][3][:1].clone()
+        full = torch.randn(L, store.feats[s_][5].shape[1]).bfloat16()
+        store.feats[s_][5] = full
+    store = Store4F(store.feats, store.vals.tolist(), store.names)
+    ds = DeviceStore4F(store, dev)
+    tr = Trainer(DIMS, n, FRAMES, dev, state_dict={k: v.float() for k, v in P.items()}, use_graph=False)
+    idx = list(range(n))
+    tr.load_from_store(ds, idx)
+    ref = {k: v.clone() for k, v in tr.score().items()}
+    got = tr.score_varlen(ds, idx)
+    batch, _, _ = store.collate(idx)
+    o0 = O.forward(P, batch["audio"].double(), batch["text"].double(), batch["video"].double())
+    o1 = O.forward(P, batch["audio"].double(), batch["feat4"].double(), batch["video"].double())
+    exact = {"val_preds_full": o0[0], "val_preds_missing": o1[0], "full_rep": o0[1][0], "missing_rep": o1[1][0],
+             "full_rnc": o0[1][1], "missing_rnc": o1[1][1], "text_rep_query_full": o0[1][2],
+             "text_rep_query_missing": o1[1][2], "text_rep_full": o0[1][3], "text_rep_missing": o1[1][3]}
+
+    def nerr(a, b):
+        a, b = a.double().cpu(), b.double().cpu()
+        return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+    for k in ref:
+        assert got[k].shape == ref[k].shape, k
+        assert nerr(got[k], ref[k]) <= 3e-3, (k, nerr(got[k], ref[k]))       # packed vs padded execution on the GPU
+        assert nerr(got[k], exact[k]) <= 1e-2, (k, nerr(got[k], exact[k]))   # vs the exact oracle (reference semantics)
