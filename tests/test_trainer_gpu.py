@@ -264,4 +264,6 @@ def test_varlen_scoring_equals_padded_scoring_and_the_oracle():
     for k in ref:
         assert got[k].shape == ref[k].shape, k
         assert nerr(got[k], ref[k]) <= 3e-3, (k, nerr(got[k], ref[k]))       # packed vs padded execution on the GPU
-        assert nerr(got[k], exact[k]) <= 1e-2, (k, nerr(got[k], exact[k]))   # vs the exact oracle (reference semantics)
+        # vs the exact oracle (reference semantics); toy dimensions: the embedding tolerance of tests/test_model_gpu.py
+        assert nerr(got[k], exact[k]) <= 2e-2, (k, nerr(got[k], exact[k]))
+        assert nerr(got[k], exact[k]) <= nerr(ref[k], exact[k]) + 3e-3, k      # no worse than the padded execution
