@@ -341,6 +341,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const bool rmw = kKind == KIND_RMW || (kKind == KIND_GENERIC && ep.out_bf16 && ep.bf16_mode == OUT_ADD);
     const bool ctx_shared = kKind == KIND_KEYPROJ && ep.q_stride == 0 && ep.nq == 1;
     constexpr int NC = kBlockN / 32;
+    // per-column vectors (bias, shared query) of an N tile -> this group's shared-memory copy (group-local named
+    // barrier, 128 threads).  With a single N tile (every frame-level GEMM) they are staged ONCE per CTA: the global
+    // load + barrier used to sit on every tile's epilogue, which paces these kernels (profiles/r2_experiments.md).
+    auto stage_vecs = [&](int n_blk) {
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the previous tile's readers are done
+      for (int j = gtid; j < kBlockN; j += 128) {
+        const int n = n_blk * kBlockN + j;
+        bias_s[j] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.f;
+        if (ctx_shared) ctx_s[j] = n < sh.N ? __ldg(ep.qv + n) : 0.f;
+      }
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+    };
+    if (n_tiles == 1) stage_vecs(0);
     int li = 0;
     for (int t = cta0; t < num_tiles; t += nctas, ++li) {
       if ((li & 1) != grp) continue;
@@ -348,13 +361,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       const int mn = t % (m_tiles * n_tiles);
       const int mu = mn / n_tiles, n_blk = mn - mu * n_tiles;
       const int m_blk = kPair ? 2 * mu + (int)crank : mu;
-      // stage the per-column vectors of this tile (group-local named barrier: 128 threads)
-      for (int j = gtid; j < kBlockN; j += 128) {
-        const int n = n_blk * kBlockN + j;
-        bias_s[j] = (ep.bias && n < sh.N) ? __ldg(ep.bias + n) : 0.f;
-        if (ctx_shared) ctx_s[j] = n < sh.N ? __ldg(ep.qv + n) : 0.f;
-      }
-      asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+      if (n_tiles > 1) stage_vecs(n_blk);
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int r0 = m_blk * 128 + ew * 32;  // first row of this warp's slab
