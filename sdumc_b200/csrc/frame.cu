@@ -8,7 +8,6 @@
 //   toolkit/models/wengnet_mosei_mult_views_text_missing.py:56-68, :79-95 (forward);
 //   the backward formulas are autograd of those lines.
 #include <algorithm>
-#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -680,176 +679,6 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   bulk_wait_all();
 }
 
-
-// ------------------------------------------------------------------------------------------
-// backward, row-wise part, SINGLE query (the FRA2UTT_new blocks).  With one query every product of the block is a
-// dot product or an outer product per frame row (~5 G FMAs per row instead of ~28 G for seven queries): a streaming
-// fp32 SIMT kernel - one warp per row, a lane owns 8 columns of every 256-column block, 16-byte coalesced
-// accesses, two rows in flight - is bound by HBM, while the padded-to-8 tensor-core version above pays the same
-// staging / hand-over structure as the 7-query case (117 vs 129 us for the audio unit).
-//   dO = dOut * M_out; delta = <O_pre, dO>;  dP_l = <X'_l, dO>;  dS_l = alpha P_l (dP_l - delta)
-//   dZ_l = dS_l c * (1 - K_l^2);  dc += sum_l dS_l K_l;  db_in += sum_l dZ_l;  dH_l (+)= P_l dO * M_in
-// Frame masks: one Philox call covers 128 columns of a row; lane i of a group of 32 / (G/128) rows draws the words
-// of (row i / (G/128), block i % (G/128)) and the owners fetch theirs by shuffle.
-// ------------------------------------------------------------------------------------------
-template <int G>
-__global__ void __launch_bounds__(G == 256 ? 512 : 256) attn_bwd1_kernel(AttnBwdArgs a) {
-  constexpr int NB = G / 256;            // 256-column blocks per row (8 columns per lane each)
-  constexpr int NBK = G / 128;           // Philox calls per row
-  constexpr int RG = 32 / NBK;           // rows per mask group
-  __shared__ float red_q[G], red_b[G];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int nwarps = (int)(gridDim.x * (blockDim.x >> 5));
-  const int gw = (int)blockIdx.x * (int)(blockDim.x >> 5) + warp;
-  const int L = a.L;
-  const long rows = (long)a.B * L;
-  // contiguous, RG-aligned row range per warp (a warp changes sample rarely)
-  long per = (rows + nwarps - 1) / nwarps;
-  per = (per + RG - 1) / RG * RG;
-  const long r_begin = std::min<long>(rows, per * gw), r_end = std::min<long>(rows, r_begin + per);
-  const DropKey key = resolve_key(a.key);
-  const uint32_t thr = drop_threshold(a.out_drop_p);
-  const float oscale = a.out_drop_p > 0.f ? 1.f / (1.f - a.out_drop_p) : 1.f;
-  const bool rmw = a.dh_mode == 1;
-  const bool shared_q = a.qp_stride_b == 0;
-
-  float dO[NB][8], cx[NB][8], dq[NB][8], dbv[NB][8];
-#pragma unroll
-  for (int n = 0; n < NB; ++n)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) dq[n][j] = dbv[n][j] = 0.f;
-  float delta = 0.f;
-  int cur_b = -1;
-
-  auto flush_dq = [&](int b) {           // per-sample queries: the sample's dQp leaves when the warp moves on
-#pragma unroll
-    for (int n = 0; n < NB; ++n)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        atomicAdd(a.dQp + (long)b * a.dqp_stride_b + n * 256 + lane * 8 + j, dq[n][j]);
-        dq[n][j] = 0.f;
-      }
-  };
-  auto load_sample = [&](int b) {
-    float part = 0.f;
-#pragma unroll
-    for (int n = 0; n < NB; ++n) {
-      const int c0 = n * 256 + lane * 8;
-      const float4 d0 = __ldg(reinterpret_cast<const float4*>(a.dOut + (long)b * a.dout_stride_b + c0));
-      const float4 d1 = __ldg(reinterpret_cast<const float4*>(a.dOut + (long)b * a.dout_stride_b + c0 + 4));
-      const float4 o0 = __ldg(reinterpret_cast<const float4*>(a.O_pre + (long)b * G + c0));
-      const float4 o1 = __ldg(reinterpret_cast<const float4*>(a.O_pre + (long)b * G + c0 + 4));
-      const float4 q0 = __ldg(reinterpret_cast<const float4*>(a.Qp + (long)b * a.qp_stride_b + c0));
-      const float4 q1 = __ldg(reinterpret_cast<const float4*>(a.Qp + (long)b * a.qp_stride_b + c0 + 4));
-      float d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
-      if (a.out_drop_p > 0.f) {          // element dropout of the pooled output: counter e >> 2, word e & 3
-        const uint32_t e = (uint32_t)b * (uint32_t)G + (uint32_t)c0;
-        const U4 ra = philox4x32_10(e >> 2, 0x5D0Cu, a.out_site, key.step, key.seed_lo, key.seed_hi);
-        const U4 rb = philox4x32_10((e >> 2) + 1, 0x5D0Cu, a.out_site, key.step, key.seed_lo, key.seed_hi);
-        const uint32_t w[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d[j] = w[j] >= thr ? d[j] * oscale : 0.f;
-      }
-      const float o[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-      const float q[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        dO[n][j] = d[j];
-        cx[n][j] = q[j];
-        part = fmaf(o[j], d[j], part);
-      }
-    }
-    delta = warp_sum(part);
-  };
-
-  for (long rg = r_begin; rg < r_end; rg += RG) {
-    // frame-mask words of this group of RG rows: lane i draws (row rg + i / NBK, block i % NBK)
-    U4 mw = U4{0, 0, 0, 0};
-    if (a.fmask_site) {
-      const long mr = rg + lane / NBK;
-      if (mr < rows) mw = frame_mask_words(key, a.fmask_site, (uint32_t)mr, (uint32_t)(lane % NBK));
-    }
-    const int n_here = (int)std::min<long>(RG, r_end - rg);
-    for (int rr = 0; rr < n_here; ++rr) {
-      const long r = rg + rr;
-      const int b = (int)(r / L);
-      if (b != cur_b) {                  // warp-uniform
-        if (cur_b >= 0 && !shared_q) flush_dq(cur_b);
-        cur_b = b;
-        load_sample(b);
-      }
-      uint4 xv[NB], kv[NB], hv[NB];
-#pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        const long off = r * G + n * 256 + lane * 8;
-        xv[n] = __ldg(reinterpret_cast<const uint4*>(a.X + off));
-        kv[n] = __ldg(reinterpret_cast<const uint4*>(a.Kt + off));
-        if (rmw) hv[n] = *reinterpret_cast<const uint4*>(a.dH + off);
-      }
-      const float p = __ldg(a.P + r);
-      float x[NB][8], k[NB][8];
-      float part = 0.f;
-#pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        unpack8(xv[n], x[n]);
-        unpack8(kv[n], k[n]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) part = fmaf(x[n][j], dO[n][j], part);
-      }
-      const float dP = warp_sum(part);
-      const float dS = a.alpha * p * (dP - delta);
-#pragma unroll
-      for (int n = 0; n < NB; ++n) {
-        float z[8], hx[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          z[j] = dS * cx[n][j] * (1.f - k[n][j] * k[n][j]);
-          dq[n][j] = fmaf(dS, k[n][j], dq[n][j]);
-          hx[j] = p * dO[n][j];
-        }
-        if (a.fmask_site) {
-          const int src = rr * NBK + 2 * n + (lane >> 4);
-          const uint32_t w0 = __shfl_sync(0xffffffffu, mw.x, src), w1 = __shfl_sync(0xffffffffu, mw.y, src);
-          const uint32_t w2 = __shfl_sync(0xffffffffu, mw.z, src), w3 = __shfl_sync(0xffffffffu, mw.w, src);
-          const int wi = (lane & 15) >> 2;
-          const uint32_t bits = (wi == 0 ? w0 : (wi == 1 ? w1 : (wi == 2 ? w2 : w3))) >> ((lane & 3) * 8);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) hx[j] = ((bits >> j) & 1u) ? 2.f * hx[j] : 0.f;
-        }
-        // dZ is stored as bf16; the bias gradient sums the rounded values' fp32 originals (like the tensor-core kernel)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dbv[n][j] += z[j];
-        if (rmw) {
-          float old[8];
-          unpack8(hv[n], old);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) hx[j] += old[j];
-        }
-        const long off = r * G + n * 256 + lane * 8;
-        *reinterpret_cast<uint4*>(a.dZ + off) = pack8(z);
-        *reinterpret_cast<uint4*>(a.dH + off) = pack8(hx);
-      }
-    }
-  }
-  if (cur_b >= 0 && !shared_q) flush_dq(cur_b);
-  // block-level reduction of the bias gradient (and of the shared query's gradient), then one atomic per column
-  for (int i = tid; i < G; i += blockDim.x) { red_q[i] = 0.f; red_b[i] = 0.f; }
-  __syncthreads();
-#pragma unroll
-  for (int n = 0; n < NB; ++n)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int c = n * 256 + lane * 8 + j;
-      atomicAdd(&red_b[c], dbv[n][j]);
-      if (shared_q) atomicAdd(&red_q[c], dq[n][j]);
-    }
-  __syncthreads();
-  for (int i = tid; i < G; i += blockDim.x) {
-    atomicAdd(a.db + i, red_b[i]);
-    if (shared_q) atomicAdd(a.dQp + i, red_q[i]);
-  }
-}
-
 static size_t attn_bwd_smem(int L, int G) {
   const size_t tile = G == 256 ? FrameCfg<256>::kTile : FrameCfg<1024>::kTile;
   return (size_t)kBwdStages * 2 * tile + (size_t)8 * (G + 8) * 2 + (size_t)2 * G * 8 * 2 + (size_t)8 * G * 4 +
@@ -869,20 +698,6 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.dOut) | reinterpret_cast<uintptr_t>(a.Qp) | reinterpret_cast<uintptr_t>(a.O_pre)) & 15u) == 0 &&
                   a.dout_stride_b % 4 == 0 && a.qp_stride_b % 4 == 0,
                   "attn_bwd: dOut / Qp / O_pre must be 16-byte aligned with strides that are multiples of 4");
-  // single query: the streaming SIMT kernel (SDUMC_ATTN1_MMA=1 keeps the tensor-core kernel for A/B timing)
-  static const bool simt1 = [] { const char* e = getenv("SDUMC_ATTN1_MMA"); return !(e && e[0] == '1'); }();
-  if (a.nq == 1 && simt1) {
-    // 32 warps per SM at G = 256 (2 x 16), 16 at G = 1024 (2 x 8: 128 accumulator registers per lane)
-    const int threads = G == 256 ? 512 : 256;
-    int grid = 2 * num_sms();
-    if (a.max_ctas > 0) grid = std::min(grid, 2 * a.max_ctas);
-    const long rows = (long)a.B * a.L;
-    grid = (int)std::min<long>(grid, (rows + threads / 32 - 1) / (threads / 32));
-    if (G == 256) attn_bwd1_kernel<256><<<grid, threads, 0, stream>>>(a);
-    else          attn_bwd1_kernel<1024><<<grid, threads, 0, stream>>>(a);
-    SDUMC_CUDA(cudaGetLastError());
-    return 0;
-  }
   const size_t smem = attn_bwd_smem(a.L, G);
   constexpr size_t kMaxDyn = 218 * 1024;   // + 8.3 KB static (dP exchange, barriers) stays under the 227 KB per-CTA limit
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
