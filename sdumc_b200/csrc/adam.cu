@@ -8,6 +8,8 @@
 namespace sdumc {
 
 __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a, float step_size, float inv_bc2_sqrt) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i4 >= a.n) return;
   const float b1 = a.beta1, b2 = a.beta2;
@@ -67,7 +69,7 @@ int launch_adam(const AdamArgs& a, cudaStream_t stream) {
   const float step_size = (float)((double)a.lr / bc1);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   const long nthreads = (a.n + 3) / 4;
-  adam_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(a, step_size, inv_bc2_sqrt);
+  SDUMC_CUDA(launch_kernel(adam_kernel, dim3((unsigned)((nthreads + 255) / 256)), dim3(256), 0, stream, 1, a, step_size, inv_bc2_sqrt));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

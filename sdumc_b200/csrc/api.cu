@@ -7,6 +7,8 @@ namespace sdumc {
 const char* last_error();
 
 __global__ void frame_mask_kernel(DropKey key, uint32_t site, long rows, int cols, float* out) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (row, 32-col chunk)
   const int chunks = (cols + 31) / 32;
   if (idx >= rows * chunks) return;
@@ -20,6 +22,8 @@ __global__ void frame_mask_kernel(DropKey key, uint32_t site, long rows, int col
 }
 
 __global__ void elem_mask_kernel(DropKey key, uint32_t site, long n, uint32_t thr, float scale, float* out) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const long e = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n) return;
   out[e] = elem_rand(key, site, (uint32_t)e) >= thr ? scale : 0.f;
@@ -64,8 +68,8 @@ int sdumc_frame_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t rows, 
   SDUMC_CHECK_ARG(out && rows > 0 && cols > 0, "sdumc_frame_mask: bad arguments");
   DropKey key = make_dropkey(seed, step);
   const long n = rows * ((cols + 31) / 32);
-  frame_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(key, site, rows, cols,
-                                                                                                 out);
+  SDUMC_CUDA(launch_kernel(frame_mask_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, key, site, rows, cols,
+                                                                                                 out));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -73,8 +77,7 @@ int sdumc_frame_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t rows, 
 int sdumc_elem_mask(uint64_t seed, uint32_t step, uint32_t site, int64_t n, float p, float* out, void* stream) {
   SDUMC_CHECK_ARG(out && n > 0 && p >= 0.f && p < 1.f, "sdumc_elem_mask: bad arguments");
   DropKey key = make_dropkey(seed, step);
-  elem_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      key, site, n, drop_threshold(p), 1.f / (1.f - p), out);
+  SDUMC_CUDA(launch_kernel(elem_mask_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1, key, site, n, drop_threshold(p), 1.f / (1.f - p), out));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

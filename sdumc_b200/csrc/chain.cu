@@ -12,6 +12,8 @@ namespace sdumc {
 
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) act_bwd_kernel(ActBwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   // 64 column-quads x 4 row lanes; the bias gradient is reduced inside the block before the atomics
   // (one atomic per column per block: same-address atomics serialise in L2).
   __shared__ float red[4][256];
@@ -59,7 +61,7 @@ int launch_act_bwd(const ActBwdArgs& a, cudaStream_t stream) {
                   "act_bwd: ld %% 4");
   int blocks = (a.rows + 63) / 64;
   if (blocks > 148) blocks = 148;
-  act_bwd_kernel<<<blocks, 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(act_bwd_kernel, dim3(blocks), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -77,6 +79,8 @@ __device__ __forceinline__ void st8(float* p, const float (&x)[8]) {
 }
 
 __global__ void __launch_bounds__(256) gate_fwd_kernel(GateFwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= a.R) return;
@@ -115,12 +119,14 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(GateFwdArgs a) {
 int launch_gate_fwd(const GateFwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.a2 && a.Wg && a.bg && a.h && a.g && a.qin && a.R > 0, "gate_fwd: bad arguments");
   SDUMC_CHECK_ARG(a.G > 0 && a.G % 256 == 0 && a.G <= 1024, "gate: general_dim %d unsupported", a.G);
-  gate_fwd_kernel<<<(a.R + 7) / 8, 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(gate_fwd_kernel, dim3((a.R + 7) / 8), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void __launch_bounds__(256) gate_bwd_kernel(GateBwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   __shared__ float sW[3 * 1024];
   __shared__ float sb[4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -187,7 +193,7 @@ int launch_gate_bwd(const GateBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.dqin && a.g && a.h && a.a2 && a.Wg && a.dh && a.da2 && a.dWg && a.dbg && a.R > 0,
                   "gate_bwd: bad arguments");
   SDUMC_CHECK_ARG(a.G > 0 && a.G % 256 == 0 && a.G <= 1024, "gate: general_dim %d unsupported", a.G);
-  gate_bwd_kernel<<<(a.R + 7) / 8, 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(gate_bwd_kernel, dim3((a.R + 7) / 8), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -196,6 +202,8 @@ int launch_gate_bwd(const GateBwdArgs& a, cudaStream_t stream) {
 // W[r,q,c] = sum_m g[r,m] c_m[r,q,c]     (7*128 = 896 values per row)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) weight_fwd_kernel(WeightFwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const long i4 = ((long)blockIdx.x * 256 + threadIdx.x) * 4;
   if (i4 >= (long)a.R * 896) return;
   const long r = i4 / 896;
@@ -213,12 +221,14 @@ __global__ void __launch_bounds__(256) weight_fwd_kernel(WeightFwdArgs a) {
 int launch_weight_fwd(const WeightFwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.c[0] && a.c[1] && a.c[2] && a.g && a.W && a.R > 0, "weight_fwd: bad arguments");
   const long n4 = (long)a.R * 896 / 4;
-  weight_fwd_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(weight_fwd_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void __launch_bounds__(256) weight_bwd_kernel(WeightBwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= a.R) return;
@@ -246,7 +256,7 @@ __global__ void __launch_bounds__(256) weight_bwd_kernel(WeightBwdArgs a) {
 int launch_weight_bwd(const WeightBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.dW && a.c[0] && a.c[1] && a.c[2] && a.g && a.dc[0] && a.dc[1] && a.dc[2] && a.dg && a.R > 0,
                   "weight_bwd: bad arguments");
-  weight_bwd_kernel<<<(a.R + 7) / 8, 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(weight_bwd_kernel, dim3((a.R + 7) / 8), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -255,6 +265,8 @@ int launch_weight_bwd(const WeightBwdArgs& a, cudaStream_t stream) {
 // r = cross_fc_att(x2) [7]; f = sum_q r_q W_q [128]; vals = fc_out_v(f).  Warp per row, lane owns 4 columns.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) final_fwd_kernel(FinalFwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int r = blockIdx.x * 8 + warp;
   if (r >= a.R) return;
@@ -286,12 +298,14 @@ __global__ void __launch_bounds__(256) final_fwd_kernel(FinalFwdArgs a) {
 int launch_final_fwd(const FinalFwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.x2 && a.Wr && a.br && a.W && a.Wv && a.bv && a.r && a.f && a.vals && a.R > 0,
                   "final_fwd: bad arguments");
-  final_fwd_kernel<<<(a.R + 7) / 8, 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(final_fwd_kernel, dim3((a.R + 7) / 8), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
 
 __global__ void __launch_bounds__(256) final_bwd_kernel(FinalBwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   __shared__ float sWr[7][128];
   __shared__ float sWv[128];
   __shared__ float sbr[8];
@@ -342,7 +356,7 @@ int launch_final_bwd(const FinalBwdArgs& a, cudaStream_t stream) {
   SDUMC_CHECK_ARG(a.x2 && a.Wr && a.W && a.r && a.f && a.Wv && a.dWc && a.dx2 && a.dWr && a.dbr && a.dWv && a.dbv &&
                       a.R > 0,
                   "final_bwd: bad arguments");
-  final_bwd_kernel<<<(a.R + 7) / 8, 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(final_bwd_kernel, dim3((a.R + 7) / 8), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <utility>
 
 #define SDUMC_INTERNAL 1
 #include "../../include/sdumc_b200.h"
@@ -31,6 +32,45 @@ int set_error(int code, const char* fmt, ...);  // returns code; message via sdu
 constexpr int kMaxDevices = 64;
 int current_device();   // cudaGetDevice(), clamped to [0, kMaxDevices)
 int num_sms();          // SM count of the current device (cached per device)
+
+// Programmatic dependent launch (PDL).  Kernels of one stream are launched with the programmatic-stream-
+// serialization attribute: the next kernel's CTAs may become resident (and run their prologue: barrier init, TMEM
+// allocation, descriptor prefetch) as soon as every CTA of the previous kernel has passed pdl_launch_dependents()
+// and SM resources are free; pdl_wait() then blocks until the previous grid has COMPLETED and its writes are
+// visible.  Every kernel of the library calls pdl_wait() before its first global-memory access, so each still
+// observes all of its predecessors complete (completion is transitive along the chain).  Captured into CUDA graphs
+// as programmatic edges.  SDUMC_PDL=0 turns it off (plain launches).
+bool pdl_enabled();
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = (unsigned)cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
 
 #define SDUMC_CHECK_ARG(cond, ...)                                   \
   do {                                                               \

@@ -60,6 +60,8 @@ constexpr int kFwdThreads = 256;
 
 template <int NQ, int G>
 __global__ void __launch_bounds__(kFwdThreads, 2) pool_fwd_kernel(PoolFwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   using FC = FrameCfg<G>;
   constexpr int kFwdRows = FC::kRows, kFwdPitch = FC::kPitch, kFwdTile = FC::kTile, kSlabs = FC::kSlabs;
   constexpr int kCW = FC::kFwdColWarps, kWCols = G / kCW;   // 128 columns per warp
@@ -308,11 +310,11 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
     attr_done[dev] = true;
   }
   if (G == 256) {
-    if (a.nq == 1) pool_fwd_kernel<1, 256><<<a.B, kFwdThreads, smem, stream>>>(a);
-    else           pool_fwd_kernel<7, 256><<<a.B, kFwdThreads, smem, stream>>>(a);
+    if (a.nq == 1) SDUMC_CUDA(launch_kernel(pool_fwd_kernel<1, 256>, dim3(a.B), dim3(kFwdThreads), smem, stream, 1, a));
+    else           SDUMC_CUDA(launch_kernel(pool_fwd_kernel<7, 256>, dim3(a.B), dim3(kFwdThreads), smem, stream, 1, a));
   } else {
-    if (a.nq == 1) pool_fwd_kernel<1, 1024><<<a.B, kFwdThreads, smem, stream>>>(a);
-    else           pool_fwd_kernel<7, 1024><<<a.B, kFwdThreads, smem, stream>>>(a);
+    if (a.nq == 1) SDUMC_CUDA(launch_kernel(pool_fwd_kernel<1, 1024>, dim3(a.B), dim3(kFwdThreads), smem, stream, 1, a));
+    else           SDUMC_CUDA(launch_kernel(pool_fwd_kernel<7, 1024>, dim3(a.B), dim3(kFwdThreads), smem, stream, 1, a));
   }
   SDUMC_CUDA(cudaGetLastError());
   return 0;
@@ -346,6 +348,8 @@ constexpr int kBwdThreads = 512;
 
 template <int NQ, int G>
 __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   using FC = FrameCfg<G>;
   constexpr int kBwdRows = FC::kRows;      // rows per stage (16 per slab)
   constexpr int kBwdPitch = FC::kPitch;    // bf16 elements per padded shared-memory row
@@ -715,11 +719,11 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   int grid = (int)std::min<long>(n_units, num_sms());   // one resident CTA per SM (shared-memory bound)
   if (a.max_ctas > 0) grid = std::min(grid, a.max_ctas);
   if (G == 256) {
-    if (a.nq == 1) attn_bwd_kernel<1, 256><<<grid, kBwdThreads, smem, stream>>>(a);
-    else           attn_bwd_kernel<7, 256><<<grid, kBwdThreads, smem, stream>>>(a);
+    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 256>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, a));
+    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 256>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, a));
   } else {
-    if (a.nq == 1) attn_bwd_kernel<1, 1024><<<grid, kBwdThreads, smem, stream>>>(a);
-    else           attn_bwd_kernel<7, 1024><<<grid, kBwdThreads, smem, stream>>>(a);
+    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 1024>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, a));
+    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 1024>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, a));
   }
   SDUMC_CUDA(cudaGetLastError());
   return 0;
@@ -729,6 +733,8 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
 // small streaming helpers
 // ------------------------------------------------------------------------------------------
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long n) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 8;
   if (i + 8 <= n) {
     const float4 a = __ldg(reinterpret_cast<const float4*>(src + i));
@@ -744,7 +750,7 @@ int launch_cast_bf16(const float* src, __nv_bfloat16* dst, long n, cudaStream_t 
   SDUMC_CHECK_ARG((reinterpret_cast<uintptr_t>(src) & 15u) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0,
                   "cast_bf16: pointers must be 16-byte aligned");
   const long nthreads = (n + 7) / 8;
-  cast_f32_bf16_kernel<<<(unsigned)((nthreads + 255) / 256), 256, 0, stream>>>(src, dst, n);
+  SDUMC_CUDA(launch_kernel(cast_f32_bf16_kernel, dim3((unsigned)((nthreads + 255) / 256)), dim3(256), 0, stream, 1, src, dst, n));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -758,6 +764,8 @@ __global__ void __launch_bounds__(256) collate_pad_kernel(const __nv_bfloat16* _
                                                            const int* __restrict__ idx, int b, int Lpad, int D,
                                                            __nv_bfloat16* __restrict__ out,
                                                            const int* __restrict__ out_off) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= (long)b * Lpad) return;
   const int i = (int)(row / Lpad), l = (int)(row - (long)i * Lpad);
@@ -776,7 +784,7 @@ int launch_collate_pad(const __nv_bfloat16* packed, const long long* row_offset,
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0,
                   "collate_pad: pointers must be 16-byte aligned");
   const long rows = (long)b * Lpad;
-  collate_pad_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(packed, row_offset, idx, b, Lpad, D, out, out_off);
+  SDUMC_CUDA(launch_kernel(collate_pad_kernel, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, stream, 1, packed, row_offset, idx, b, Lpad, D, out, out_off));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -785,6 +793,8 @@ int launch_collate_pad(const __nv_bfloat16* packed, const long long* row_offset,
 // and those of the MLP layers whose dZ comes straight out of a GEMM epilogue); cols % 8 == 0, cols <= 1024
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ X, long ld, long rows, int cols,
                                                            float* __restrict__ out) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   __shared__ float red[1024];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < cols; i += 256) red[i] = 0.f;
@@ -811,7 +821,7 @@ int launch_colsum_bf16(const __nv_bfloat16* X, long ld, long rows, int cols, flo
                   "colsum_bf16: bad arguments (cols %% 8 == 0, cols <= 1024, ld %% 8 == 0, 16-byte aligned)");
   long blocks = (rows + 63) / 64;
   if (blocks > (long)num_sms() * 8) blocks = (long)num_sms() * 8;
-  colsum_bf16_kernel<<<(unsigned)blocks, 256, 0, stream>>>(X, ld, rows, cols, out);
+  SDUMC_CUDA(launch_kernel(colsum_bf16_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, X, ld, rows, cols, out));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -118,6 +118,10 @@ int current_device() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
   return dev;
 }
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SDUMC_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
 int num_sms() {
   static int sms[kMaxDevices] = {0};
   const int dev = current_device();
@@ -139,24 +143,9 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, const GemmS
     SDUMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done[dev] = true;
   }
-  if constexpr (kPair) {
-    // clusters of two CTAs (one TPC): cta_group::2 MMAs
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid, 1, 1);
-    cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
-    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SDUMC_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, sh, ep));
-  } else {
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, sh, ep);
-  }
+  // pairs: clusters of two CTAs (one TPC) for the cta_group::2 MMAs
+  SDUMC_CUDA(launch_kernel(kern, dim3((unsigned)grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, kPair ? 2 : 1, ta, tb,
+                           sh, ep));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }

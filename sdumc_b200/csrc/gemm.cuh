@@ -212,6 +212,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (descriptor prefetch, barrier init, TMEM allocation) may overlap the tail of the previous
+  // kernel; nothing below touches global memory before the previous grid is complete
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp < 4) reg_dealloc<40>();   // warpgroup 0 (producer, MMA issuer, TMEM allocator, spare) keeps 40 registers
   if (warp == 0) {

@@ -45,6 +45,8 @@ __device__ __forceinline__ float sqdiff_range(const float* a, const float* b, lo
 }
 
 __global__ void __launch_bounds__(256) loss_sums_kernel(LossSumsArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   __shared__ float scratch[8];
   float s[5];
   s[0] = s[1] = 0.f;
@@ -68,13 +70,15 @@ int launch_loss_sums(const LossSumsArgs& a, cudaStream_t stream) {
                   "loss_sums: bad arguments");
   int blocks = (a.B * 896 / 4 + 255) / 256;
   if (blocks > 296) blocks = 296;
-  loss_sums_kernel<<<blocks, 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(loss_sums_kernel, dim3(blocks), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
 
 // grads: d/dv MSE = w * 2 (v - y) / Bg ;  d/dp RMSE = w * (p - t) / (N * rmse), N = Bg * width
 __global__ void __launch_bounds__(256) loss_finish_kernel(LossFinishArgs a) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const float Bg = (float)a.B_global;
   const float mse0 = a.sums[0] / Bg, mse1 = a.sums[1] / Bg;
   const int Gd = a.in.G > 0 ? a.in.G : 256;
@@ -110,13 +114,15 @@ int launch_loss_finish(const LossFinishArgs& a, cudaStream_t stream) {
                   "loss_finish: bad arguments");
   int blocks = (a.in.B * 896 + 255) / 256;
   if (blocks > 592) blocks = 592;
-  loss_finish_kernel<<<blocks, 256, 0, stream>>>(a);
+  SDUMC_CUDA(launch_kernel(loss_finish_kernel, dim3(blocks), dim3(256), 0, stream, 1, a));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
 
 // stand-alone sum of squared differences and its gradient (MSELoss / RMSELoss modules)
 __global__ void __launch_bounds__(256) sqdiff_sum_kernel(const float* a, const float* b, long n, float* out) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   __shared__ float scratch[8];
   float s = 0.f;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
@@ -130,11 +136,13 @@ int launch_sqdiff_sum(const float* a, const float* b, long n, float* out_sum, cu
   SDUMC_CHECK_ARG(a && b && out_sum && n > 0, "sqdiff_sum: bad arguments");
   long blocks = (n + 255) / 256;
   if (blocks > 296) blocks = 296;
-  sqdiff_sum_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, b, n, out_sum);
+  SDUMC_CUDA(launch_kernel(sqdiff_sum_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, a, b, n, out_sum));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
 __global__ void sqdiff_grad_kernel(const float* a, const float* b, long n, const float* coef, float* da, float* db) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const float c = coef[0];
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const float g = c * (a[i] - b[i]);
@@ -147,7 +155,7 @@ int launch_sqdiff_grad(const float* a, const float* b, long n, const float* coef
   SDUMC_CHECK_ARG(a && b && coef && da && n > 0, "sqdiff_grad: bad arguments");
   long blocks = (n + 255) / 256;
   if (blocks > 592) blocks = 592;
-  sqdiff_grad_kernel<<<(unsigned)blocks, 256, 0, stream>>>(a, b, n, coef, da, db);
+  SDUMC_CUDA(launch_kernel(sqdiff_grad_kernel, dim3((unsigned)blocks), dim3(256), 0, stream, 1, a, b, n, coef, da, db));
   SDUMC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -164,6 +172,8 @@ static constexpr int kRncMaxN = 8192;
 // Writes perm (sorted pos -> row), ys (sorted labels), pos (row -> sorted pos).
 __global__ void __launch_bounds__(256) rnc_sort_kernel(const float* __restrict__ labels, int n, int* perm, float* ys,
                                                         int* pos) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   extern __shared__ unsigned char smraw[];
   float* key = reinterpret_cast<float*>(smraw);
   __shared__ int part[8][32];
@@ -205,6 +215,8 @@ __device__ __forceinline__ int rnc_bucket_of(float y, float y0, float inv_delta,
   return f <= 0.f ? 0 : (f >= (float)(nb - 1) ? nb - 1 : (int)f);
 }
 __global__ void __launch_bounds__(256) rnc_bucket_kernel(const float* __restrict__ ys, int n, int* T, float* hdr) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   const float y0 = ys[0], y1 = ys[n - 1];
   const int nb = n;
@@ -255,6 +267,8 @@ __device__ void block_scan(const float* src, double* dst, int n, double* wsum /*
 // would cancel).  64x64 output tile per CTA, 4x4 per thread, feature chunks of 64 through shared memory, so
 // the feature matrix is read n/64 times instead of once per anchor row.
 __global__ void __launch_bounds__(256) rnc_dist_kernel(RncArgs a, float* dist) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   __shared__ float Fi[64][65];
   __shared__ float Fj[64][65];
   const int n = a.n, D = a.D;
@@ -306,6 +320,8 @@ __global__ void __launch_bounds__(256) rnc_dist_kernel(RncArgs a, float* dist) {
 // side; with a degenerate label range the index is disabled and the search covers the whole side.
 __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* perm, const float* ys_g, const int* pos,
                                                        const int* T_g, const float* hdr, float* Cmat) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   extern __shared__ unsigned char smraw[];
   const int n = a.n, D = a.D;
   double* pre = reinterpret_cast<double*>(smraw);
@@ -502,6 +518,8 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
 // n = 8192, a quarter of the data-parallel step's RnC time.)
 template <bool kCol>
 __global__ void __launch_bounds__(256) rnc_grad_kernel(RncArgs a, const float* __restrict__ Cmat) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   constexpr int KC = 32;
   __shared__ __align__(16) float As[KC][68];   // [k][m]  (+4: the transposing store of the row part is 4-way, not 32-way, conflicted)
   __shared__ __align__(16) float Bs[KC][64];   // [k][d]
@@ -595,16 +613,16 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
     attr_done[dev] = true;
   }
   if (!a.reuse_sort) {   // a data-parallel rank calls once per anchor range with the same labels: sort once
-    rnc_sort_kernel<<<(a.n + 31) / 32, 256, (size_t)a.n * 4, stream>>>(a.labels, a.n, perm, ys, pos);
+    SDUMC_CUDA(launch_kernel(rnc_sort_kernel, dim3((a.n + 31) / 32), dim3(256), (size_t)a.n * 4, stream, 1, a.labels, a.n, perm, ys, pos));
     SDUMC_CUDA(cudaGetLastError());
-    rnc_bucket_kernel<<<(a.n + 255) / 256, 256, 0, stream>>>(ys, a.n, T, hdr);
+    SDUMC_CUDA(launch_kernel(rnc_bucket_kernel, dim3((a.n + 255) / 256), dim3(256), 0, stream, 1, ys, a.n, T, hdr));
     SDUMC_CUDA(cudaGetLastError());
   }
-  rnc_dist_kernel<<<dim3((a.n + 63) / 64, (rows + 63) / 64), 256, 0, stream>>>(a, Cmat);
+  SDUMC_CUDA(launch_kernel(rnc_dist_kernel, dim3(dim3((a.n + 63) / 64, (rows + 63) / 64)), dim3(256), 0, stream, 1, a, Cmat));
   SDUMC_CUDA(cudaGetLastError());
   const size_t smem = (size_t)a.n * 28 + 16;
   const int row_threads = a.n >= 4096 ? 1024 : (a.n >= 1024 ? 512 : 256);
-  rnc_row_kernel<<<rows, row_threads, smem, stream>>>(a, perm, ys, pos, T, hdr, Cmat);
+  SDUMC_CUDA(launch_kernel(rnc_row_kernel, dim3(rows), dim3(row_threads), smem, stream, 1, a, perm, ys, pos, T, hdr, Cmat));
   SDUMC_CUDA(cudaGetLastError());
   if (a.dfeats) {
     SDUMC_CHECK_ARG((reinterpret_cast<uintptr_t>(a.dfeats) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.feats) & 15u) == 0,
@@ -615,10 +633,10 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
     // at least 64 reduction steps per CTA
     const int rt = (rows + 63) / 64, ct = (a.n + 63) / 64;
     const int rsplit = std::max(1, std::min(a.n / 64, (5 * sms + rt * dt - 1) / (rt * dt)));
-    rnc_grad_kernel<false><<<dim3(rt, rsplit, dt), 256, 0, stream>>>(a, Cmat);
+    SDUMC_CUDA(launch_kernel(rnc_grad_kernel<false>, dim3(dim3(rt, rsplit, dt)), dim3(256), 0, stream, 1, a, Cmat));
     SDUMC_CUDA(cudaGetLastError());
     const int csplit = std::max(1, std::min(rows / 64, (5 * sms + ct * dt - 1) / (ct * dt)));
-    rnc_grad_kernel<true><<<dim3(ct, csplit, dt), 256, 0, stream>>>(a, Cmat);
+    SDUMC_CUDA(launch_kernel(rnc_grad_kernel<true>, dim3(dim3(ct, csplit, dt)), dim3(256), 0, stream, 1, a, Cmat));
     SDUMC_CUDA(cudaGetLastError());
   }
   return 0;

@@ -139,6 +139,12 @@ class Engine:
         # Measured 5.17 vs 3.99 ms per step (profiles/r2_experiments.md): the non-persistent kernels of a unit only find
         # the SMs its own predecessor frees, so the short (text) pipelines become the long pole.
         self.sm_shares = os.environ.get("SDUMC_SM_SHARES", "0") == "1" and multi_stream
+        # Frame-level work that nothing on the critical path waits for (the Cross_Attention key projections during
+        # utterance chain A, the Cross_Attention weight gradients during the backward chain B7-B9) runs on an auxiliary
+        # stream UNDER the latency-bound utterance chain, on at most `overlap_ctas` SMs so that the chain's small
+        # kernels always find free SMs.  SDUMC_OVERLAP=0 restores the serial schedule.
+        self.overlap = os.environ.get("SDUMC_OVERLAP", "1") == "1" and multi_stream
+        self.overlap_ctas = int(os.environ.get("SDUMC_OVERLAP_CTAS", "96"))
         self.layout = layout
         self.G = layout.G
         self.device = device
@@ -390,6 +396,28 @@ class Engine:
                          qp_stride_b=0, **vl)
         self._parallel(len(units), fra2utt_unit)
 
+        # 3'. the Cross_Attention key projections depend on the in-projections only: issued here on an auxiliary stream,
+        #     they stream under utterance chain A (joined before the pooling kernels of step 4)
+        for (p, m) in units:
+            nr = nrows[_unit_stream(p, m)]
+            if keep:
+                self._new(st, f"Kc.{p}.{m}", (nr, G), torch.bfloat16)
+            else:
+                st.t[f"Kc.{p}.{m}"] = torch.empty(nr, G, dtype=torch.bfloat16, device=dev)
+
+        def cross_keyproj(i, mc):
+            p, m = units[i]
+            pre = f"cross_att_fra2utt_{m}"
+            nr = nrows[_unit_stream(p, m)]
+            # K is materialised (kept for the backward pass when training, a temporary when scoring): the 7 scores
+            # per row come from the pooling kernel's tensor-core product instead of 7 x 256 SIMT FMAs in the GEMM
+            # epilogue - writing and re-reading K costs less than those FMAs
+            ops.gemm(st.t[f"Xc.{p}.{m}"], W.bf16(pre + ".input_proj.weight"), M=nr, N=G, K=G,
+                     bias=W.f32(pre + ".input_proj.bias"), act=ops.ACT_TANH, out_bf16=st.t[f"Kc.{p}.{m}"], max_ctas=mc)
+        early_k = self.overlap and not varlen
+        if early_k:
+            self._side(lambda: [cross_keyproj(i, self.overlap_ctas) for i in range(len(units))])
+
         # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
         cat = self._new(st, "cat", (R, 3 * G))
         cat_b = self._new(st, "cat_bf16", (R, 3 * G), torch.bfloat16)
@@ -434,9 +462,9 @@ class Engine:
             L = cfg.frames[_unit_stream(p, m)]
             nr = nrows[_unit_stream(p, m)]
             self._new(st, f"Sc.{p}.{m}", (nr, NQ))
-            if keep:
-                self._new(st, f"Kc.{p}.{m}", (nr, G), torch.bfloat16)
             self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
+        if early_k:
+            self._join_side()
 
         def cross_unit(i):
             p, m = units[i]
@@ -445,15 +473,11 @@ class Engine:
             S = st.t[f"Sc.{p}.{m}"]
             pre = f"cross_att_fra2utt_{m}"
             qp = Qp[m][p * B * NQ:(p + 1) * B * NQ]
-            # K is materialised (kept for the backward pass when training, a temporary when scoring): the 7 scores
-            # per row come from the pooling kernel's tensor-core product instead of 7 x 256 SIMT FMAs in the GEMM
-            # epilogue - writing and re-reading K costs less than those FMAs
-            nr = nrows[_unit_stream(p, m)]
             vl = dict(row_off=cfg.row_off[_unit_stream(p, m)], Hpad=pad_c[("cross_att_fra2utt", m)][0],
                       Kpad=pad_c[("cross_att_fra2utt", m)][1]) if varlen else {}
-            Kt = st.t[f"Kc.{p}.{m}"] if keep else torch.empty(nr, G, dtype=torch.bfloat16, device=dev)
-            ops.gemm(X, W.bf16(pre + ".input_proj.weight"), M=nr, N=G, K=G, bias=W.f32(pre + ".input_proj.bias"),
-                     act=ops.ACT_TANH, out_bf16=Kt, max_ctas=unit_share.get(i, 0))
+            Kt = st.t[f"Kc.{p}.{m}"]
+            if not early_k:
+                cross_keyproj(i, unit_share.get(i, 0))
             ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=st.t[f"Oc_pre.{p}.{m}"], out=C[m][p * B * NQ:(p + 1) * B * NQ],
                          out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
                          drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step,
@@ -569,13 +593,18 @@ class Engine:
         # the three modalities' blocks run side by side, each on a share of the SMs proportional to its frames
         mod_share = _shares({m: cfg.frames[_unit_stream(0, m)] for m in range(3)}) if self.sm_shares else {}
 
+        deferred = [] if self.overlap else None     # the blocks' weight-gradient GEMMs: nothing reads them before Adam
+
         def cross_attn_bwd(m):                     # passes of one modality accumulate into the same dH: in order
             for p in range(NP):
                 self._attn_block_bwd(W, st, p, m, "cross_att_fra2utt", NQ, dOut=dC[m][p * B * NQ:(p + 1) * B * NQ],
                                      Qp=t[f"Qp.{m}"][p * B * NQ:(p + 1) * B * NQ], qp_stride=NQ * G,
                                      dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH, started=started,
-                                     max_ctas=mod_share.get(m, 0))
+                                     max_ctas=mod_share.get(m, 0), defer_dw=deferred)
         self._parallel(3, cross_attn_bwd)
+        if deferred:
+            # ... so they stream under the latency-bound backward chain B7-B9 (joined before the early gradient bucket)
+            self._side(lambda: [fn(self.overlap_ctas) for fn, _ in deferred], *[k for _, ks in deferred for k in ks])
         # B7. query projections -> dQ
         dQ = z(R * NQ, G)                            # the three blocks add their share side by side (fp32 reds)
         self._parallel(3, lambda m: self._linear_bwd(W, st, f"cross_att_fra2utt_{m}.query_proj", dQp[m],
@@ -636,7 +665,7 @@ class Engine:
         self._join_side()
 
     def _attn_block_bwd(self, W: Weights, st: State, p: int, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
-                        dH: Dict[str, torch.Tensor], started: Dict[str, bool], max_ctas: int = 0):
+                        dH: Dict[str, torch.Tensor], started: Dict[str, bool], max_ctas: int = 0, defer_dw=None):
         cfg = st.cfg
         G = self.G
         t = st.t
@@ -663,5 +692,10 @@ class Engine:
                  out_bf16=dH[s], bf16_mode=ops.OUT_ADD, seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev,
                  max_ctas=max_ctas)
         # dW_in += dZ^T X'
-        ops.gemm(dZ, X, M=G, N=G, K=B * L, a_mn=True, b_mn=True, k_splits=_ksplits(B * L, G, G, max_ctas or NUM_SMS),
-                 out_f32=W.grad(pre + ".input_proj.weight"), f32_mode=ops.OUT_ATOMIC, max_ctas=max_ctas)
+        def dw(mc):
+            ops.gemm(dZ, X, M=G, N=G, K=B * L, a_mn=True, b_mn=True, k_splits=_ksplits(B * L, G, G, mc or NUM_SMS),
+                     out_f32=W.grad(pre + ".input_proj.weight"), f32_mode=ops.OUT_ATOMIC, max_ctas=mc)
+        if defer_dw is not None:
+            defer_dw.append((dw, (dZ, X)))
+        else:
+            dw(max_ctas)

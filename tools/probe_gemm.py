@@ -164,6 +164,34 @@ def run_case(name: str) -> dict:
         res["tflops"] = 2.0 * M * N * K / ms / 1e9
         res["gbs"] = (A.numel() * 2 + B.numel() * 2 + M * N * (2 if ks == 1 else 4)) / ms / 1e6
         res["ok"] = True
+    elif kind == "memref":
+        # memref:<MB>  torch reference rates on the same box: read-only (sum), copy, write-only (fill), L2 flushed
+        mb = int(rest[0])
+        x = torch.randn(mb << 19, device=dev, dtype=torch.bfloat16)
+        y = torch.empty_like(x)
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+        def t(fn):
+            ts = []
+            for _ in range(3):
+                fn()
+            for _ in range(10):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                fn()
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            return sorted(ts)[len(ts) // 2]
+        xi = x.view(torch.int32)
+        res["sum_ms"] = t(lambda: xi.sum())
+        res["sum_gbs"] = (mb << 20) / res["sum_ms"] / 1e6
+        res["copy_ms"] = t(lambda: y.copy_(x))
+        res["copy_gbs"] = 2 * (mb << 20) / res["copy_ms"] / 1e6
+        res["fill_ms"] = t(lambda: y.zero_())
+        res["fill_gbs"] = (mb << 20) / res["fill_ms"] / 1e6
+        res["ok"] = True
     elif kind == "nullchain":
         # 20 dependent trivial kernels (cast of 1 KB) replayed as a CUDA graph: the floor of a dependent launch
         a = torch.zeros(256, device=dev)
