@@ -32,6 +32,8 @@ int set_error(int code, const char* fmt, ...);  // returns code; message via sdu
 constexpr int kMaxDevices = 64;
 int current_device();   // cudaGetDevice(), clamped to [0, kMaxDevices)
 int num_sms();          // SM count of the current device (cached per device)
+// tensor map of a dense bf16 frame tensor [B, L, G] (SWIZZLE_128B boxes of 64 columns x box_rows rows of one sample)
+int get_frame_tmap(const void* ptr, int G, int L, int B, int box_rows, CUtensorMap* out);
 
 // Programmatic dependent launch (PDL).  Kernels of one stream are launched with the programmatic-stream-
 // serialization attribute: the next kernel's CTAs may become resident (and run their prologue: barrier init, TMEM
@@ -223,6 +225,26 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
+}
+// 3-D tiled TMA (frame tensors viewed as [B, L, G]: a box never crosses a sample, rows past L are zero-filled on load
+// and skipped on store)
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"((uint64_t)tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tmap, int c0, int c1, int c2, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((uint64_t)tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// global += shared (element type of the tensor map: bf16), performed at L2 (SASS: UTMAREDG)
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tmap, int c0, int c1, int c2, const void* smem_src) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"((uint64_t)tmap), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
 }
 // 1-D bulk copy global -> shared, completes on an mbarrier (SASS: UBLKCP); 16-byte aligned, size % 16 == 0
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {

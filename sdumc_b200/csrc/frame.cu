@@ -347,16 +347,21 @@ constexpr int kBwdStages = 2;
 constexpr int kBwdThreads = 512;
 
 template <int NQ, int G>
-__global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a) {
-  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
-  pdl_launch_dependents();
+__global__ void __launch_bounds__(kBwdThreads, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmK,
+                const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmH, AttnBwdArgs a) {
   using FC = FrameCfg<G>;
   constexpr int kBwdRows = FC::kRows;      // rows per stage (16 per slab)
-  constexpr int kBwdPitch = FC::kPitch;    // bf16 elements per padded shared-memory row
-  constexpr int kBwdTile = FC::kTile;      // bytes of one padded bf16 [kBwdRows, G] tile
+  constexpr int kBwdPitch = FC::kPitch;    // bf16 elements per padded row of the small dO operand copy
+  constexpr int kBoxes = G / 64;           // 64-column boxes per tile: one per column group of warps
+  constexpr int kBox = kBwdRows * 128;     // bytes of one SWIZZLE_128B box [kBwdRows rows x 64 columns]
+  constexpr int kBwdTile = kBoxes * kBox;  // bytes of one bf16 [kBwdRows, G] tile (32 KB)
   constexpr int kSlabs = FC::kSlabs, kCW = FC::kBwdColWarps;   // row slabs / column groups (64 columns per warp)
-  extern __shared__ __align__(128) unsigned char dyn[];
-  // layout: ring [2 stages][X' tile, K tile] | dO_b [8][264] | dOT [256][8] | QpT [256][8] | dqp_s [8][256] f32 | P_s [L][8] f32
+  static_assert(kCW == kBoxes, "one column group of warps per box");
+  extern __shared__ unsigned char dyn_raw[];
+  // layout: ring [2 stages][X' tile, K tile] (1024-byte aligned: swizzle atoms) | dO_b [8][G+8] | dOT [G][8] | QpT [G][8] |
+  //         dqp_s [8][G] f32 | P_s [L][8] f32
+  unsigned char* dyn = dyn_raw + ((1024u - (smem_u32(dyn_raw) & 1023u)) & 1023u);
   unsigned char* ring = dyn;
   __nv_bfloat16* dO_b = reinterpret_cast<__nv_bfloat16*>(dyn + kBwdStages * 2 * kBwdTile);
   __nv_bfloat16* dOT = dO_b + 8 * kBwdPitch;
@@ -385,29 +390,33 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
   const int u_begin = (int)(((long)n_units * blockIdx.x) / gridDim.x);
   const int my_units = (int)(((long)n_units * (blockIdx.x + 1)) / gridDim.x) - u_begin;
 
-  auto issue_stage = [&](int k) {                     // lane 0 of warp w: rows w*rpw.. of X' and of K of unit k
-    constexpr int rpw = kBwdRows / 16;
+  // Stage k = unit u_begin + k: 2 * kBoxes TMA boxes (X' boxes, then K boxes) of [kBwdRows rows x 64 columns], each
+  // landing 128B-swizzled (conflict-free ldmatrix without padding).  Box i is always issued - and later stored - by
+  // lane 0 of warp i % 16, so the refill of a slot needs no CTA-wide hand-shake beyond the end-of-stage barrier.
+  constexpr int kNB = 2 * kBoxes;
+  auto issue_box = [&](int k, int i) {
     const int u = u_begin + k;
     const int ub = u / n_iter, it = u - ub * n_iter;
     const int slot = k % kBwdStages;
-    const int rows = min(kBwdRows, L - it * kBwdRows);
-    unsigned char* dst = ring + slot * 2 * kBwdTile;
+    unsigned char* dst = ring + slot * 2 * kBwdTile + i * kBox;
+    const int c = i < kBoxes ? i : i - kBoxes;
+    tma_load_3d(dst, i < kBoxes ? &tmX : &tmK, c * 64, it * kBwdRows, ub, &full_bar[slot]);
+  };
+  auto issue_stage = [&](int k) {                     // all warps; lane 0 of warp w issues boxes w, w + 16, ...
     if (lane == 0) {
-      if (warp == 0) mbar_expect_tx(&full_bar[slot], (uint32_t)rows * G * 2 * 2);
-      const int r1 = min(rows, warp * rpw + rpw);
-      for (int r = warp * rpw; r < r1; ++r) {
-        const long src = (((long)ub * L + (long)it * kBwdRows) + r) * G;   // host guarantees dense [B*L,256] tensors
-        bulk_load(dst + r * kBwdPitch * 2, a.X + src, G * 2, &full_bar[slot]);
-        bulk_load(dst + kBwdTile + r * kBwdPitch * 2, a.Kt + src, G * 2, &full_bar[slot]);
-      }
+      if (warp == 0) mbar_expect_tx(&full_bar[k % kBwdStages], 2u * kBwdTile);   // rows past L are zero-filled, bytes count
+      for (int i = warp; i < kNB; i += kBwdThreads / 32) issue_box(k, i);
     }
   };
   if (tid == 0) {
     for (int i = 0; i < kBwdStages; ++i) mbar_init(&full_bar[i], 1);
     fence_mbar_init();
+    tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH);
   }
   for (int i = tid; i < 8 * G; i += kBwdThreads) dqp_s[i] = 0.f;
   __syncthreads();
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
   for (int i = 0; i < kBwdStages && i < my_units; ++i) issue_stage(i);
 
   // per-sample constants: masked dO (bf16, both layouts), Qp^T (bf16), probabilities, delta.
@@ -527,35 +536,26 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       b = ub;
       load_sample(b);
     }
-    __nv_bfloat16* Zb = a.dZ + (long)b * L * G;
-    __nv_bfloat16* Hb = a.dH + (long)b * L * G;
     const int slot = k % kBwdStages;
     mbar_wait(&full_bar[slot], (uint32_t)((k / kBwdStages) & 1));
     unsigned char* st = ring + slot * 2 * kBwdTile;
-    __nv_bfloat16* Xs = reinterpret_cast<__nv_bfloat16*>(st) + rw * 16 * kBwdPitch + hc;            // this warp's 16 rows x 64 columns
-    __nv_bfloat16* Ks = reinterpret_cast<__nv_bfloat16*>(st + kBwdTile) + rw * 16 * kBwdPitch + hc;
+    // this warp's 16 rows x 64 columns: rows rw*16.. of box qc.  Byte address of (row r, 16-byte chunk c) inside a box:
+    // r * 128 + ((c ^ (r & 7)) << 4); every row this lane touches has r & 7 == lane & 7 (ldmatrix) or gid (fragments)
+    unsigned char* Xs = st + qc * kBox + rw * 16 * 128;
+    unsigned char* Ks = st + kBwdTile + qc * kBox + rw * 16 * 128;
     const int l0 = it * kBwdRows + rw * 16;           // first frame of this warp's slab
-    const int valid = min(16, L - l0);                // may be <= 0 for a trailing warp
-    if (valid < 16) {                                 // rows past L: zero so they add nothing to dQp / db
-      for (int i = lane; i < 16 * 8; i += 32) {          // this warp's 16 rows x 64 columns, 8 columns at a time
-        const int r = i / 8, c = (i % 8) * 8;
-        if (r >= valid) {
-          *reinterpret_cast<uint4*>(Xs + r * kBwdPitch + c) = make_uint4(0, 0, 0, 0);
-          *reinterpret_cast<uint4*>(Ks + r * kBwdPitch + c) = make_uint4(0, 0, 0, 0);
-        }
-      }
-      __syncwarp();
-    }
+    const int valid = min(16, L - l0);                // may be <= 0 for a trailing warp (rows past L arrive as zeros)
     if (valid > 0) {
       // (1) dP = X' * dO^T: this warp's 64 columns, then add the partials of the other column groups
       float dP[4] = {0.f, 0.f, 0.f, 0.f};
       {
-        const __nv_bfloat16* arow = Xs + ((lane & 7) + ((lane >> 3) & 1) * 8) * kBwdPitch + (lane >> 4) * 8;
+        const unsigned char* arow = Xs + ((lane & 7) + ((lane >> 3) & 1) * 8) * 128;
+        const int achunk = lane >> 4, sw = lane & 7;
         const __nv_bfloat16* brow = dO_b + gid * kBwdPitch + hc + 2 * tq;
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
           uint32_t af[4];
-          ldsm_x4(af, arow + kk * 16);
+          ldsm_x4(af, arow + (((kk * 2 + achunk) ^ sw) << 4));
           const uint32_t b0 = *reinterpret_cast<const uint32_t*>(brow + kk * 16);
           const uint32_t b1 = *reinterpret_cast<const uint32_t*>(brow + kk * 16 + 8);
           mma_16816(dP, af, b0, b1);
@@ -588,32 +588,38 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
       // (4) dQp^T += K^T * dS  (before the K tile is overwritten by dZ)
       {
         const uint32_t bt0 = movmatrix_trans(dS_lo), bt1 = movmatrix_trans(dS_hi);
-        const __nv_bfloat16* arow = Ks + ((lane & 7) + (lane >> 4) * 8) * kBwdPitch + ((lane >> 3) & 1) * 8;
+        const unsigned char* arow = Ks + ((lane & 7) + (lane >> 4) * 8) * 128;
+        const int achunk = (lane >> 3) & 1, sw = lane & 7;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt) {
           uint32_t af[4];
-          ldsm_x4_trans(af, arow + mt * 16);
+          ldsm_x4_trans(af, arow + (((mt * 2 + achunk) ^ sw) << 4));
           mma_16816(dq_acc[mt], af, bt0, bt1);
         }
       }
       // frame-mask words of this thread's two rows (the 128-column block holding this warp's quarter)
+      // (one Philox call per lane: lane i draws the words of slab row i & 15, the owners of rows gid / gid + 8 fetch
+      // them by shuffle - the four lanes of a row group used to draw the same two rows each)
       U4 ma, mb;
       if (a.fmask_site) {
-        const uint32_t r0 = (uint32_t)((long)b * L + l0 + gid);
-        ma = frame_mask_words(key, a.fmask_site, r0, (uint32_t)(hc >> 7));
-        mb = frame_mask_words(key, a.fmask_site, r0 + 8, (uint32_t)(hc >> 7));
+        const uint32_t r0 = (uint32_t)((long)b * L + l0);
+        const U4 mine = frame_mask_words(key, a.fmask_site, r0 + (uint32_t)(lane & 15), (uint32_t)(hc >> 7));
+        ma.x = __shfl_sync(0xffffffffu, mine.x, gid);     mb.x = __shfl_sync(0xffffffffu, mine.x, gid + 8);
+        ma.y = __shfl_sync(0xffffffffu, mine.y, gid);     mb.y = __shfl_sync(0xffffffffu, mine.y, gid + 8);
+        ma.z = __shfl_sync(0xffffffffu, mine.z, gid);     mb.z = __shfl_sync(0xffffffffu, mine.z, gid + 8);
+        ma.w = __shfl_sync(0xffffffffu, mine.w, gid);     mb.w = __shfl_sync(0xffffffffu, mine.w, gid + 8);
       }
       // (3) dK = dS * Qp, dXv = P * dO, eight columns at a time; dZ and the masked dXv replace K and X' in place
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
-        const int col = nt * 8 + 2 * tq;               // relative to this warp's quarter
+        const int off = gid * 128 + ((nt ^ gid) << 4) + tq * 4;   // columns nt*8 + 2tq, +1 of row gid (row gid + 8: + 1024)
         const uint32_t bq = *reinterpret_cast<const uint32_t*>(QpT + (hc + nt * 8 + gid) * 8 + 2 * tq);
         const uint32_t bo = *reinterpret_cast<const uint32_t*>(dOT + (hc + nt * 8 + gid) * 8 + 2 * tq);
         float dK[4], dX[4];
         mma_1688(dK, dS_lo, dS_hi, bq);
         mma_1688(dX, P_lo, P_hi, bo);
-        uint32_t* k0p = reinterpret_cast<uint32_t*>(Ks + gid * kBwdPitch + col);
-        uint32_t* k1p = reinterpret_cast<uint32_t*>(Ks + (gid + 8) * kBwdPitch + col);
+        uint32_t* k0p = reinterpret_cast<uint32_t*>(Ks + off);
+        uint32_t* k1p = reinterpret_cast<uint32_t*>(Ks + off + 8 * 128);
         const uint32_t kv0 = *k0p, kv1 = *k1p;
         const float k00 = __uint_as_float(kv0 << 16), k01 = __uint_as_float(kv0 & 0xffff0000u);
         const float k10 = __uint_as_float(kv1 << 16), k11 = __uint_as_float(kv1 & 0xffff0000u);
@@ -630,30 +636,39 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
           dX[0] = (wa & 1u) ? 2.f * dX[0] : 0.f; dX[1] = (wa & 2u) ? 2.f * dX[1] : 0.f;
           dX[2] = (wb & 1u) ? 2.f * dX[2] : 0.f; dX[3] = (wb & 2u) ? 2.f * dX[3] : 0.f;
         }
-        *reinterpret_cast<uint32_t*>(Xs + gid * kBwdPitch + col) = pack2(dX[0], dX[1]);
-        *reinterpret_cast<uint32_t*>(Xs + (gid + 8) * kBwdPitch + col) = pack2(dX[2], dX[3]);
+        *reinterpret_cast<uint32_t*>(Xs + off) = pack2(dX[0], dX[1]);
+        *reinterpret_cast<uint32_t*>(Xs + off + 8 * 128) = pack2(dX[2], dX[3]);
       }
-      // tiles -> global: the slab's 16 finished rows leave as full rows, 16 / kCW per warp
-      fence_proxy_async();
-      asm volatile("bar.sync %0, %1;" ::"r"(1 + rw), "n"(kCW * 32) : "memory");
-      if (lane == 0) {
-        constexpr int spw = 16 / kCW;                  // rows stored per warp
-        const __nv_bfloat16* Kr = Ks - hc;             // row starts of this slab
-        const __nv_bfloat16* Xr = Xs - hc;
-        const int r1 = min(valid, qc * spw + spw);
-        for (int r = qc * spw; r < r1; ++r) {
-          const long dst = (long)(l0 + r) * G;
-          bulk_store(Zb + dst, Kr + r * kBwdPitch, G * 2);
-          if (rmw) bulk_reduce_add_bf16(Hb + dst, Xr + r * kBwdPitch, G * 2);
-          else     bulk_store(Hb + dst, Xr + r * kBwdPitch, G * 2);
-        }
-      }
-      bulk_commit();
-      bulk_wait_read();
     }
-    // every warp's stores have read this slot: refill it with the unit two ahead
+    // tiles -> global: when every warp is done with the stage, box i leaves through ONE tensor store issued by the
+    // lane that loaded it (dZ boxes: store; dH boxes: store, or reduce-add at L2 in accumulate mode; rows past L are
+    // clipped by the tensor map); once that store has read shared memory the same lane refills the box with the unit
+    // two ahead - the other warps are already waiting for the next stage
+    fence_proxy_async();
     __syncthreads();
-    if (k + kBwdStages < my_units) issue_stage(k + kBwdStages);
+    if (lane == 0) {
+      bool any = false;
+      for (int i = warp; i < kNB; i += kBwdThreads / 32) {
+        const unsigned char* src = st + i * kBox;
+        if (i < kBoxes) {
+          if (rmw) tma_reduce_add_3d(&tmH, i * 64, it * kBwdRows, ub, src);
+          else     tma_store_3d(&tmH, i * 64, it * kBwdRows, ub, src);
+        } else {
+          tma_store_3d(&tmZ, (i - kBoxes) * 64, it * kBwdRows, ub, src);
+        }
+        any = true;
+      }
+      if (any) {
+        bulk_commit();
+        if (k + kBwdStages < my_units) {
+          bulk_wait_read();
+          if (warp == 0) mbar_expect_tx(&full_bar[slot], 2u * kBwdTile);
+          for (int i = warp; i < kNB; i += kBwdThreads / 32) issue_box(k + kBwdStages, i);
+        }
+      } else if (warp == 0 && k + kBwdStages < my_units) {
+        mbar_expect_tx(&full_bar[slot], 2u * kBwdTile);
+      }
+    }
   }
   if (b >= 0) flush_dqp(b);
   // db: reduce over the 8 row groups of the warp, then over the warps through shared memory
@@ -684,9 +699,9 @@ __global__ void __launch_bounds__(kBwdThreads, 1) attn_bwd_kernel(AttnBwdArgs a)
 }
 
 static size_t attn_bwd_smem(int L, int G) {
-  const size_t tile = G == 256 ? FrameCfg<256>::kTile : FrameCfg<1024>::kTile;
-  return (size_t)kBwdStages * 2 * tile + (size_t)8 * (G + 8) * 2 + (size_t)2 * G * 8 * 2 + (size_t)8 * G * 4 +
-         (size_t)L * 8 * 4;
+  const size_t tile = 64 * 256 * 2;   // bf16 [rows per stage, G] = 32 KB for both widths (unpadded: swizzled boxes)
+  return 1024 /* alignment of the swizzle atoms */ + (size_t)kBwdStages * 2 * tile + (size_t)8 * (G + 8) * 2 +
+         (size_t)2 * G * 8 * 2 + (size_t)8 * G * 4 + (size_t)L * 8 * 4;
 }
 
 int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
@@ -696,7 +711,7 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   const int G = a.G > 0 ? a.G : 256;
   SDUMC_CHECK_ARG(G == 256 || G == 1024, "attn_bwd: general_dim %d unsupported (256 or 1024)", G);
   SDUMC_CHECK_ARG(a.ldx == G && a.ldk == G && a.lddz == G && a.lddh == G,
-                  "attn_bwd: frame tensors must be dense [B*L,G] (bulk-copy staging)");
+                  "attn_bwd: frame tensors must be dense [B*L,G] (tensor-map staging)");
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.X) | reinterpret_cast<uintptr_t>(a.Kt) | reinterpret_cast<uintptr_t>(a.dH) |
                     reinterpret_cast<uintptr_t>(a.dZ)) & 15u) == 0, "attn_bwd: frame tensors must be 16-byte aligned");
   SDUMC_CHECK_ARG(((reinterpret_cast<uintptr_t>(a.dOut) | reinterpret_cast<uintptr_t>(a.Qp) | reinterpret_cast<uintptr_t>(a.O_pre)) & 15u) == 0 &&
@@ -716,14 +731,19 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   }
   const int rows_per_stage = G == 256 ? FrameCfg<256>::kRows : FrameCfg<1024>::kRows;
   const long n_units = (long)a.B * ((a.L + rows_per_stage - 1) / rows_per_stage);
+  CUtensorMap tx, tk, tz, th;     // [B, L, G] views: boxes of 64 columns x one stage of rows of one sample
+  SDUMC_TRY(get_frame_tmap(a.X, G, a.L, a.B, rows_per_stage, &tx));
+  SDUMC_TRY(get_frame_tmap(a.Kt, G, a.L, a.B, rows_per_stage, &tk));
+  SDUMC_TRY(get_frame_tmap(a.dZ, G, a.L, a.B, rows_per_stage, &tz));
+  SDUMC_TRY(get_frame_tmap(a.dH, G, a.L, a.B, rows_per_stage, &th));
   int grid = (int)std::min<long>(n_units, num_sms());   // one resident CTA per SM (shared-memory bound)
   if (a.max_ctas > 0) grid = std::min(grid, a.max_ctas);
   if (G == 256) {
-    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 256>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, a));
-    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 256>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, a));
+    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 256>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tx, tk, tz, th, a));
+    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 256>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tx, tk, tz, th, a));
   } else {
-    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 1024>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, a));
-    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 1024>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, a));
+    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 1024>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tx, tk, tz, th, a));
+    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 1024>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tx, tk, tz, th, a));
   }
   SDUMC_CUDA(cudaGetLastError());
   return 0;

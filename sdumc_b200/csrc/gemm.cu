@@ -106,6 +106,40 @@ static int get_tmap(const void* ptr, long ld, long inner, long outer, int box_in
   return 0;
 }
 
+int get_frame_tmap(const void* ptr, int G, int L, int B, int box_rows, CUtensorMap* out) {
+  SDUMC_CHECK_ARG(ptr != nullptr && (reinterpret_cast<uintptr_t>(ptr) & 15u) == 0, "frame tensor %p not 16-byte aligned", ptr);
+  SDUMC_CHECK_ARG(G % 64 == 0 && L > 0 && B > 0 && box_rows > 0 && box_rows <= 256, "frame tensor map: bad shape");
+  TmapKey key{ptr, -(long)B, G, L, 64, box_rows, 2};     // ld < 0 marks the 3-D maps in the shared cache
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    auto it = g_tmaps.find(key);
+    if (it != g_tmaps.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return set_error(SDUMC_ERR_CUDA, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  cuuint64_t gdim[3] = {(cuuint64_t)G, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t gstr[2] = {(cuuint64_t)G * 2, (cuuint64_t)L * G * 2};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap tm;
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(SDUMC_ERR_CUDA, "cuTensorMapEncodeTiled (frames) failed (%d) G=%d L=%d B=%d box_rows=%d", (int)r, G, L,
+                     B, box_rows);
+  {
+    std::lock_guard<std::mutex> g(g_tmap_mu);
+    if (g_tmaps.size() > 4096) g_tmaps.clear();
+    g_tmaps.emplace(key, tm);
+  }
+  *out = tm;
+  return 0;
+}
+
 void clear_tmap_cache() {
   std::lock_guard<std::mutex> g(g_tmap_mu);
   g_tmaps.clear();
