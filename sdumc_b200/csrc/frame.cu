@@ -347,7 +347,7 @@ constexpr int kBwdStages = 2;
 constexpr int kBwdThreads = 512;
 
 template <int NQ, int G>
-__global__ void __launch_bounds__(kBwdThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads + 32, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmZ, const __grid_constant__ CUtensorMap tmH, AttnBwdArgs a) {
   using FC = FrameCfg<G>;
@@ -369,7 +369,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   float* dqp_s = reinterpret_cast<float*>(QpT + G * 8);
   float* P_s = dqp_s + 8 * G;
   __shared__ float delta_s[8];
-  __shared__ __align__(8) uint64_t full_bar[kBwdStages];
+  __shared__ __align__(8) uint64_t full_bar[kBwdStages];   // TMA -> compute warps: the stage has landed
+  __shared__ __align__(8) uint64_t done_bar[kBwdStages];   // compute warps (16 arrivals) -> DMA warp: the stage may leave
+  auto compute_sync = [] { asm volatile("bar.sync 9, %0;" ::"n"(kBwdThreads) : "memory"); };   // the 16 compute warps
   const int tid = threadIdx.x, lane = tid & 31;
   // the broadcast makes the warp index provably warp-uniform, so bulk-copy addresses derived from it live in
   // uniform registers (no per-lane serialisation loop around UBLKCP)
@@ -377,7 +379,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int gid = lane >> 2, tq = lane & 3;           // fragment coordinates: row group / column pair
   const int rw = warp % kSlabs, qc = warp / kSlabs;     // row slab of the stage / column group
   const int hc = qc * 64;                              // first column of this warp's 64-column group
-  __shared__ float4 dp_x[kBwdThreads];                // partial dP exchange inside a warp quartet
+  __shared__ float4 dp_xx[2][kBwdThreads];            // partial dP exchange inside a slab, double-buffered by stage parity:
+                                                      // the warps of a slab are only loosely coupled (one barrier per stage)
   const int L = a.L;
   const int n_iter = (L + kBwdRows - 1) / kBwdRows;
   const bool rmw = a.dh_mode == 1;
@@ -391,8 +394,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int my_units = (int)(((long)n_units * (blockIdx.x + 1)) / gridDim.x) - u_begin;
 
   // Stage k = unit u_begin + k: 2 * kBoxes TMA boxes (X' boxes, then K boxes) of [kBwdRows rows x 64 columns], each
-  // landing 128B-swizzled (conflict-free ldmatrix without padding).  Box i is always issued - and later stored - by
-  // lane 0 of warp i % 16, so the refill of a slot needs no CTA-wide hand-shake beyond the end-of-stage barrier.
+  // landing 128B-swizzled (conflict-free ldmatrix without padding).
   constexpr int kNB = 2 * kBoxes;
   auto issue_box = [&](int k, int i) {
     const int u = u_begin + k;
@@ -402,22 +404,55 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int c = i < kBoxes ? i : i - kBoxes;
     tma_load_3d(dst, i < kBoxes ? &tmX : &tmK, c * 64, it * kBwdRows, ub, &full_bar[slot]);
   };
-  auto issue_stage = [&](int k) {                     // all warps; lane 0 of warp w issues boxes w, w + 16, ...
-    if (lane == 0) {
-      if (warp == 0) mbar_expect_tx(&full_bar[k % kBwdStages], 2u * kBwdTile);   // rows past L are zero-filled, bytes count
-      for (int i = warp; i < kNB; i += kBwdThreads / 32) issue_box(k, i);
-    }
+  auto issue_stage = [&](int k) {                     // one thread (the DMA warp's lane 0)
+    mbar_expect_tx(&full_bar[k % kBwdStages], 2u * kBwdTile);   // rows past L are zero-filled, their bytes count
+#pragma unroll 1
+    for (int i = 0; i < kNB; ++i) issue_box(k, i);
   };
   if (tid == 0) {
-    for (int i = 0; i < kBwdStages; ++i) mbar_init(&full_bar[i], 1);
+    for (int i = 0; i < kBwdStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&done_bar[i], kBwdThreads / 32); }
     fence_mbar_init();
     tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmZ); tma_prefetch_desc(&tmH);
   }
-  for (int i = tid; i < 8 * G; i += kBwdThreads) dqp_s[i] = 0.f;
+  if (tid < kBwdThreads) for (int i = tid; i < 8 * G; i += kBwdThreads) dqp_s[i] = 0.f;
   __syncthreads();
   pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
   pdl_launch_dependents();
-  for (int i = 0; i < kBwdStages && i < my_units; ++i) issue_stage(i);
+
+  if (warp == kBwdThreads / 32) {
+    // ===================== DMA warp: every tensor copy of the CTA =====================
+    // loads of unit k into slot k % 2 (2 * kBoxes boxes, one expect_tx); when all 16 compute warps have released the
+    // slot (done_bar), its boxes leave through tensor stores (dZ: store; dH: store, or reduce-add at L2 in accumulate
+    // mode; rows past L are clipped by the tensor map) and, once those have read shared memory, the slot is refilled
+    // with the unit two ahead.  The compute warps never wait for a store.
+    if (lane == 0) {
+      for (int i = 0; i < kBwdStages && i < my_units; ++i) issue_stage(i);
+      for (int k = 0; k < my_units; ++k) {
+        const int u = u_begin + k;
+        const int ub = u / n_iter, it = u - ub * n_iter;
+        const int slot = k % kBwdStages;
+        mbar_wait(&done_bar[slot], (uint32_t)((k / kBwdStages) & 1));
+        const unsigned char* st = ring + slot * 2 * kBwdTile;
+#pragma unroll 1
+        for (int i = 0; i < kNB; ++i) {
+          const unsigned char* src = st + i * kBox;
+          if (i < kBoxes) {
+            if (rmw) tma_reduce_add_3d(&tmH, i * 64, it * kBwdRows, ub, src);
+            else     tma_store_3d(&tmH, i * 64, it * kBwdRows, ub, src);
+          } else {
+            tma_store_3d(&tmZ, (i - kBoxes) * 64, it * kBwdRows, ub, src);
+          }
+        }
+        bulk_commit();
+        if (k + kBwdStages < my_units) {
+          bulk_wait_read();
+          issue_stage(k + kBwdStages);
+        }
+      }
+      bulk_wait_all();
+    }
+    return;
+  }
 
   // per-sample constants: masked dO (bf16, both layouts), Qp^T (bf16), probabilities, delta.
   // All global loads of a batch are issued before the first use: with one CTA per SM this prologue is pure
@@ -488,7 +523,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     QpT[g * 8 + q] = __float2bfloat16(0.f);
   }
   if (tid < 8) delta_s[tid] = 0.f;
-  __syncthreads();
+  compute_sync();
   // a float4 group lies inside one query row (64 groups per query): warp-reduce, then one atomic per warp and query
 #pragma unroll
   for (int j = 0; j < kPer; ++j) {
@@ -496,7 +531,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const float s = warp_sum(dpart[j]);
     if (lane == 0 && i < kV4) atomicAdd(&delta_s[(i * 4) / G], s);
   }
-  __syncthreads();
+  compute_sync();
   dl0 = delta_s[2 * tq];
   dl1 = delta_s[2 * tq + 1];
   };
@@ -518,20 +553,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       if (q + 1 < NQ) { atomicAdd(&dqp_s[(q + 1) * G + c], dq_acc[mt][1]); atomicAdd(&dqp_s[(q + 1) * G + c + 8], dq_acc[mt][3]); }
       dq_acc[mt][0] = dq_acc[mt][1] = dq_acc[mt][2] = dq_acc[mt][3] = 0.f;
     }
-    __syncthreads();
+    compute_sync();
     float* dst = a.dQp + (a.qp_stride_b == 0 ? 0 : (long)b * a.dqp_stride_b);
     for (int i = tid; i < NQ * G; i += kBwdThreads) {
       atomicAdd(dst + i, dqp_s[i]);
       dqp_s[i] = 0.f;
     }
-    __syncthreads();
+    compute_sync();
   };
 
   int b = -1;
   for (int k = 0; k < my_units; ++k) {
     const int u = u_begin + k;
     const int ub = u / n_iter, it = u - ub * n_iter;
-    if (ub != b) {                                    // CTA-uniform; the previous unit ended with a __syncthreads
+    if (ub != b) {                                    // uniform over the compute warps; flush_dqp's barriers separate the samples
       if (b >= 0) flush_dqp(b);
       b = ub;
       load_sample(b);
@@ -549,6 +584,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // (1) dP = X' * dO^T: this warp's 64 columns, then add the partials of the other column groups
       float dP[4] = {0.f, 0.f, 0.f, 0.f};
       {
+        float4* dp_x = dp_xx[k & 1];
         const unsigned char* arow = Xs + ((lane & 7) + ((lane >> 3) & 1) * 8) * 128;
         const int achunk = lane >> 4, sw = lane & 7;
         const __nv_bfloat16* brow = dO_b + gid * kBwdPitch + hc + 2 * tq;
@@ -640,35 +676,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         *reinterpret_cast<uint32_t*>(Xs + off + 8 * 128) = pack2(dX[2], dX[3]);
       }
     }
-    // tiles -> global: when every warp is done with the stage, box i leaves through ONE tensor store issued by the
-    // lane that loaded it (dZ boxes: store; dH boxes: store, or reduce-add at L2 in accumulate mode; rows past L are
-    // clipped by the tensor map); once that store has read shared memory the same lane refills the box with the unit
-    // two ahead - the other warps are already waiting for the next stage
+    // the warp's part of the stage is final in shared memory: release the slot to the DMA warp and go on
     fence_proxy_async();
-    __syncthreads();
-    if (lane == 0) {
-      bool any = false;
-      for (int i = warp; i < kNB; i += kBwdThreads / 32) {
-        const unsigned char* src = st + i * kBox;
-        if (i < kBoxes) {
-          if (rmw) tma_reduce_add_3d(&tmH, i * 64, it * kBwdRows, ub, src);
-          else     tma_store_3d(&tmH, i * 64, it * kBwdRows, ub, src);
-        } else {
-          tma_store_3d(&tmZ, (i - kBoxes) * 64, it * kBwdRows, ub, src);
-        }
-        any = true;
-      }
-      if (any) {
-        bulk_commit();
-        if (k + kBwdStages < my_units) {
-          bulk_wait_read();
-          if (warp == 0) mbar_expect_tx(&full_bar[slot], 2u * kBwdTile);
-          for (int i = warp; i < kNB; i += kBwdThreads / 32) issue_box(k + kBwdStages, i);
-        }
-      } else if (warp == 0 && k + kBwdStages < my_units) {
-        mbar_expect_tx(&full_bar[slot], 2u * kBwdTile);
-      }
-    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&done_bar[slot]);
   }
   if (b >= 0) flush_dqp(b);
   // db: reduce over the 8 row groups of the warp, then over the warps through shared memory
@@ -685,7 +696,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   }
   float* db_s = dqp_s;                                // the dQp staging buffer is idle now (flushed and re-zeroed)
   for (int i = tid; i < G; i += kBwdThreads) db_s[i] = 0.f;
-  __syncthreads();
+  compute_sync();
   if (gid == 0) {
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
@@ -693,9 +704,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       atomicAdd(&db_s[hc + nt * 8 + 2 * tq + 1], db_acc[nt][1]);
     }
   }
-  __syncthreads();
+  compute_sync();
   for (int i = tid; i < G; i += kBwdThreads) atomicAdd(a.db + i, db_s[i]);
-  bulk_wait_all();
 }
 
 static size_t attn_bwd_smem(int L, int G) {
@@ -718,7 +728,7 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
                   a.dout_stride_b % 4 == 0 && a.qp_stride_b % 4 == 0,
                   "attn_bwd: dOut / Qp / O_pre must be 16-byte aligned with strides that are multiples of 4");
   const size_t smem = attn_bwd_smem(a.L, G);
-  constexpr size_t kMaxDyn = 218 * 1024;   // + 8.3 KB static (dP exchange, barriers) stays under the 227 KB per-CTA limit
+  constexpr size_t kMaxDyn = 210 * 1024;   // + 16.5 KB static (dP exchange x2, barriers) stays under the 227 KB per-CTA limit
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
   static bool attr_done[kMaxDevices] = {false};
   const int dev = current_device();
@@ -739,11 +749,11 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
   int grid = (int)std::min<long>(n_units, num_sms());   // one resident CTA per SM (shared-memory bound)
   if (a.max_ctas > 0) grid = std::min(grid, a.max_ctas);
   if (G == 256) {
-    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 256>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tx, tk, tz, th, a));
-    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 256>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tx, tk, tz, th, a));
+    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 256>, dim3(grid), dim3(kBwdThreads + 32), smem, stream, 1, tx, tk, tz, th, a));
+    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 256>, dim3(grid), dim3(kBwdThreads + 32), smem, stream, 1, tx, tk, tz, th, a));
   } else {
-    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 1024>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tx, tk, tz, th, a));
-    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 1024>, dim3(grid), dim3(kBwdThreads), smem, stream, 1, tx, tk, tz, th, a));
+    if (a.nq == 1) SDUMC_CUDA(launch_kernel(attn_bwd_kernel<1, 1024>, dim3(grid), dim3(kBwdThreads + 32), smem, stream, 1, tx, tk, tz, th, a));
+    else           SDUMC_CUDA(launch_kernel(attn_bwd_kernel<7, 1024>, dim3(grid), dim3(kBwdThreads + 32), smem, stream, 1, tx, tk, tz, th, a));
   }
   SDUMC_CUDA(cudaGetLastError());
   return 0;

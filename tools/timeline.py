@@ -43,10 +43,10 @@ def main():
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA and e.time_range.end > e.time_range.start]
     ks = sorted(({"name": short(e.name), "t0": e.time_range.start, "t1": e.time_range.end,
                   "stream": getattr(e, "stream", -1) if hasattr(e, "stream") else -1} for e in evs), key=lambda k: k["t0"])
-    # split into replays at the largest gaps
-    gaps = sorted(((ks[i + 1]["t0"] - max(k["t1"] for k in ks[: i + 1]), i) for i in range(len(ks) - 1)), reverse=True)[:2]
-    cuts = sorted(i for _, i in gaps)
-    step = ks[cuts[0] + 1: cuts[1] + 1]
+    # three identical replays were recorded (graph launches are serialised): the middle third is one step
+    assert len(ks) % 3 == 0, f"{len(ks)} kernels recorded for 3 replays"
+    n = len(ks) // 3
+    step = ks[n:2 * n]
     t0 = step[0]["t0"]
     for k in step:
         k["t0"] -= t0
