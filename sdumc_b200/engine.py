@@ -144,6 +144,10 @@ class Engine:
         # stream UNDER the latency-bound utterance chain, on at most `overlap_ctas` SMs so that the chain's small
         # kernels always find free SMs.  SDUMC_OVERLAP=0 restores the serial schedule.
         self.overlap = os.environ.get("SDUMC_OVERLAP", "1") == "1" and multi_stream
+        # the forward half (key projections under chain A) measured slower than the serial schedule (335 vs 311 us: the
+        # chain's kernels are memory-latency-bound and stretch 3x next to a streaming GEMM), the backward half faster
+        # (363 vs 471 us): profiles/r2_experiments.md
+        self.overlap_fwd = os.environ.get("SDUMC_OVERLAP_FWD", "0") == "1" and self.overlap
         self.overlap_ctas = int(os.environ.get("SDUMC_OVERLAP_CTAS", "96"))
         self.layout = layout
         self.G = layout.G
@@ -414,7 +418,7 @@ class Engine:
             # epilogue - writing and re-reading K costs less than those FMAs
             ops.gemm(st.t[f"Xc.{p}.{m}"], W.bf16(pre + ".input_proj.weight"), M=nr, N=G, K=G,
                      bias=W.f32(pre + ".input_proj.bias"), act=ops.ACT_TANH, out_bf16=st.t[f"Kc.{p}.{m}"], max_ctas=mc)
-        early_k = self.overlap and not varlen
+        early_k = self.overlap_fwd and not varlen
         if early_k:
             self._side(lambda: [cross_keyproj(i, self.overlap_ctas) for i in range(len(units))])
 
@@ -658,9 +662,10 @@ class Engine:
             X = t[f"X.{s}"]
             rows, D = X.shape
             mc = dw_share.get(i, 0)
+            # (the short column-sum kernel first: behind the persistent GEMMs it would run alone at the end of the step)
+            ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
             ops.gemm(dHs, X, M=G, N=D, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, G, D, mc or NUM_SMS),
                      out_f32=W.grad(wname + ".weight"), f32_mode=ops.OUT_ATOMIC, max_ctas=mc)
-            ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
         self._parallel(len(items), inproj_bwd)
         self._join_side()
 
