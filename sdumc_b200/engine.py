@@ -662,10 +662,9 @@ class Engine:
             X = t[f"X.{s}"]
             rows, D = X.shape
             mc = dw_share.get(i, 0)
-            # (the short column-sum kernel first: behind the persistent GEMMs it would run alone at the end of the step)
-            ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
             ops.gemm(dHs, X, M=G, N=D, K=rows, a_mn=True, b_mn=True, k_splits=_ksplits(rows, G, D, mc or NUM_SMS),
                      out_f32=W.grad(wname + ".weight"), f32_mode=ops.OUT_ATOMIC, max_ctas=mc)
+            ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
         self._parallel(len(items), inproj_bwd)
         self._join_side()
 
