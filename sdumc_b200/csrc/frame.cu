@@ -379,8 +379,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int gid = lane >> 2, tq = lane & 3;           // fragment coordinates: row group / column pair
   const int rw = warp % kSlabs, qc = warp / kSlabs;     // row slab of the stage / column group
   const int hc = qc * 64;                              // first column of this warp's 64-column group
-  __shared__ float4 dp_xx[2][kBwdThreads];            // partial dP exchange inside a slab, double-buffered by stage parity:
-                                                      // the warps of a slab are only loosely coupled (one barrier per stage)
+  // partial dP exchange inside a slab.  The warps of a slab are only loosely coupled (one barrier per stage), so the
+  // buffer is double-buffered by stage parity; at G = 1024 (32 KB more of per-sample operands) there is no room for
+  // the second copy and a second slab barrier after the reads takes its place
+  constexpr int kDpBufs = G == 256 ? 2 : 1;
+  __shared__ float4 dp_xx[kDpBufs][kBwdThreads];
   const int L = a.L;
   const int n_iter = (L + kBwdRows - 1) / kBwdRows;
   const bool rmw = a.dh_mode == 1;
@@ -584,7 +587,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // (1) dP = X' * dO^T: this warp's 64 columns, then add the partials of the other column groups
       float dP[4] = {0.f, 0.f, 0.f, 0.f};
       {
-        float4* dp_x = dp_xx[k & 1];
+        float4* dp_x = dp_xx[kDpBufs == 2 ? (k & 1) : 0];
         const unsigned char* arow = Xs + ((lane & 7) + ((lane >> 3) & 1) * 8) * 128;
         const int achunk = lane >> 4, sw = lane & 7;
         const __nv_bfloat16* brow = dO_b + gid * kBwdPitch + hc + 2 * tq;
@@ -613,6 +616,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           }
           dP[0] = o.x; dP[1] = o.y; dP[2] = o.z; dP[3] = o.w;
         }
+        if constexpr (kDpBufs == 1) asm volatile("bar.sync %0, %1;" ::"r"(1 + rw), "n"(kCW * 32) : "memory");
       }
       // (2) dS = alpha * P * (dP - delta) on the accumulator layout: rows gid / gid+8, queries 2tq / 2tq+1
       const bool v0 = gid < valid, v1 = gid + 8 < valid;
@@ -728,15 +732,16 @@ int launch_attn_bwd(const AttnBwdArgs& a, cudaStream_t stream) {
                   a.dout_stride_b % 4 == 0 && a.qp_stride_b % 4 == 0,
                   "attn_bwd: dOut / Qp / O_pre must be 16-byte aligned with strides that are multiples of 4");
   const size_t smem = attn_bwd_smem(a.L, G);
-  constexpr size_t kMaxDyn = 210 * 1024;   // + 16.5 KB static (dP exchange x2, barriers) stays under the 227 KB per-CTA limit
+  // + 16.5 KB (G = 256: dP exchange x2, barriers) / 8.3 KB static stays under the 227 KB per-CTA limit
+  const size_t kMaxDyn = (G == 256 ? 210 : 218) * 1024;
   SDUMC_CHECK_ARG(smem <= kMaxDyn, "attn_bwd: L=%d too long for the shared-memory probability cache", a.L);
   static bool attr_done[kMaxDevices] = {false};
   const int dev = current_device();
   if (!attr_done[dev]) {
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
-    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<1, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024));
+    SDUMC_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<7, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 218 * 1024));
     attr_done[dev] = true;
   }
   const int rows_per_stage = G == 256 ? FrameCfg<256>::kRows : FrameCfg<1024>::kRows;

@@ -295,6 +295,9 @@ class Engine:
         #    side, each on a share of the SMs proportional to its FLOPs (outputs are allocated before the fork)
         plan = []
         varlen = cfg.row_off is not None
+        # modality m can run its passes as one GEMM when the passes' streams have the same shape (audio / video: the same
+        # stream; text: the text and the text-substitute streams, equal in the fixed-length configurations)
+        mrg = {m: drop and not varlen and len({cfg.frames[_unit_stream(p, m)] for p in range(NP)}) == 1 for m in range(3)}
         if varlen:
             assert not drop and not keep, "the varlen layout is defined for eval mode (no dropout, no backward)"
         nrows: Dict[str, int] = {}
@@ -318,10 +321,19 @@ class Engine:
             mod = _stream_mod(s)
             users = [(p, m) for (p, m) in units if _unit_stream(p, m) == s]
             if drop:
+                # the dropped copies of one (block, modality) are contiguous over the passes ([NP, B*L, G]): the passes
+                # share the block's weights, so its key projection and its weight gradient run as ONE GEMM over both
                 tg, sites = [], []
                 for (p, m) in users:
                     for blk in ("fra2utt", "cross_att_fra2utt"):
-                        tg.append(self._new(st, f"X{blk[0]}.{p}.{m}", (B * L, G), torch.bfloat16))
+                        if mrg[m]:
+                            key_ = f"X{blk[0]}.all.{m}"
+                            if key_ not in st.t:
+                                self._new(st, key_, (NP, B * L, G), torch.bfloat16)
+                            st.t[f"X{blk[0]}.{p}.{m}"] = st.t[key_][p]
+                        else:
+                            self._new(st, f"X{blk[0]}.{p}.{m}", (B * L, G), torch.bfloat16)
+                        tg.append(st.t[f"X{blk[0]}.{p}.{m}"])
                         sites.append(site_id(f"{blk}_{m}.in", p))
                 plan.append((s, xb, L, D, INPROJ[mod], tg, sites, None))
             else:
@@ -358,15 +370,40 @@ class Engine:
         # 2. FRA2UTT_new per unit: key projection + scores (GEMM epilogue), softmax + pooling
         u_pool = [self._new(st, f"u.{m}", (R, G)) for m in range(3)]
         u_pool_b = [self._new(st, f"u_bf16.{m}", (R, G), torch.bfloat16) for m in range(3)]
-        for (p, m) in units:
-            L = cfg.frames[_unit_stream(p, m)]
-            nr = nrows[_unit_stream(p, m)]
-            self._new(st, f"Sf.{p}.{m}", (nr, 1))
-            if keep:
-                self._new(st, f"Kf.{p}.{m}", (nr, G), torch.bfloat16)
-            self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
+        for m in range(3):
+            merged = mrg[m]                         # pass-contiguous X' exist: one key-projection GEMM per modality
+            nr = nrows[_unit_stream(0, m)]
+            if merged:
+                Sall = self._new(st, f"Sf.all.{m}", (NP, nr, 1))
+                Kall = self._new(st, f"Kf.all.{m}", (NP, nr, G), torch.bfloat16) if keep else None
+            for p in range(NP):
+                nr_p = nrows[_unit_stream(p, m)]
+                if merged:
+                    st.t[f"Sf.{p}.{m}"] = Sall[p]
+                    if keep:
+                        st.t[f"Kf.{p}.{m}"] = Kall[p]
+                else:
+                    self._new(st, f"Sf.{p}.{m}", (nr_p, 1))
+                    if keep:
+                        self._new(st, f"Kf.{p}.{m}", (nr_p, G), torch.bfloat16)
+                self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
 
         unit_share = _shares({i: cfg.frames[_unit_stream(p, m)] for i, (p, m) in enumerate(units)}) if self.sm_shares else {}
+
+        def fra2utt_mod(m):                         # merged: ONE key projection (+ scores) over both passes, then the pools
+            pre = f"fra2utt_{m}"
+            L = cfg.frames[_unit_stream(0, m)]
+            nr = nrows[_unit_stream(0, m)]
+            Kall = st.t[f"Kf.all.{m}"].view(NP * nr, G) if keep else None
+            ops.gemm(st.t[f"Xf.all.{m}"].view(NP * nr, G), W.bf16(pre + ".input_proj.weight"), M=NP * nr, N=G, K=G,
+                     bias=W.f32(pre + ".input_proj.bias"), act=ops.ACT_TANH, epi_kind=ops.EPI_KEYPROJ, out_bf16=Kall,
+                     qv=W.f32(pre + ".attention_context_vector"), q_stride=0, nq=1, L=L,
+                     scores=st.t[f"Sf.all.{m}"].view(NP * nr, 1))
+            for p in range(NP):
+                ops.pool_fwd(st.t[f"Xf.{p}.{m}"], st.t[f"Sf.{p}.{m}"], B=B, L=L, nq=1, O_pre=st.t[f"Of_pre.{p}.{m}"],
+                             out=u_pool[m][p * B:(p + 1) * B], out_stride_b=G, out_bf16=u_pool_b[m][p * B:(p + 1) * B],
+                             drop_p=FRAME_P, site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev,
+                             Kt=None, Qp=None, qp_stride_b=0)
 
         def fra2utt_unit(i):
             p, m = units[i]
@@ -398,16 +435,29 @@ class Engine:
                          out_stride_b=G, out_bf16=u_pool_b[m][p * B:(p + 1) * B], drop_p=FRAME_P if drop else 0.0,
                          site=site_id(pre + ".out", p), seed=seed, step=step, step_dev=cfg.step_dev, Kt=Kp, Qp=Qc,
                          qp_stride_b=0, **vl)
-        self._parallel(len(units), fra2utt_unit)
+        fu_jobs = []                                # per modality when merged, else per (pass, modality) unit
+        for m in range(3):
+            if mrg[m] and G == 256:
+                fu_jobs.append((fra2utt_mod, m))
+            else:
+                fu_jobs += [(fra2utt_unit, i) for i, (p_, m_) in enumerate(units) if m_ == m]
+        self._parallel(len(fu_jobs), lambda j: fu_jobs[j][0](fu_jobs[j][1]))
 
         # 3'. the Cross_Attention key projections depend on the in-projections only: issued here on an auxiliary stream,
         #     they stream under utterance chain A (joined before the pooling kernels of step 4)
-        for (p, m) in units:
-            nr = nrows[_unit_stream(p, m)]
-            if keep:
-                self._new(st, f"Kc.{p}.{m}", (nr, G), torch.bfloat16)
-            else:
-                st.t[f"Kc.{p}.{m}"] = torch.empty(nr, G, dtype=torch.bfloat16, device=dev)
+        for m in range(3):
+            if mrg[m]:
+                Kall = self._new(st, f"Kc.all.{m}", (NP, nrows[_unit_stream(0, m)], G), torch.bfloat16)
+            for p in range(NP):
+                st.t[f"Kc.{p}.{m}"] = Kall[p] if mrg[m] else torch.empty(nrows[_unit_stream(p, m)], G, dtype=torch.bfloat16,
+                                                                         device=dev)
+
+        def cross_keyproj_mod(m, mc):               # merged: one GEMM over both passes of the modality
+            pre = f"cross_att_fra2utt_{m}"
+            nr = nrows[_unit_stream(0, m)]
+            ops.gemm(st.t[f"Xc.all.{m}"].view(NP * nr, G), W.bf16(pre + ".input_proj.weight"), M=NP * nr, N=G, K=G,
+                     bias=W.f32(pre + ".input_proj.bias"), act=ops.ACT_TANH, out_bf16=st.t[f"Kc.all.{m}"].view(NP * nr, G),
+                     max_ctas=mc)
 
         def cross_keyproj(i, mc):
             p, m = units[i]
@@ -419,8 +469,14 @@ class Engine:
             ops.gemm(st.t[f"Xc.{p}.{m}"], W.bf16(pre + ".input_proj.weight"), M=nr, N=G, K=G,
                      bias=W.f32(pre + ".input_proj.bias"), act=ops.ACT_TANH, out_bf16=st.t[f"Kc.{p}.{m}"], max_ctas=mc)
         early_k = self.overlap_fwd and not varlen
+        kp_jobs = []
+        for m in range(3):
+            if mrg[m]:
+                kp_jobs.append((cross_keyproj_mod, m))
+            else:
+                kp_jobs += [(cross_keyproj, i) for i, (p_, m_) in enumerate(units) if m_ == m]
         if early_k:
-            self._side(lambda: [cross_keyproj(i, self.overlap_ctas) for i in range(len(units))])
+            self._side(lambda: [fn(x, self.overlap_ctas) for fn, x in kp_jobs])
 
         # 3. utterance chain A: modality MLPs, raw gate, partial fusions, 7 query MLPs, query projections
         cat = self._new(st, "cat", (R, 3 * G))
@@ -469,6 +525,8 @@ class Engine:
             self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
         if early_k:
             self._join_side()
+        else:
+            self._parallel(len(kp_jobs), lambda j: kp_jobs[j][0](kp_jobs[j][1], 0))
 
         def cross_unit(i):
             p, m = units[i]
@@ -480,8 +538,6 @@ class Engine:
             vl = dict(row_off=cfg.row_off[_unit_stream(p, m)], Hpad=pad_c[("cross_att_fra2utt", m)][0],
                       Kpad=pad_c[("cross_att_fra2utt", m)][1]) if varlen else {}
             Kt = st.t[f"Kc.{p}.{m}"]
-            if not early_k:
-                cross_keyproj(i, unit_share.get(i, 0))
             ops.pool_fwd(X, S, B=B, L=L, nq=NQ, O_pre=st.t[f"Oc_pre.{p}.{m}"], out=C[m][p * B * NQ:(p + 1) * B * NQ],
                          out_stride_b=NQ * G, out_bf16=C_b[m][p * B * NQ:(p + 1) * B * NQ],
                          drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step,
@@ -598,13 +654,32 @@ class Engine:
         mod_share = _shares({m: cfg.frames[_unit_stream(0, m)] for m in range(3)}) if self.sm_shares else {}
 
         deferred = [] if self.overlap else None     # the blocks' weight-gradient GEMMs: nothing reads them before Adam
+        mrg = {m: f"Xc.all.{m}" in t for m in range(3)}   # pass-contiguous X' (see forward): one weight-gradient GEMM
+
+        def block_dw(blk, m, dZall, mc=0):          # dW_in += dZ^T X' over both passes
+            pre = f"{blk}_{m}"
+            Xall = t[f"X{blk[0]}.all.{m}"]
+            rows = Xall.shape[0] * Xall.shape[1]
+            ops.gemm(dZall.view(rows, G), Xall.view(rows, G), M=G, N=G, K=rows, a_mn=True, b_mn=True,
+                     k_splits=_ksplits(rows, G, G, mc or NUM_SMS), out_f32=W.grad(pre + ".input_proj.weight"),
+                     f32_mode=ops.OUT_ATOMIC, max_ctas=mc)
+
+        def new_dz(m):
+            return torch.empty(NP, B * cfg.frames[_unit_stream(0, m)], G, dtype=torch.bfloat16, device=dev) if mrg[m] else None
+        dZc = [new_dz(m) for m in range(3)]
 
         def cross_attn_bwd(m):                     # passes of one modality accumulate into the same dH: in order
             for p in range(NP):
                 self._attn_block_bwd(W, st, p, m, "cross_att_fra2utt", NQ, dOut=dC[m][p * B * NQ:(p + 1) * B * NQ],
                                      Qp=t[f"Qp.{m}"][p * B * NQ:(p + 1) * B * NQ], qp_stride=NQ * G,
                                      dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH, started=started,
-                                     max_ctas=mod_share.get(m, 0), defer_dw=deferred)
+                                     max_ctas=mod_share.get(m, 0), defer_dw=deferred,
+                                     dZ=dZc[m][p] if mrg[m] else None)
+            if mrg[m]:
+                if deferred is not None:
+                    deferred.append((lambda mc, m=m: block_dw("cross_att_fra2utt", m, dZc[m], mc), (dZc[m],)))
+                else:
+                    block_dw("cross_att_fra2utt", m, dZc[m])
         self._parallel(3, cross_attn_bwd)
         if deferred:
             # ... so they stream under the latency-bound backward chain B7-B9 (joined before the early gradient bucket)
@@ -644,13 +719,17 @@ class Engine:
             self._join_side()                         # the chain's weight gradients ran on side streams
             on_chain_grads_final()
         # B10. FRA2UTT_new blocks
+        dZf = [new_dz(m) for m in range(3)]
+
         def fra2utt_bwd(m):
             pre = f"fra2utt_{m}"
             for p in range(NP):
                 self._attn_block_bwd(W, st, p, m, "fra2utt", 1, dOut=du[m][p * B:(p + 1) * B],
                                      Qp=W.f32(pre + ".attention_context_vector"), qp_stride=0,
                                      dQp=W.grad(pre + ".attention_context_vector"), dH=dH, started=started,
-                                     max_ctas=mod_share.get(m, 0))
+                                     max_ctas=mod_share.get(m, 0), dZ=dZf[m][p] if mrg[m] else None)
+            if mrg[m]:
+                block_dw("fra2utt", m, dZf[m])
         self._parallel(3, fra2utt_bwd)
         # B11. in-projection weight / bias gradients (inputs carry no gradient)
         items = list(dH.items())
@@ -669,7 +748,10 @@ class Engine:
         self._join_side()
 
     def _attn_block_bwd(self, W: Weights, st: State, p: int, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
-                        dH: Dict[str, torch.Tensor], started: Dict[str, bool], max_ctas: int = 0, defer_dw=None):
+                        dH: Dict[str, torch.Tensor], started: Dict[str, bool], max_ctas: int = 0, defer_dw=None,
+                        dZ: Optional[torch.Tensor] = None):
+        """One (pass, modality) attention block: attn_bwd (row-wise part), dH += (dZ W_in) * M_in and - unless the caller
+        passed its own dZ buffer and runs the weight gradient over both passes at once - dW_in += dZ^T X'."""
         cfg = st.cfg
         G = self.G
         t = st.t
@@ -682,7 +764,9 @@ class Engine:
         Kt = t[f"K{tag}.{p}.{m}"]
         P = t[f"S{tag}.{p}.{m}"]
         Opre = t[f"O{tag}_pre.{p}.{m}"]
-        dZ = torch.empty(B * L, G, dtype=torch.bfloat16, device=self.device)
+        own_dw = dZ is None
+        if own_dw:
+            dZ = torch.empty(B * L, G, dtype=torch.bfloat16, device=self.device)
         first = not started.get(s, False)          # the first block of a stream stores, later ones accumulate
         started[s] = True
         fmask = site_id(pre + ".in", p) if cfg.dropout else 0
@@ -699,6 +783,8 @@ class Engine:
         def dw(mc):
             ops.gemm(dZ, X, M=G, N=G, K=B * L, a_mn=True, b_mn=True, k_splits=_ksplits(B * L, G, G, mc or NUM_SMS),
                      out_f32=W.grad(pre + ".input_proj.weight"), f32_mode=ops.OUT_ATOMIC, max_ctas=mc)
+        if not own_dw:
+            return
         if defer_dw is not None:
             defer_dw.append((dw, (dZ, X)))
         else:
