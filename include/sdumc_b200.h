@@ -316,9 +316,13 @@ typedef struct sdumc_rnc_args {
   void* workspace;
   uint64_t workspace_bytes;
   int32_t reuse_sort;  /* 1: the workspace still holds the label sort of a previous call with the same labels */
-  int32_t reserved;
+  int32_t phase;       /* 0: everything.  1: only the part that depends on the labels (sort, bucket index, the four
+                          boundaries of every (anchor, element) pair) - a trainer runs it early, off the critical path;
+                          feats / loss / dfeats may be NULL.  2: only the feature-dependent part (distances, loss,
+                          gradient), after a phase-1 call with the same labels, row range and workspace. */
 } sdumc_rnc_args;
-uint64_t sdumc_rnc_workspace_bytes(int32_t n, int32_t D);
+uint64_t sdumc_rnc_workspace_bytes(int32_t n, int32_t D);            /* all n anchor rows in one call */
+uint64_t sdumc_rnc_workspace_bytes_rows(int32_t n, int32_t D, int32_t rows); /* calls with at most `rows` anchors */
 int sdumc_rnc(const sdumc_rnc_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------

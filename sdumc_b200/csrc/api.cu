@@ -120,7 +120,8 @@ int sdumc_sqdiff_grad(const float* a, const float* b, int64_t n, const float* co
                       void* stream) {
   return launch_sqdiff_grad(a, b, n, coef_dev, da, db_or_null, static_cast<cudaStream_t>(stream));
 }
-uint64_t sdumc_rnc_workspace_bytes(int32_t n, int32_t D) { return rnc_workspace_bytes(n, D); }
+uint64_t sdumc_rnc_workspace_bytes(int32_t n, int32_t D) { return rnc_workspace_bytes(n, D, n); }
+uint64_t sdumc_rnc_workspace_bytes_rows(int32_t n, int32_t D, int32_t rows) { return rnc_workspace_bytes(n, D, rows); }
 
 int sdumc_struct_size(int which) {
   switch (which) {

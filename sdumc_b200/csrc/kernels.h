@@ -41,7 +41,7 @@ int launch_loss_finish(const LossFinishArgs& a, cudaStream_t stream);
 int launch_sqdiff_sum(const float* a, const float* b, long n, float* out_sum, cudaStream_t stream);
 int launch_sqdiff_grad(const float* a, const float* b, long n, const float* coef, float* da, float* db_or_null,
                        cudaStream_t stream);
-size_t rnc_workspace_bytes(int n, int D);
+size_t rnc_workspace_bytes(int n, int D, int rows);
 int launch_rnc(const RncArgs& a, cudaStream_t stream);
 // adam.cu
 int launch_adam(const AdamArgs& a, cudaStream_t stream);

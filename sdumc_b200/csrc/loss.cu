@@ -309,26 +309,25 @@ __global__ void __launch_bounds__(256) rnc_dist_kernel(RncArgs a, float* dist) {
   }
 }
 
-// One CTA per anchor row.  Shared memory: pre[n] (double), e[n], aux[n] (logits, then 1/D), dist[n], ys[n] (float),
-// T[n+1] (bucket index).  Cmat holds the row's distances on entry (rnc_dist_kernel) and its gradient coefficients on
-// exit.  Each element needs four boundary searches over the sorted labels (two for its denominator, two for the
-// window of positives whose negative set contains it).  Every boundary is the rank of a VALUE (y_i -+ threshold) in
-// the sorted labels, so the search starts from the bucket index: [T[b-1], T[b+2]) around the value's bucket b holds
-// ~3 labels instead of n, and the reference's fp32 predicate (loss.py:303, evaluated verbatim) decides inside it -
-// ~2 dependent shared-memory reads per search instead of 13 at n = 8192.  The bracket is exact: the predicate and
-// the value differ by fp32 rounding (~1e-6), a bucket is >= 1e-5 wide, and one full bucket of margin is kept on each
-// side; with a degenerate label range the index is disabled and the search covers the whole side.
-__global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* perm, const float* ys_g, const int* pos,
-                                                       const int* T_g, const float* hdr, float* Cmat) {
+// The four boundaries every (anchor i, element j) pair needs depend on the LABELS only (two for the denominator of j as
+// a positive: its negative set is a prefix plus a suffix of the sorted order; two for the window of positives whose
+// negative set contains j).  rnc_bounds_kernel computes them - one CTA per anchor, shared memory: ys[n], T[n+1] - into
+// bounds[row][s] = {left_end, right_begin, a0, b1} (16-bit: n <= 8192), so the data-parallel trainer runs it at the
+// START of the step on a side stream (the labels are inputs) and only the feature-dependent part (rnc_row_kernel)
+// sits between the forward and the backward pass.
+// Every boundary is the rank of a VALUE (y_i -+ threshold) in the sorted labels, so the search starts from the bucket
+// index: [T[b-1], T[b+2]) around the value's bucket b holds ~3 labels instead of n, and the reference's fp32
+// predicate (loss.py:303, evaluated verbatim) decides inside it - ~2 dependent shared-memory reads per search instead
+// of 13 at n = 8192.  The bracket is exact: the predicate and the value differ by fp32 rounding (~1e-6), a bucket is
+// >= 1e-5 wide, and one full bucket of margin is kept on each side; with a degenerate label range the index is
+// disabled and the search covers the whole side.
+__global__ void __launch_bounds__(1024) rnc_bounds_kernel(RncArgs a, const float* ys_g, const int* pos, const int* T_g,
+                                                          const float* hdr, ushort4* bounds) {
   pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
   pdl_launch_dependents();
   extern __shared__ unsigned char smraw[];
-  const int n = a.n, D = a.D;
-  double* pre = reinterpret_cast<double*>(smraw);
-  float* e = reinterpret_cast<float*>(pre + n);
-  float* aux = e + n;
-  float* dist_s = aux + n;
-  float* ys = dist_s + n;
+  const int n = a.n;
+  float* ys = reinterpret_cast<float*>(smraw);
   int* T = reinterpret_cast<int*>(ys + n);
   const float y0 = hdr[0], inv_delta = hdr[1];
   const int nb = n;
@@ -378,6 +377,86 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
     }
     return m;
   };
+  const int NT = blockDim.x;
+  const int i = a.row_begin + blockIdx.x;
+  const int t = threadIdx.x;
+  const int pi = pos[i];
+  const float yi = a.labels[i];
+  ushort4* brow = bounds + (long)blockIdx.x * n;
+  for (int s = t; s <= n; s += NT) T[s] = T_g[s];
+  for (int s = t; s < n; s += NT) ys[s] = ys_g[s];
+  __syncthreads();
+  for (int s = t; s < n; s += NT) {
+    int left_end = 0, right_begin = 1, a0 = 0, b1 = 1;
+    if (s != pi) {
+      int lo, hi;
+      {
+        // j = s as a POSITIVE: its negative set {x: d_ix >= d_is - 1e-4} = [0, left_end) + [right_begin, n)
+        const float thr = fabsf(yi - ys[s]) - 0.0001f;
+        auto in_neg = [&](int x) { return fabsf(yi - ys[x]) >= thr; };        // loss.py:303, verbatim
+        auto not_neg = [&](int x) { return !(fabsf(yi - ys[x]) >= thr); };
+        if (s > pi) {
+          right_begin = walk_down(s, pi + 1, in_neg);   // first s' in (pi,n) with d >= thr: just below s
+          bracket(yi - thr, 0, pi, lo, hi);             // first s' in [0,pi) with d < thr, i.e. label > y_i - thr (mirror side)
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (in_neg(mid)) lo = mid + 1; else hi = mid;
+          }
+          left_end = lo;
+        } else {
+          left_end = walk_up(s + 1, pi, not_neg);       // first s' in [0,pi) with d < thr: just above s
+          bracket(yi + thr, pi + 1, n, lo, hi);         // first s' in (pi,n) with d >= thr, i.e. label >= y_i + thr (mirror side)
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (in_neg(mid)) hi = mid; else lo = mid + 1;
+          }
+          right_begin = lo;
+        }
+      }
+      {
+        // j = s as a NEGATIVE: the positives k whose negative set contains j are a window k in [a0, pi) and (pi, b1):
+        // (d_ik - 1e-4) <= d_ij; d_ik decreases towards pi on the left and grows on the right
+        const float dij = fabsf(yi - ys[s]);
+        auto has_j = [&](int x) { return dij >= fabsf(yi - ys[x]) - 0.0001f; };
+        auto not_has_j = [&](int x) { return !(dij >= fabsf(yi - ys[x]) - 0.0001f); };
+        if (s < pi) {
+          a0 = walk_down(s, 0, has_j);                       // first k in [0,pi) with the predicate: just below s
+          bracket(yi + (dij + 0.0001f), pi + 1, n, lo, hi);  // first k in (pi,n) violating it: label > y_i + d_ij + 1e-4
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (has_j(mid)) lo = mid + 1; else hi = mid;
+          }
+          b1 = lo;  // window is (pi, b1)
+        } else {
+          b1 = walk_up(s + 1, n, not_has_j);                 // just above s
+          bracket(yi - (dij + 0.0001f), 0, pi, lo, hi);      // first k with label >= y_i - d_ij - 1e-4
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (has_j(mid)) hi = mid; else lo = mid + 1;
+          }
+          a0 = lo;
+        }
+      }
+    }
+    brow[s] = make_ushort4((unsigned short)left_end, (unsigned short)right_begin, (unsigned short)a0, (unsigned short)b1);
+  }
+}
+
+// One CTA per anchor row: the feature-dependent part.  Shared memory: pre[n] (double), e[n], aux[n] (logits, then
+// 1/D).  Cmat holds the row's distances on entry (rnc_dist_kernel) and its gradient coefficients on exit.  With one
+// CTA of 32 warps per SM every exposed global-memory round trip adds to the kernel, so a thread fetches everything it
+// needs from global memory for its (at most 8) elements - permutation entry, distance, boundary quadruple - once, up
+// front, into registers.
+constexpr int kRncPerThread = 8;   // elements per thread: the launcher sizes the CTA as ceil(n / 8) threads (n <= 8192)
+__global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* perm, const int* pos,
+                                                       const ushort4* __restrict__ bounds, float* Cmat) {
+  pdl_wait();                // predecessors complete + visible (see common.cuh: PDL)
+  pdl_launch_dependents();
+  extern __shared__ unsigned char smraw[];
+  const int n = a.n;
+  double* pre = reinterpret_cast<double*>(smraw);
+  float* e = reinterpret_cast<float*>(pre + n);
+  float* aux = e + n;
   __shared__ float red[32];
   __shared__ double wsum[32];
   __shared__ float bcast;
@@ -386,25 +465,38 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
   const int i = a.row_begin + blockIdx.x;
   const int t = threadIdx.x;
   const int pi = pos[i];
-  const float yi = a.labels[i];
   const float inv_t = 1.f / a.temperature;
   float* crow = Cmat + (long)blockIdx.x * n;
-  (void)D;
+  const ushort4* brow = bounds + (long)blockIdx.x * n;
 
-  // 1. logits in sorted order (the whole distance row moves to shared memory before crow is overwritten), running max
+  int jv[kRncPerThread];
+  float dv[kRncPerThread];
+  ushort4 bv[kRncPerThread];
+#pragma unroll
+  for (int u = 0; u < kRncPerThread; ++u) {
+    const int s = t + u * NT;
+    jv[u] = s < n ? __ldg(perm + s) : -1;
+  }
+#pragma unroll
+  for (int u = 0; u < kRncPerThread; ++u) {
+    const int s = t + u * NT;
+    dv[u] = jv[u] >= 0 ? crow[jv[u]] : 0.f;
+    bv[u] = s < n ? __ldg(brow + s) : make_ushort4(0, 1, 0, 1);
+  }
+
+  // 1. logits in sorted order, running max
   float mx = -INFINITY;
-  for (int s = t; s <= n; s += NT) T[s] = T_g[s];
-  for (int s = t; s < n; s += NT) {
-    ys[s] = ys_g[s];
-    const int j = perm[s];
-    const float ds = crow[j];
-    dist_s[s] = ds;
-    float lg = -INFINITY;
-    if (j != i) {
-      lg = -ds * inv_t;
-      mx = fmaxf(mx, lg);
+#pragma unroll
+  for (int u = 0; u < kRncPerThread; ++u) {
+    const int s = t + u * NT;
+    if (s < n) {
+      float lg = -INFINITY;
+      if (jv[u] != i) {
+        lg = -dv[u] * inv_t;
+        mx = fmaxf(mx, lg);
+      }
+      aux[s] = lg;
     }
-    aux[s] = lg;
   }
   mx = warp_max(mx);
   if ((t & 31) == 0) red[t >> 5] = mx;
@@ -423,37 +515,21 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
   block_scan(e, pre, n, wsum);
   const double total = pre[n - 1];
 
-  // 3. per positive k: denominator = prefix [0,lo) + suffix [hi,n)
+  // 3. per positive k: denominator = prefix [0, left_end) + suffix [right_begin, n)
   float lsum = 0.f;
-  for (int s = t; s < n; s += NT) {
-    float rinv = 0.f;
-    if (s != pi) {
-      const float thr = fabsf(yi - ys[s]) - 0.0001f;
-      auto in_neg = [&](int x) { return fabsf(yi - ys[x]) >= thr; };        // loss.py:303, verbatim
-      auto not_neg = [&](int x) { return !(fabsf(yi - ys[x]) >= thr); };
-      int left_end, right_begin, lo, hi;
-      if (s > pi) {
-        right_begin = walk_down(s, pi + 1, in_neg);   // first s' in (pi,n) with d >= thr: just below s
-        bracket(yi - thr, 0, pi, lo, hi);             // first s' in [0,pi) with d < thr, i.e. label > y_i - thr (mirror side)
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (in_neg(mid)) lo = mid + 1; else hi = mid;
-        }
-        left_end = lo;
-      } else {
-        left_end = walk_up(s + 1, pi, not_neg);       // first s' in [0,pi) with d < thr: just above s
-        bracket(yi + thr, pi + 1, n, lo, hi);         // first s' in (pi,n) with d >= thr, i.e. label >= y_i + thr (mirror side)
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (in_neg(mid)) hi = mid; else lo = mid + 1;
-        }
-        right_begin = lo;
+#pragma unroll
+  for (int u = 0; u < kRncPerThread; ++u) {
+    const int s = t + u * NT;
+    if (s < n) {
+      float rinv = 0.f;
+      if (s != pi) {
+        const int left_end = bv[u].x, right_begin = bv[u].y;
+        const double Dk = (left_end > 0 ? pre[left_end - 1] : 0.0) + (total - pre[right_begin - 1]);
+        lsum += logf((float)Dk) - (aux[s] - mx);
+        rinv = __frcp_rn((float)Dk);
       }
-      const double Dk = (left_end > 0 ? pre[left_end - 1] : 0.0) + (total - pre[right_begin - 1]);
-      lsum += logf((float)Dk) - (aux[s] - mx);
-      rinv = __frcp_rn((float)Dk);
+      aux[s] = rinv;  // the logit at s was consumed above by this thread only
     }
-    aux[s] = rinv;  // the logit at s was consumed above by this thread only
   }
   lsum = warp_sum(lsum);
   __syncthreads();
@@ -466,44 +542,25 @@ __global__ void __launch_bounds__(1024) rnc_row_kernel(RncArgs a, const int* per
   }
   if (!a.dfeats) return;
 
-  // 4. backward: G_j = sum of 1/D_k over the k whose negative set contains j (a window around i)
+  // 4. backward: G_j = sum of 1/D_k over the k whose negative set contains j (the window [a0, pi) + (pi, b1))
   __syncthreads();
   block_scan(aux, pre, n, wsum);  // pre = prefix sums of 1/D_k
   const float cscale = a.grad_scale / ((float)n * (float)(n - 1));
-  for (int s = t; s < n; s += NT) {
-    const int j = perm[s];
-    float c = 0.f;
-    if (s != pi) {
-      const float dij = fabsf(yi - ys[s]);
-      // window of positives k whose negative set contains j: k in [a0, pi) and (pi, b1), where
-      // (d_ik - 1e-4) <= d_ij; d_ik decreases towards pi on the left and grows on the right
-      auto has_j = [&](int x) { return dij >= fabsf(yi - ys[x]) - 0.0001f; };
-      auto not_has_j = [&](int x) { return !(dij >= fabsf(yi - ys[x]) - 0.0001f); };
-      int a0, b1, lo, hi;
-      if (s < pi) {
-        a0 = walk_down(s, 0, has_j);                       // first k in [0,pi) with the predicate: just below s
-        bracket(yi + (dij + 0.0001f), pi + 1, n, lo, hi);  // first k in (pi,n) violating it: label > y_i + d_ij + 1e-4
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (has_j(mid)) lo = mid + 1; else hi = mid;
-        }
-        b1 = lo;  // window is (pi, b1)
-      } else {
-        b1 = walk_up(s + 1, n, not_has_j);                 // just above s
-        bracket(yi - (dij + 0.0001f), 0, pi, lo, hi);      // first k with label >= y_i - d_ij - 1e-4
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (has_j(mid)) hi = mid; else lo = mid + 1;
-        }
-        a0 = lo;
+  const double pre_pi = pre[pi];
+#pragma unroll
+  for (int u = 0; u < kRncPerThread; ++u) {
+    const int s = t + u * NT;
+    if (s < n) {
+      float c = 0.f;
+      if (s != pi) {
+        const int a0 = bv[u].z, b1 = bv[u].w;
+        const double Gj = (pre_pi - (a0 > 0 ? pre[a0 - 1] : 0.0)) + (pre[b1 - 1] - pre_pi);
+        const float dl = cscale * (e[s] * (float)Gj - 1.f);  // d loss / d logit_ij
+        // logit = -dist / t  ->  d loss / d dist = -dl / t ; direction (f_i - f_j) / dist
+        c = dv[u] > 0.f ? -dl * inv_t / dv[u] : 0.f;
       }
-      const double Gj = (pre[pi] - (a0 > 0 ? pre[a0 - 1] : 0.0)) + (pre[b1 - 1] - pre[pi]);
-      const float dl = cscale * (e[s] * (float)Gj - 1.f);  // d loss / d logit_ij
-      // logit = -dist / t  ->  d loss / d dist = -dl / t ; direction (f_i - f_j) / dist
-      const float dist = dist_s[s];
-      c = dist > 0.f ? -dl * inv_t / dist : 0.f;
+      crow[jv[u]] = c;  // coefficient of (f_i - f_j) in d loss/d f_i, and of -(f_i - f_j) in d loss/d f_j
     }
-    crow[j] = c;  // coefficient of (f_i - f_j) in d loss/d f_i, and of -(f_i - f_j) in d loss/d f_j
   }
 }
 
@@ -582,21 +639,26 @@ __global__ void __launch_bounds__(256) rnc_grad_kernel(RncArgs a, const float* _
 }
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
-size_t rnc_workspace_bytes(int n, int D) {
+size_t rnc_workspace_bytes(int n, int D, int rows) {
   (void)D;
-  // perm, ys, pos, bucket index (+ header) + the full coefficient matrix (callers with a row slice use fewer rows)
-  return align_up((size_t)n * 4, 256) * 3 + align_up((size_t)(n + 1) * 4 + 16, 256) + align_up((size_t)n * (size_t)n * 4, 256);
+  if (rows <= 0 || rows > n) rows = n;
+  // perm, ys, pos, bucket index (+ header) + per anchor row of the call: n coefficients (fp32) and n boundary quadruples
+  return align_up((size_t)n * 4, 256) * 3 + align_up((size_t)(n + 1) * 4 + 16, 256) +
+         align_up((size_t)rows * (size_t)n * 4, 256) + align_up((size_t)rows * (size_t)n * 8, 256);
 }
 
 int launch_rnc(const RncArgs& a, cudaStream_t stream) {
-  SDUMC_CHECK_ARG(a.feats && a.labels && a.loss && a.workspace, "rnc: null pointer");
+  SDUMC_CHECK_ARG(a.labels && a.workspace && (a.phase == 1 || (a.feats && a.loss)), "rnc: null pointer");
   SDUMC_CHECK_ARG(a.n >= 2 && a.n <= kRncMaxN, "rnc: n=%d out of range [2, %d]", a.n, kRncMaxN);
   SDUMC_CHECK_ARG(a.D > 0 && a.D % 4 == 0 && a.D <= 256, "rnc: feature dim %d unsupported", a.D);
   SDUMC_CHECK_ARG(a.row_begin >= 0 && a.row_end <= a.n && a.row_begin < a.row_end, "rnc: bad row range");
   const int rows = a.row_end - a.row_begin;
   const size_t seg = align_up((size_t)a.n * 4, 256);
   const size_t segT = align_up((size_t)(a.n + 1) * 4 + 16, 256);
-  const size_t need = seg * 3 + segT + align_up((size_t)rows * (size_t)a.n * 4, 256);
+  const size_t segC = align_up((size_t)rows * (size_t)a.n * 4, 256);
+  const size_t need = seg * 3 + segT + segC + align_up((size_t)rows * (size_t)a.n * 8, 256);
+  const int phase = a.phase;     // 0: everything; 1: the label-only part (sort, bucket index, boundaries); 2: the rest
+  SDUMC_CHECK_ARG(phase >= 0 && phase <= 2, "rnc: phase %d (0 all, 1 labels, 2 features)", phase);
   SDUMC_CHECK_ARG(a.workspace_bytes >= need, "rnc: workspace %zu < %zu", a.workspace_bytes, need);
   unsigned char* ws = static_cast<unsigned char*>(a.workspace);
   int* perm = reinterpret_cast<int*>(ws);
@@ -605,24 +667,31 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
   float* hdr = reinterpret_cast<float*>(ws + 3 * seg);
   int* T = reinterpret_cast<int*>(ws + 3 * seg + 16);
   float* Cmat = reinterpret_cast<float*>(ws + 3 * seg + segT);
+  ushort4* bounds = reinterpret_cast<ushort4*>(ws + 3 * seg + segT + segC);
   static bool attr_done[kMaxDevices] = {false};
   const int dev = current_device();
   if (!attr_done[dev]) {
-    SDUMC_CUDA(cudaFuncSetAttribute(rnc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kRncMaxN * 28 + 16));
+    SDUMC_CUDA(cudaFuncSetAttribute(rnc_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRncMaxN * 16));
+    SDUMC_CUDA(cudaFuncSetAttribute(rnc_bounds_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRncMaxN * 8 + 16));
     attr_done[dev] = true;
   }
-  if (!a.reuse_sort) {   // a data-parallel rank calls once per anchor range with the same labels: sort once
+  // one anchor per CTA; the row kernel keeps kRncPerThread elements per thread in registers
+  const int row_threads = std::min(1024, std::max(64, (a.n + kRncPerThread * 32 - 1) / (kRncPerThread * 32) * 32));
+  if (phase != 2 && !a.reuse_sort) {   // a caller with several anchor ranges over the same labels sorts once
     SDUMC_CUDA(launch_kernel(rnc_sort_kernel, dim3((a.n + 31) / 32), dim3(256), (size_t)a.n * 4, stream, 1, a.labels, a.n, perm, ys, pos));
     SDUMC_CUDA(cudaGetLastError());
     SDUMC_CUDA(launch_kernel(rnc_bucket_kernel, dim3((a.n + 255) / 256), dim3(256), 0, stream, 1, ys, a.n, T, hdr));
     SDUMC_CUDA(cudaGetLastError());
   }
+  if (phase != 2) {
+    SDUMC_CUDA(launch_kernel(rnc_bounds_kernel, dim3(rows), dim3(row_threads), (size_t)a.n * 8 + 16, stream, 1, a, ys, pos, T,
+                             hdr, bounds));
+    SDUMC_CUDA(cudaGetLastError());
+  }
+  if (phase == 1) return 0;
   SDUMC_CUDA(launch_kernel(rnc_dist_kernel, dim3(dim3((a.n + 63) / 64, (rows + 63) / 64)), dim3(256), 0, stream, 1, a, Cmat));
   SDUMC_CUDA(cudaGetLastError());
-  const size_t smem = (size_t)a.n * 28 + 16;
-  const int row_threads = a.n >= 4096 ? 1024 : (a.n >= 1024 ? 512 : 256);
-  SDUMC_CUDA(launch_kernel(rnc_row_kernel, dim3(rows), dim3(row_threads), smem, stream, 1, a, perm, ys, pos, T, hdr, Cmat));
+  SDUMC_CUDA(launch_kernel(rnc_row_kernel, dim3(rows), dim3(row_threads), (size_t)a.n * 16, stream, 1, a, perm, pos, bounds, Cmat));
   SDUMC_CUDA(cudaGetLastError());
   if (a.dfeats) {
     SDUMC_CHECK_ARG((reinterpret_cast<uintptr_t>(a.dfeats) & 15u) == 0 && (reinterpret_cast<uintptr_t>(a.feats) & 15u) == 0,

@@ -218,23 +218,35 @@ def sqdiff_grad(a, b, coef, da, db=None) -> None:
           "sdumc_sqdiff_grad")
 
 
-def rnc_workspace_bytes(n: int, D: int) -> int:
+def rnc_workspace_bytes(n: int, D: int, rows: int = 0) -> int:
+    """Workspace of sdumc_rnc for calls with at most `rows` anchor rows (0: all n)."""
+    if rows:
+        return int(_lib.lib().sdumc_rnc_workspace_bytes_rows(n, D, rows))
     return int(_lib.lib().sdumc_rnc_workspace_bytes(n, D))
 
 
-def rnc(feats, labels, *, loss, dfeats=None, row_begin=0, row_end=None, temperature=2.0, grad_scale=1.0,
-        workspace=None, reuse_sort=False) -> None:
-    """Rank-N-Contrast over feats [n,D] (rows = view-0 samples then view-1 samples), labels [n]."""
-    n, D = feats.shape
+RNC_ALL, RNC_LABELS, RNC_FEATURES = 0, 1, 2
+
+
+def rnc(feats, labels, *, loss=None, dfeats=None, row_begin=0, row_end=None, temperature=2.0, grad_scale=1.0,
+        workspace=None, reuse_sort=False, phase=RNC_ALL, D=None) -> None:
+    """Rank-N-Contrast over feats [n,D] (rows = view-0 samples then view-1 samples), labels [n].
+    phase = RNC_LABELS runs only what depends on the labels (sort, bucket index, boundaries; feats may be None),
+    RNC_FEATURES the rest on the same workspace - a trainer hides the first under its forward pass."""
+    n = labels.numel()
+    D = feats.shape[1] if feats is not None else (D or 64)
     a = STRUCTS["sdumc_rnc_args"]()
     a.feats, a.labels, a.n, a.D = ptr(feats), ptr(labels), n, D
     a.row_begin, a.row_end = row_begin, (n if row_end is None else row_end)
     a.temperature, a.loss, a.dfeats, a.grad_scale = temperature, ptr(loss), ptr(dfeats), grad_scale
     if workspace is None:
-        workspace = torch.empty(rnc_workspace_bytes(n, D), dtype=torch.uint8, device=feats.device)
+        workspace = torch.empty(rnc_workspace_bytes(n, D), dtype=torch.uint8, device=labels.device)
     a.workspace, a.workspace_bytes = ptr(workspace), workspace.numel()
     a.reuse_sort = 1 if reuse_sort else 0
-    call("sdumc_rnc", a, launches=(6 if dfeats is not None else 4) - (2 if reuse_sort else 0))
+    a.phase = phase
+    n_lab = (0 if reuse_sort else 2) + 1
+    n_feat = 4 if dfeats is not None else 2
+    call("sdumc_rnc", a, launches={RNC_ALL: n_lab + n_feat, RNC_LABELS: n_lab, RNC_FEATURES: n_feat}[phase])
 
 
 def adam(p, g, m, v, *, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0,

@@ -106,7 +106,10 @@ class Trainer:
         self.d_th, self.d_ct = z(R * Gd).view(R, Gd), z(R * 896).view(R, 896)
         self.y2 = z(R)
         n_g = 2 * B * self.world
-        self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64), dtype=torch.uint8, device=dev)
+        self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64, rows=2 * B), dtype=torch.uint8, device=dev)
+        self.y_glob = z(n_g)                  # labels of the global Rank-N-Contrast problem (rank-major rows)
+        self._label_stream = None
+        self._labels_ready = False
         self.cur_B = self.B
         self.train_dropout = True      # tests switch dropout off to compare against a deterministic reference
         self._comm_stream = None
@@ -333,16 +336,19 @@ class Trainer:
         self.rnc_val.zero_()
         d_rnc.zero_()
         w6 = self.loss_w[5]
+        if not self._labels_ready:                                        # (a caller that skipped _step_body)
+            self._rnc_labels_early()
+        self._labels_ready = False
+        torch.cuda.current_stream().wait_stream(self._label_stream)      # the label-only part (_rnc_labels_early)
         if W_ == 1:
-            y2[:B].copy_(y)
-            y2[B:].copy_(y)
-            ops.rnc(st.t["rnc"], y2, loss=self.rnc_val, dfeats=d_rnc, grad_scale=w6, workspace=self.rnc_ws)
+            ops.rnc(st.t["rnc"], y2, loss=self.rnc_val, dfeats=d_rnc, grad_scale=w6, workspace=self.rnc_ws,
+                    phase=ops.RNC_FEATURES)
         else:
             from . import dp
 
             def rnc_fn(feats_g, y_g, lo, hi, loss, dfeats):   # this rank's anchors: one contiguous row range
-                ops.rnc(feats_g, y_g, loss=loss, dfeats=dfeats, row_begin=lo, row_end=hi, grad_scale=w6,
-                        workspace=self.rnc_ws)
+                ops.rnc(feats_g, self.y_glob[:feats_g.shape[0]], loss=loss, dfeats=dfeats, row_begin=lo, row_end=hi,
+                        grad_scale=w6, workspace=self.rnc_ws, phase=ops.RNC_FEATURES)
             # one all_gather (features + labels) and one reduce_scatter (RnC gradient + loss + the sums of squares)
             loss_g, d_local = dp.rnc_global(rnc.contiguous(), y.contiguous(), self.pg, rnc_fn, extra=self.sums)
             self.rnc_val.copy_(loss_g)
@@ -352,8 +358,36 @@ class Trainer:
                         d_v0=d_vals[:B], d_v1=d_vals[B:], d_th1=d_th[B:], d_ct1=d_ct[B:], d_f0=d_f[:B], d_f1=d_f[B:])
         return d_vals, d_f, d_rnc, d_th, d_ct
 
+    def _rnc_labels_early(self):
+        """Everything of the Rank-N-Contrast term that depends on the labels only (the global labels, their sort, the
+        bucket index and the four boundaries of every (anchor, element) pair: most of the term's instructions) runs on a
+        side stream from the start of the step, under the forward pass; _loss_and_seeds joins it."""
+        B, W_ = self.cur_B, self.world
+        y = self.labels[:B]
+        main = torch.cuda.current_stream()
+        if self._label_stream is None:
+            self._label_stream = torch.cuda.Stream(device=self.device)
+        ls = self._label_stream
+        ls.wait_stream(main)
+        with torch.cuda.stream(ls):
+            y2 = self.y2[:2 * B]
+            y2[:B].copy_(y)
+            y2[B:].copy_(y)
+            if W_ == 1:
+                ops.rnc(None, y2, workspace=self.rnc_ws, phase=ops.RNC_LABELS)
+            else:
+                import torch.distributed as dist
+
+                from . import dp
+                y_g = self.y_glob[:W_ * 2 * B]
+                dist.all_gather_into_tensor(y_g, y2, group=self.pg)       # rank-major rows, like dp.global_views
+                lo, hi = dp.anchor_range(B, W_, self.rank)
+                ops.rnc(None, y_g, row_begin=lo, row_end=hi, workspace=self.rnc_ws, phase=ops.RNC_LABELS)
+        self._labels_ready = True
+
     def _step_body(self):
         self.step_dev.add_(1)
+        self._rnc_labels_early()
         st = self._forward(dropout=self.train_dropout, need_grad=True)
         d_vals, d_f, d_rnc, d_th, d_ct = self._loss_and_seeds(st)
         self.grads.zero_()

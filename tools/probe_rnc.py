@@ -33,3 +33,17 @@ if __name__ == "__main__":
     e1.record()
     torch.cuda.synchronize()
     print(f"RNC world={world} n={n} ms_per_step {e0.elapsed_time(e1) / 10:.3f}")
+    if "--kernels" in sys.argv:       # per-kernel durations (CUPTI through torch.profiler; the image has no nsys)
+        from collections import defaultdict
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(5):
+                go()
+            torch.cuda.synchronize()
+        tot = defaultdict(lambda: [0, 0.0])
+        for e in prof.events():
+            if e.device_type == torch.autograd.DeviceType.CUDA:
+                tot[e.name.split("(")[0][-60:]][0] += 1
+                tot[e.name.split("(")[0][-60:]][1] += e.time_range.end - e.time_range.start
+        for name, (cnt, us) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+            print(f"  {us / 5:8.1f} us/step  x{cnt // 5}  {name}")
