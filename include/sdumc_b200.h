@@ -319,7 +319,8 @@ typedef struct sdumc_rnc_args {
   int32_t phase;       /* 0: everything.  1: only the part that depends on the labels (sort, bucket index, the four
                           boundaries of every (anchor, element) pair) - a trainer runs it early, off the critical path;
                           feats / loss / dfeats may be NULL.  2: only the feature-dependent part (distances, loss,
-                          gradient), after a phase-1 call with the same labels, row range and workspace. */
+                          gradient), after a phase-1 call with the same labels, row range and workspace.
+                          3: sort + bucket index only; a phase-1 call with reuse_sort = 1 then adds the boundaries. */
 } sdumc_rnc_args;
 uint64_t sdumc_rnc_workspace_bytes(int32_t n, int32_t D);            /* all n anchor rows in one call */
 uint64_t sdumc_rnc_workspace_bytes_rows(int32_t n, int32_t D, int32_t rows); /* calls with at most `rows` anchors */

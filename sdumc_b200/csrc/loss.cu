@@ -648,7 +648,7 @@ size_t rnc_workspace_bytes(int n, int D, int rows) {
 }
 
 int launch_rnc(const RncArgs& a, cudaStream_t stream) {
-  SDUMC_CHECK_ARG(a.labels && a.workspace && (a.phase == 1 || (a.feats && a.loss)), "rnc: null pointer");
+  SDUMC_CHECK_ARG(a.labels && a.workspace && (a.phase == 1 || a.phase == 3 || (a.feats && a.loss)), "rnc: null pointer");
   SDUMC_CHECK_ARG(a.n >= 2 && a.n <= kRncMaxN, "rnc: n=%d out of range [2, %d]", a.n, kRncMaxN);
   SDUMC_CHECK_ARG(a.D > 0 && a.D % 4 == 0 && a.D <= 256, "rnc: feature dim %d unsupported", a.D);
   SDUMC_CHECK_ARG(a.row_begin >= 0 && a.row_end <= a.n && a.row_begin < a.row_end, "rnc: bad row range");
@@ -657,8 +657,9 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
   const size_t segT = align_up((size_t)(a.n + 1) * 4 + 16, 256);
   const size_t segC = align_up((size_t)rows * (size_t)a.n * 4, 256);
   const size_t need = seg * 3 + segT + segC + align_up((size_t)rows * (size_t)a.n * 8, 256);
-  const int phase = a.phase;     // 0: everything; 1: the label-only part (sort, bucket index, boundaries); 2: the rest
-  SDUMC_CHECK_ARG(phase >= 0 && phase <= 2, "rnc: phase %d (0 all, 1 labels, 2 features)", phase);
+  const int phase = a.phase;     // 0: everything; 1: the label-only part (sort, bucket index, boundaries); 2: the rest;
+                                 // 3: sort + bucket index only (then 1 with reuse_sort = the boundaries)
+  SDUMC_CHECK_ARG(phase >= 0 && phase <= 3, "rnc: phase %d (0 all, 1 labels, 2 features, 3 sort)", phase);
   SDUMC_CHECK_ARG(a.workspace_bytes >= need, "rnc: workspace %zu < %zu", a.workspace_bytes, need);
   unsigned char* ws = static_cast<unsigned char*>(a.workspace);
   int* perm = reinterpret_cast<int*>(ws);
@@ -683,6 +684,7 @@ int launch_rnc(const RncArgs& a, cudaStream_t stream) {
     SDUMC_CUDA(launch_kernel(rnc_bucket_kernel, dim3((a.n + 255) / 256), dim3(256), 0, stream, 1, ys, a.n, T, hdr));
     SDUMC_CUDA(cudaGetLastError());
   }
+  if (phase == 3) return 0;
   if (phase != 2) {
     SDUMC_CUDA(launch_kernel(rnc_bounds_kernel, dim3(rows), dim3(row_threads), (size_t)a.n * 8 + 16, stream, 1, a, ys, pos, T,
                              hdr, bounds));

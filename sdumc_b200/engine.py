@@ -280,7 +280,12 @@ class Engine:
         self._linear_bwd(W, st, name + ".0", None, x_lo_bf16, Y=None, dropped=True, dX=dX, dX_mode=dX_mode, dZ=dZ_lo)
 
     # ------------------------------------------------------------------ forward
-    def forward(self, W: Weights, inputs: Dict[str, torch.Tensor], cfg: Cfg) -> State:
+    def forward(self, W: Weights, inputs: Dict[str, torch.Tensor], cfg: Cfg, on_pools_done=None,
+                on_frames_done=None) -> State:
+        """on_pools_done() / on_frames_done() are called (on the launching stream) once the FRA2UTT_new blocks / the last
+        frame-level kernel of the forward pass have been issued: what follows is the latency-bound utterance chain A / B,
+        which leaves most SMs idle - the place for side work of the caller (the trainer forks the label-only parts of
+        the Rank-N-Contrast term there)."""
         st = State(cfg)
         G = self.G
         B, NP = cfg.B, cfg.n_pass
@@ -442,6 +447,8 @@ class Engine:
             else:
                 fu_jobs += [(fra2utt_unit, i) for i, (p_, m_) in enumerate(units) if m_ == m]
         self._parallel(len(fu_jobs), lambda j: fu_jobs[j][0](fu_jobs[j][1]))
+        if on_pools_done is not None:
+            on_pools_done()
 
         # 3'. the Cross_Attention key projections depend on the in-projections only: issued here on an auxiliary stream,
         #     they stream under utterance chain A (joined before the pooling kernels of step 4)
@@ -543,6 +550,8 @@ class Engine:
                          drop_p=FRAME_P if drop else 0.0, site=site_id(pre + ".out", p), seed=seed, step=step,
                          step_dev=cfg.step_dev, Kt=Kt, Qp=qp, qp_stride_b=NQ * G, **vl)
         self._parallel(len(units), cross_unit)
+        if on_frames_done is not None:
+            on_frames_done()
 
         # 5. utterance chain B
         c = []

@@ -225,7 +225,7 @@ def rnc_workspace_bytes(n: int, D: int, rows: int = 0) -> int:
     return int(_lib.lib().sdumc_rnc_workspace_bytes(n, D))
 
 
-RNC_ALL, RNC_LABELS, RNC_FEATURES = 0, 1, 2
+RNC_ALL, RNC_LABELS, RNC_FEATURES, RNC_SORT = 0, 1, 2, 3
 
 
 def rnc(feats, labels, *, loss=None, dfeats=None, row_begin=0, row_end=None, temperature=2.0, grad_scale=1.0,
@@ -246,7 +246,7 @@ def rnc(feats, labels, *, loss=None, dfeats=None, row_begin=0, row_end=None, tem
     a.phase = phase
     n_lab = (0 if reuse_sort else 2) + 1
     n_feat = 4 if dfeats is not None else 2
-    call("sdumc_rnc", a, launches={RNC_ALL: n_lab + n_feat, RNC_LABELS: n_lab, RNC_FEATURES: n_feat}[phase])
+    call("sdumc_rnc", a, launches={RNC_ALL: n_lab + n_feat, RNC_LABELS: n_lab, RNC_FEATURES: n_feat, RNC_SORT: 2}[phase])
 
 
 def adam(p, g, m, v, *, lr, step, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=0.0, grad_scale=1.0,

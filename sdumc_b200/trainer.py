@@ -314,11 +314,11 @@ class Trainer:
         self._staged = None
 
     # ---- the step --------------------------------------------------------------------------
-    def _forward(self, dropout: bool, need_grad: bool):
+    def _forward(self, dropout: bool, need_grad: bool, on_pools_done=None, on_frames_done=None):
         b = self.cur_B
         cfg = Cfg(B=b, n_pass=2, frames=dict(self.cur_frames), dropout=dropout, need_grad=need_grad,
                   seed=self.drop_seed, step=0, step_dev=self.step_dev)
-        return self.engine.forward(self.W, self.inputs, cfg)
+        return self.engine.forward(self.W, self.inputs, cfg, on_pools_done=on_pools_done, on_frames_done=on_frames_done)
 
     def _loss_and_seeds(self, st):
         """6-term loss (:134-148) -> self.terms, gradient seeds -> self.d_*."""
@@ -358,10 +358,13 @@ class Trainer:
                         d_v0=d_vals[:B], d_v1=d_vals[B:], d_th1=d_th[B:], d_ct1=d_ct[B:], d_f0=d_f[:B], d_f1=d_f[B:])
         return d_vals, d_f, d_rnc, d_th, d_ct
 
-    def _rnc_labels_early(self):
+    def _rnc_labels_early(self, part: int = 0):
         """Everything of the Rank-N-Contrast term that depends on the labels only (the global labels, their sort, the
         bucket index and the four boundaries of every (anchor, element) pair: most of the term's instructions) runs on a
-        side stream from the start of the step, under the forward pass; _loss_and_seeds joins it."""
+        side stream under the latency-bound utterance chains of the forward pass, which leave most SMs idle (forked at
+        the start of the step it only delays the in-projections: the big kernels want whole SMs):
+        part 1 - label all-gather (data-parallel), sort, bucket index - is forked after the FRA2UTT_new blocks (chain A),
+        part 2 - the boundaries - after the Cross_Attention blocks (chain B); part 0 = both.  _loss_and_seeds joins."""
         B, W_ = self.cur_B, self.world
         y = self.labels[:B]
         main = torch.cuda.current_stream()
@@ -371,24 +374,26 @@ class Trainer:
         ls.wait_stream(main)
         with torch.cuda.stream(ls):
             y2 = self.y2[:2 * B]
-            y2[:B].copy_(y)
-            y2[B:].copy_(y)
-            if W_ == 1:
-                ops.rnc(None, y2, workspace=self.rnc_ws, phase=ops.RNC_LABELS)
-            else:
-                import torch.distributed as dist
-
+            y_g = y2 if W_ == 1 else self.y_glob[:W_ * 2 * B]
+            lo, hi = (0, 2 * B)
+            if W_ > 1:
                 from . import dp
-                y_g = self.y_glob[:W_ * 2 * B]
-                dist.all_gather_into_tensor(y_g, y2, group=self.pg)       # rank-major rows, like dp.global_views
                 lo, hi = dp.anchor_range(B, W_, self.rank)
-                ops.rnc(None, y_g, row_begin=lo, row_end=hi, workspace=self.rnc_ws, phase=ops.RNC_LABELS)
-        self._labels_ready = True
+            if part in (0, 1):
+                y2[:B].copy_(y)
+                y2[B:].copy_(y)
+                if W_ > 1:
+                    import torch.distributed as dist
+                    dist.all_gather_into_tensor(y_g, y2, group=self.pg)       # rank-major rows, like dp.global_views
+                ops.rnc(None, y_g, row_begin=lo, row_end=hi, workspace=self.rnc_ws, phase=ops.RNC_SORT)
+            if part in (0, 2):
+                ops.rnc(None, y_g, row_begin=lo, row_end=hi, workspace=self.rnc_ws, phase=ops.RNC_LABELS, reuse_sort=True)
+                self._labels_ready = True
 
     def _step_body(self):
         self.step_dev.add_(1)
-        self._rnc_labels_early()
-        st = self._forward(dropout=self.train_dropout, need_grad=True)
+        st = self._forward(dropout=self.train_dropout, need_grad=True, on_pools_done=lambda: self._rnc_labels_early(1),
+                           on_frames_done=lambda: self._rnc_labels_early(2))
         d_vals, d_f, d_rnc, d_th, d_ct = self._loss_and_seeds(st)
         self.grads.zero_()
         if self.world == 1:
