@@ -92,6 +92,38 @@ def test_device_philox_matches_numpy():
             assert np.array_equal(fm[r, c0:c0 + 32], want_row)
 
 
+def test_rnc_phases_equal_the_single_call():
+    """sdumc_rnc split into its label-only phase(s) (sort + bucket index, boundaries) and its feature phase - what the
+    trainer runs on a side stream under the forward pass - gives the same loss and gradient as the single call,
+    for a full problem and for an anchor slice (a data-parallel rank), with tied labels; a row-sized workspace
+    (sdumc_rnc_workspace_bytes_rows) is enough for the slice."""
+    from sdumc_b200 import ops
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(11)
+    for n, D, (lo, hi) in ((600, 64, (0, 600)), (2048, 64, (512, 1024))):
+        feats = (torch.randn(n, D, device=dev, generator=g) * 0.4).contiguous()
+        y = ((torch.randn(n // 2, device=dev, generator=g).clamp(-3, 3) * 4).round() / 4).repeat(2).contiguous()
+
+        def run(phases, ws):
+            loss = torch.zeros(1, device=dev)
+            df = torch.zeros(n, D, device=dev)
+            for ph, kw in phases:
+                ops.rnc(feats if ph in (ops.RNC_ALL, ops.RNC_FEATURES) else None, y, loss=loss, dfeats=df, row_begin=lo,
+                        row_end=hi, grad_scale=0.8, workspace=ws, phase=ph, D=D, **kw)
+            return loss.clone(), df.clone()
+        ws_full = torch.empty(ops.rnc_workspace_bytes(n, D), dtype=torch.uint8, device=dev)
+        ws_rows = torch.empty(ops.rnc_workspace_bytes(n, D, rows=hi - lo), dtype=torch.uint8, device=dev)
+        assert ws_rows.numel() <= ws_full.numel()
+        l0, d0 = run([(ops.RNC_ALL, {})], ws_full)
+        l1, d1 = run([(ops.RNC_LABELS, {}), (ops.RNC_FEATURES, {})], ws_rows)
+        l2, d2 = run([(ops.RNC_SORT, {}), (ops.RNC_LABELS, {"reuse_sort": True}), (ops.RNC_FEATURES, {})], ws_rows)
+        assert float(l0) != 0.0 and torch.isfinite(d0).all()
+        for l, d in ((l1, d1), (l2, d2)):
+            # loss and gradient are accumulated with fp32 atomics (the order varies between launches): equal to rounding
+            assert abs(float(l) - float(l0)) <= 2e-6 * abs(float(l0)), (float(l), float(l0))
+            assert float((d - d0).abs().max()) <= 1e-6 * float(d0.abs().max())
+
+
 def test_rnc_kernels_at_data_parallel_size():
     """n = 4096 rows (the global Rank-N-Contrast problem of a 4-GPU job): the large-n launch configuration
     (1024-thread anchor kernel, tiled row-gradient kernel, split column kernel, shared label sort).
