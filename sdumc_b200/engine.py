@@ -303,6 +303,10 @@ class Engine:
         # modality m can run its passes as one GEMM when the passes' streams have the same shape (audio / video: the same
         # stream; text: the text and the text-substitute streams, equal in the fixed-length configurations)
         mrg = {m: drop and not varlen and len({cfg.frames[_unit_stream(p, m)] for p in range(NP)}) == 1 for m in range(3)}
+        # without input dropout the passes of a modality fed by ONE stream (audio, video) see identical frames: its
+        # FRA2UTT block and its Cross_Attention key projection are computed once and shared by the passes (scoring, the
+        # validation passes, --no_dropout training)
+        same = {m: (not drop) and NP > 1 and len({_unit_stream(p, m) for p in range(NP)}) == 1 for m in range(3)}
         if varlen:
             assert not drop and not keep, "the varlen layout is defined for eval mode (no dropout, no backward)"
         nrows: Dict[str, int] = {}
@@ -383,6 +387,11 @@ class Engine:
                 Kall = self._new(st, f"Kf.all.{m}", (NP, nr, G), torch.bfloat16) if keep else None
             for p in range(NP):
                 nr_p = nrows[_unit_stream(p, m)]
+                if same[m] and p > 0:                  # shared with pass 0 (read-only from here on)
+                    for nm in ("Sf", "Kf", "Of_pre"):
+                        if f"{nm}.0.{m}" in st.t:
+                            st.t[f"{nm}.{p}.{m}"] = st.t[f"{nm}.0.{m}"]
+                    continue
                 if merged:
                     st.t[f"Sf.{p}.{m}"] = Sall[p]
                     if keep:
@@ -445,8 +454,13 @@ class Engine:
             if mrg[m] and G == 256:
                 fu_jobs.append((fra2utt_mod, m))
             else:
-                fu_jobs += [(fra2utt_unit, i) for i, (p_, m_) in enumerate(units) if m_ == m]
+                fu_jobs += [(fra2utt_unit, i) for i, (p_, m_) in enumerate(units) if m_ == m and not (same[m] and p_ > 0)]
         self._parallel(len(fu_jobs), lambda j: fu_jobs[j][0](fu_jobs[j][1]))
+        for m in range(3):
+            if same[m]:
+                for p in range(1, NP):                  # the pooled output (and its dropout-free copy) of pass 0
+                    u_pool[m][p * B:(p + 1) * B].copy_(u_pool[m][:B])
+                    u_pool_b[m][p * B:(p + 1) * B].copy_(u_pool_b[m][:B])
         if on_pools_done is not None:
             on_pools_done()
 
@@ -456,6 +470,9 @@ class Engine:
             if mrg[m]:
                 Kall = self._new(st, f"Kc.all.{m}", (NP, nrows[_unit_stream(0, m)], G), torch.bfloat16)
             for p in range(NP):
+                if same[m] and p > 0:
+                    st.t[f"Kc.{p}.{m}"] = st.t[f"Kc.0.{m}"]
+                    continue
                 st.t[f"Kc.{p}.{m}"] = Kall[p] if mrg[m] else torch.empty(nrows[_unit_stream(p, m)], G, dtype=torch.bfloat16,
                                                                          device=dev)
 
@@ -481,7 +498,7 @@ class Engine:
             if mrg[m]:
                 kp_jobs.append((cross_keyproj_mod, m))
             else:
-                kp_jobs += [(cross_keyproj, i) for i, (p_, m_) in enumerate(units) if m_ == m]
+                kp_jobs += [(cross_keyproj, i) for i, (p_, m_) in enumerate(units) if m_ == m and not (same[m] and p_ > 0)]
         if early_k:
             self._side(lambda: [fn(x, self.overlap_ctas) for fn, x in kp_jobs])
 
