@@ -280,15 +280,16 @@ def run_ours(args):
         shapes = {"val_preds_full": (1,), "val_preds_missing": (1,), "full_rep": (128,), "missing_rep": (128,),
                   "full_rnc": (64,), "missing_rnc": (64,), "text_rep_query_full": (256,), "text_rep_query_missing": (256,),
                   "text_rep_full": (7, 128), "text_rep_missing": (7, 128)}
-        host_out = {k: torch.empty((n_mine,) + sh, dtype=torch.float32).pin_memory() for k, sh in shapes.items()}
+        import math
+        width = sum(math.prod(sh) for sh in shapes.values())
+        host_pack = torch.empty(n_mine, width, dtype=torch.float32).pin_memory()      # one packed row per utterance
 
         def infer_pass():
             lo = 0
             for c in mine:
                 tr.load_from_store(store, [i % pool for i in c])
-                out = tr.score()
-                for k in shapes:
-                    host_out[k][lo:lo + len(c)].copy_(out[k].reshape((len(c),) + shapes[k]), non_blocking=True)
+                tr.score()
+                host_pack[lo:lo + len(c)].copy_(tr.last_packed, non_blocking=True)   # all 10 outputs: one D2H copy
                 lo += len(c)
         for c in mine[:3] + mine[-1:]:              # warm-up: capture the graphs of both batch shapes
             tr.load_from_store(store, [i % pool for i in c])
@@ -301,7 +302,9 @@ def run_ours(args):
         e1.record()
         barrier()
         ms_inf = max_over_ranks(e0.elapsed_time(e1))
-        d2h = sum(v.numel() * 4 for v in host_out.values())
+        host_out = tr.unpack_scores(host_pack)
+        assert set(host_out) == set(shapes) and all(tuple(host_out[k].shape[1:]) == shapes[k] for k in shapes)
+        d2h = host_pack.numel() * 4
         inf = {"value": n_total / (ms_inf * 1e-3), "unit": "utterances/s", "utterances": n_total, "batch": bs_inf,
                "ms_total": ms_inf, "batches_per_rank": len(mine), "d2h_bytes_per_rank": d2h,
                "finite": bool(torch.isfinite(host_out["val_preds_full"]).all()),
@@ -310,7 +313,7 @@ def run_ours(args):
                             "frac": n_total / world / (ms_inf * 1e-3) * F_INFER_PER_SAMPLE / 1e12 / peaks["tc_sustained"]},
                "note": "main_frame_val_text_missing_inference path: collate from the device store + two eval passes "
                        "(graph replay) + D2H of predictions and embeddings, per batch of 128; whole job over all ranks"}
-        del store, host_out
+        del store, host_out, host_pack
         tr.load_batch(batch["audio"], batch["text"], batch["video"], batch["feat4"], batch["vals"])
 
     # ---- roofline: the step is bounded by the tensor cores (99 % of its FLOPs are dense

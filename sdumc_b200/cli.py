@@ -325,16 +325,16 @@ def main_inference(argv=None):
             "text_rep_query_full", "text_rep_query_missing", "text_rep_full", "text_rep_missing")
     results = {}
     for split_name, store in (("train", train), ("val", val), ("test", test)):
-        acc = {k: [] for k in keys}
+        acc = []                                    # one packed [b, width] row block per batch (one D2H copy each)
         labels, names = [], []
         t0 = time.time()
         for batch, vals, nm in prefetched(tr, store.batches(args.batch_size, rank, world), store):   # whole reference batches per rank
-            out = tr.score()
-            for k in keys:
-                acc[k].append(out[k].float().cpu().numpy())
+            tr.score()
+            acc.append(tr.last_packed.cpu())
             labels.append(vals.numpy())
             names += nm
-        res = {k: np.concatenate(v) for k, v in acc.items()}
+        packed = torch.cat(acc).numpy() if acc else np.zeros((0, 1), dtype=np.float32)
+        res = {k: np.ascontiguousarray(v) for k, v in tr.unpack_scores(packed).items()} if acc else {k: packed[:0] for k in keys}
         res["val_labels"], res["names"] = np.concatenate(labels), names
         if world > 1:
             # every rank scored whole reference batches (a sample's output depends on its batch's padding); put the

@@ -513,8 +513,31 @@ class Trainer:
                 "full_rnc": rnc[0], "missing_rnc": rnc[1], "text_rep_query_full": th[0].contiguous(),
                 "text_rep_query_missing": th[1].contiguous(), "text_rep_full": ct[0], "text_rep_missing": ct[1]}
 
+    SCORE_KEYS = ("val_preds_full", "val_preds_missing", "full_rep", "missing_rep", "full_rnc", "missing_rnc",
+                  "text_rep_query_full", "text_rep_query_missing", "text_rep_full", "text_rep_missing")
+
     def _score_body(self):
-        return self._score_dict(self._forward(dropout=False, need_grad=False))
+        d = self._score_dict(self._forward(dropout=False, need_grad=False))
+        self._pack_scores(d)
+        return d
+
+    def _pack_scores(self, d):
+        """All outputs of a scored batch side by side in one [b, sum of widths] fp32 tensor (part of the captured graph):
+        a caller that collects every batch on the host needs ONE device->host copy per batch instead of ten."""
+        b = d["val_preds_full"].shape[0]
+        self.score_layout = [(k, tuple(d[k].shape[1:])) for k in self.SCORE_KEYS]
+        self.last_packed = torch.cat([d[k].reshape(b, -1).float() for k in self.SCORE_KEYS], dim=1)
+
+    def unpack_scores(self, packed):
+        """Splits a (host or device, torch or numpy) [n, width] array of packed score rows into the dict of score()."""
+        out, c = {}, 0
+        for k, shp in self.score_layout:
+            w = 1
+            for x in shp:
+                w *= x
+            out[k] = packed[:, c:c + w].reshape((packed.shape[0],) + shp)
+            c += w
+        return out
 
     @torch.no_grad()
     def score_varlen(self, store, idx):
@@ -545,7 +568,9 @@ class Trainer:
             inputs[key], row_off[key] = dst, off
         cfg = Cfg(B=b, n_pass=2, frames=dict(zip(("a", "t0", "v", "t1"), frames)), dropout=False, need_grad=False,
                   seed=self.drop_seed, step=0, step_dev=self.step_dev, row_off=row_off)
-        return self._score_dict(self.engine.forward(self.W, inputs, cfg))
+        d = self._score_dict(self.engine.forward(self.W, inputs, cfg))
+        self._pack_scores(d)
+        return d
 
     @torch.no_grad()
     def score(self):
@@ -553,12 +578,14 @@ class Trainer:
         the inference CLI collects: predictions + the 4 embeddings of each pass.  Full-size batches replay a
         captured CUDA graph (~100 launches per batch otherwise dominate at the reference's inference batch of
         128): the returned tensors are then overwritten by the next score() call on the same batch shape - copy what
-        must survive.  Other recurring shapes get their own graph like train_step()."""
+        must survive.  Other recurring shapes get their own graph like train_step().  `last_packed` holds the same
+        outputs as one [b, width] tensor (see _pack_scores / unpack_scores)."""
         key = self._shape_key()[:2]
         ent = self._score_graphs.get(key)
         if ent is not None:
             self._cache_touch(self._score_graphs, key)
             ent["graph"].replay()
+            self.last_packed = ent["packed"]
             return ent["outputs"]
         seen = self._seen.get(("score",) + key, 0)
         self._seen[("score",) + key] = seen + 1
@@ -570,6 +597,6 @@ class Trainer:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             out = self._score_body()
-        self._cache_put(self._score_graphs, key, {"graph": g, "outputs": out})
+        self._cache_put(self._score_graphs, key, {"graph": g, "outputs": out, "packed": self.last_packed})
         g.replay()
         return out
