@@ -112,14 +112,14 @@ def load_splits(args):
     return tuple(stores)
 
 
-def prefetched(tr, batches, store=None):
+def prefetched(tr, batches, store=None, labels: bool = True):
     """Iterates (batch, vals, names) with the NEXT batch's host->device copy already in flight on the trainer's
     copy stream (the reference gets the same overlap from DataLoader workers + pin_memory).  A DeviceStore4F
     yields index lists instead: the batch is gathered on the device by the collate kernel."""
     from .dataset import DeviceStore4F
     if isinstance(store, DeviceStore4F):
         for idx, vals, nm in batches:
-            tr.load_from_store(store, idx)
+            tr.load_from_store(store, idx, labels=labels)
             yield idx, vals, nm
         return
     it = iter(batches)
@@ -328,7 +328,7 @@ def main_inference(argv=None):
         acc = []                                    # one packed [b, width] row block per batch (one D2H copy each)
         labels, names = [], []
         t0 = time.time()
-        for batch, vals, nm in prefetched(tr, store.batches(args.batch_size, rank, world), store):   # whole reference batches per rank
+        for batch, vals, nm in prefetched(tr, store.batches(args.batch_size, rank, world), store, labels=False):  # whole reference batches per rank
             tr.score()
             acc.append(tr.last_packed.cpu())
             labels.append(vals.numpy())

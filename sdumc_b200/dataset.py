@@ -221,7 +221,10 @@ class DeviceStore4F:
     def batch_frames(self, idx: Sequence[int]) -> Tuple[int, int, int, int]:
         """Per-modality batch maximum = the padded length the reference collater would produce (idx: utterance ids
         of the packed store, as yielded by batches())."""
-        return tuple(max(self.lengths[s][i] for i in idx) for s in STREAMS)
+        if getattr(self, "_len_np", None) is None or any(len(self._len_np[s]) != len(self.lengths[s]) for s in STREAMS):
+            self._len_np = {s: np.asarray(self.lengths[s], dtype=np.int64) for s in STREAMS}    # vectorised maxima
+        ii = np.asarray(idx, dtype=np.int64)
+        return tuple(int(self._len_np[s][ii].max()) for s in STREAMS)
 
     def batches(self, batch_size: int, rank: int = 0, world: int = 1, lockstep: bool = False) -> Iterator:
         """Same batch composition as Store4F.batches, yielding utterance-id lists (+ host labels, names)."""

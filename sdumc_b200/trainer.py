@@ -17,6 +17,7 @@ from __future__ import annotations
 
 from typing import Dict, Optional, Sequence
 
+import numpy as np
 import torch
 
 from . import _lib, ops
@@ -239,14 +240,15 @@ class Trainer:
                 ops.cast_bf16(tmp.view(-1), dst.view(-1))
         self.labels[:b].copy_(vals.reshape(-1), non_blocking=True)
 
-    def load_from_store(self, store, idx):
+    def load_from_store(self, store, idx, labels: bool = True):
         """Builds the batch `idx` of a DeviceStore4F directly in the static input buffers with the collate kernel
-        (gather + right-zero-pad to the batch maximum, read_data.py:223-248): no host->device copy of features."""
+        (gather + right-zero-pad to the batch maximum, read_data.py:223-248): no host->device copy of features.
+        labels=False skips the label gather (scoring does not read them)."""
         b = len(idx)
         if b > self.B:
             raise ValueError(f"batch of {b} exceeds the trainer's capacity {self.B}")
         frames = store.batch_frames(idx)
-        idx_dev = torch.tensor(list(idx), dtype=torch.int32).to(self.device, non_blocking=True)
+        idx_dev = torch.from_numpy(np.asarray(idx, dtype=np.int32)).to(self.device, non_blocking=True)
         self.cur_B = b
         for key, s, L in zip(("a", "t0", "v", "t1"), ("audio", "text", "video", "feat4"), frames):
             D = self.in_dims[key]
@@ -257,7 +259,8 @@ class Trainer:
             dst = self.in_flat[key][:b * L * D]
             ops.collate_pad(store.packed[s], store.offsets[s], idx_dev, L, dst)
             self.inputs[key] = dst.view(b, L, D)
-        self.labels[:b].copy_(store.vals[idx_dev.long()])
+        if labels:
+            self.labels[:b].copy_(store.vals[idx_dev.long()])
 
     def _check_stream(self, key, src, b):
         L, D = int(src.shape[1]), int(src.shape[2])
