@@ -335,14 +335,16 @@ int launch_pool_fwd(const PoolFwdArgs& a, cudaStream_t stream) {
 //   dQp^T [256 x 8 q]     += K^T[256 x 16 rows] * dS      A: ldmatrix.trans from the K tile, B: movmatrix(dS)
 //   dK  [16 x 256]         = dS[16 x 8] * Qp              A: the dP accumulator fragment, reused as operand
 //   dXv [16 x 256]         = P [16 x 8] * dO
-// 16 warps per CTA; a stage is 64 frame rows of X' and K, brought into a 2-deep shared-memory ring by per-row
-// bulk copies (rows padded to 528 B so ldmatrix is conflict-free).  Warp w works on rows 16*(w&3).. of the
-// stage and on column quarter (w>>2) of every product (4 warps per scheduler hide the dependent-chain
-// latency that bounded the 8-warp version); the only exchange inside a quartet is the 16x8 partial dP (each
-// quarter reduces over its own 64 columns) and the hand-over of finished rows to the warp that stores them.
-// dZ and the value-path gradient are written back into the tiles in place and leave through bulk
-// stores; the "+= old dH" of the accumulate mode is a bulk reduce-add performed at L2, so the old
-// gradient is never read by the SM.
+// 16 compute warps + 1 DMA warp per CTA; a stage is 64 frame rows of X' and K in a 2-deep shared-memory ring.  The
+// frame tensors are addressed through [B, L, G] tensor maps: a stage = 2 * G/64 SWIZZLE_128B boxes of 64 columns x one
+// stage of rows of ONE sample (rows past L: zero-filled on load, clipped on store), conflict-free for ldmatrix
+// without padding (chunk ^ (row & 7)).  Compute warp w works on rows 16*(w&3).. of the stage and on column quarter
+// (w>>2) = box (w>>2) of every product (4 warps per scheduler hide the dependent-chain latency that bounded the
+// 8-warp version); the only exchange inside a quartet is the 16x8 partial dP (each quarter reduces over its own 64
+// columns).  dZ and the value-path gradient are written back into the boxes in place; a warp releases the slot with
+// one mbarrier arrive, and the DMA warp - which issues every copy of the CTA - sends the boxes out with tensor stores
+// (the "+= old dH" of the accumulate mode is a tensor reduce-add performed at L2, so the old gradient is never read
+// by the SM), waits until they have read shared memory and refills the slot with the unit two ahead.
 constexpr int kBwdStages = 2;
 constexpr int kBwdThreads = 512;
 
