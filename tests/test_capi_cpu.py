@@ -50,6 +50,25 @@ def test_argument_errors_are_return_codes_not_crashes(lib):
     assert lib.sdumc_rnc(C.byref(a), None) < 0
 
 
+def test_rnc_workspace_sizes_and_phase_argument(lib):
+    """sdumc_rnc_workspace_bytes_rows: a caller with at most `rows` anchors per call (a data-parallel rank) needs the
+    label structures + rows * n coefficients and boundary quadruples, never more than the all-rows size; an unknown
+    `phase` is an argument error (return code, no CUDA call)."""
+    from sdumc_b200 import _lib
+    lib.sdumc_rnc_workspace_bytes.restype = C.c_uint64
+    lib.sdumc_rnc_workspace_bytes_rows.restype = C.c_uint64
+    n, D = 8192, 64
+    full = lib.sdumc_rnc_workspace_bytes(n, D)
+    part = lib.sdumc_rnc_workspace_bytes_rows(n, D, 1024)
+    assert lib.sdumc_rnc_workspace_bytes_rows(n, D, n) == full == lib.sdumc_rnc_workspace_bytes_rows(n, D, 0)
+    assert 1024 * n * 12 <= part <= 1024 * n * 12 + 5 * (n + 64) * 4 + 2048 < full
+    a = _lib.STRUCTS["sdumc_rnc_args"]()
+    dummy = (C.c_float * 4)()
+    a.feats = a.labels = a.loss = a.workspace = C.addressof(dummy)
+    a.n, a.D, a.row_begin, a.row_end, a.workspace_bytes, a.phase = n, D, 0, 1024, part, 7
+    assert lib.sdumc_rnc(C.byref(a), None) < 0 and b"phase" in lib.sdumc_last_error()
+
+
 def test_kernels_are_blackwell_native():
     """SASS of the shipped library: tcgen05 MMAs (UTCHMMA), TMEM loads (LDTM), TMA loads (UTMALDG)."""
     from sdumc_b200 import _lib
