@@ -122,7 +122,7 @@ def test_prefetch_iterator_stages_one_batch_ahead():
         def commit_staged(self):
             self.log.append(("commit",))
 
-        def load_from_store(self, store, idx):
+        def load_from_store(self, store, idx, labels=True):
             self.log.append(("gather", tuple(idx)))
 
     host = Store4F.synthetic(10, dims=(16, 24, 8, 24), frames=(6, 3, 4, 3), seed=1)
