@@ -675,7 +675,8 @@ class Engine:
             if s_ not in dH:
                 dH[s_] = torch.empty(B * cfg.frames[s_], G, dtype=torch.bfloat16, device=dev)
         started: Dict[str, bool] = {}
-        dQp = [z(R * NQ, G) for _ in range(3)]     # attn_bwd accumulates (a sample may be split over CTAs)
+        zq = z(4, R * NQ, G)                       # one fill for the four accumulators below
+        dQp = [zq[m] for m in range(3)]            # attn_bwd accumulates (a sample may be split over CTAs)
         # the three modalities' blocks run side by side, each on a share of the SMs proportional to its frames
         mod_share = _shares({m: cfg.frames[_unit_stream(0, m)] for m in range(3)}) if self.sm_shares else {}
 
@@ -711,7 +712,7 @@ class Engine:
             # ... so they stream under the latency-bound backward chain B7-B9 (joined before the early gradient bucket)
             self._side(lambda: [fn(self.overlap_ctas) for fn, _ in deferred], *[k for _, ks in deferred for k in ks])
         # B7. query projections -> dQ
-        dQ = z(R * NQ, G)                            # the three blocks add their share side by side (fp32 reds)
+        dQ = zq[3]                                   # the three blocks add their share side by side (fp32 reds)
         self._parallel(3, lambda m: self._linear_bwd(W, st, f"cross_att_fra2utt_{m}.query_proj", dQp[m],
                                                      t["Q_bf16"].view(R * NQ, G), Y=None, dropped=False, dX=dQ,
                                                      dX_mode=ops.OUT_ATOMIC))

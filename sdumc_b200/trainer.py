@@ -98,13 +98,19 @@ class Trainer:
         # device-resident scalars (CUDA-graph replay)
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)      # optimisation step, 1-based after the bump
         self.lr_dev = torch.full((1,), self.lr, dtype=torch.float32, device=dev)
-        self.sums = z(8)
         self.terms = z(8)
-        self.rnc_val = z(1)
         R = 2 * B
-        self.d_vals, self.d_f, self.d_rnc = z(R), z(R * 128).view(R, 128), z(R * 64).view(R, 64)
         Gd = self.layout.G
-        self.d_th, self.d_ct = z(R * Gd).view(R, Gd), z(R * 896).view(R, 896)
+        # accumulators that every step starts from zero live side by side: ONE fill per step instead of five
+        self._zero_block = z(16 + R * 64 + R * Gd + R * 896)
+        zb, o = self._zero_block, 16
+        self.sums, self.rnc_val = zb[:8], zb[8:9]
+        self.d_rnc = zb[o:o + R * 64].view(R, 64)
+        o += R * 64
+        self.d_th = zb[o:o + R * Gd].view(R, Gd)
+        o += R * Gd
+        self.d_ct = zb[o:o + R * 896].view(R, 896)
+        self.d_vals, self.d_f = z(R), z(R * 128).view(R, 128)
         self.y2 = z(R)
         n_g = 2 * B * self.world
         self.rnc_ws = torch.empty(ops.rnc_workspace_bytes(n_g, 64, rows=2 * B), dtype=torch.uint8, device=dev)
@@ -332,12 +338,8 @@ class Trainer:
         R = 2 * B
         d_vals, d_f, d_rnc, d_th, d_ct, y2 = (self.d_vals[:R], self.d_f[:R], self.d_rnc[:R], self.d_th[:R],
                                               self.d_ct[:R], self.y2[:R])
-        d_th.zero_()
-        d_ct.zero_()
-        self.sums.zero_()
+        self._zero_block.zero_()                                  # sums, rnc_val, d_rnc, d_th, d_ct
         ops.loss_sums(vals[0], vals[1], y, th[0], th[1], ct[0], ct[1], f[0], f[1], B=B, sums=self.sums)
-        self.rnc_val.zero_()
-        d_rnc.zero_()
         w6 = self.loss_w[5]
         if not self._labels_ready:                                        # (a caller that skipped _step_body)
             self._rnc_labels_early()
