@@ -70,11 +70,15 @@ def test_rnc_workspace_sizes_and_phase_argument(lib):
 
 
 def test_kernels_are_blackwell_native():
-    """SASS of the shipped library: tcgen05 MMAs (UTCHMMA), TMEM loads (LDTM), TMA loads (UTMALDG)."""
+    """SASS of the shipped library: tcgen05 MMAs (UTCHMMA, the CTA-pair form .2CTA), TMEM loads (LDTM), TMA loads
+    (UTMALDG 2-D for the GEMMs, 3-D for the attention backward), tensor stores and the L2-side tensor reduce-add of the
+    attention backward (UTMASTG / UTMAREDG), programmatic dependent launch (ACQBULK = griddepcontrol.wait, PREEXIT =
+    griddepcontrol.launch_dependents)."""
     from sdumc_b200 import _lib
     sass = subprocess.run(["cuobjdump", "-sass", str(_lib.LIB_PATH)], capture_output=True, text=True).stdout
     assert "sm_100a" in sass
-    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG", "UTCBAR"):
+    for mnemonic in ("UTCHMMA", "UTCHMMA.2CTA", "LDTM", "UTMALDG.2D", "UTMALDG.3D", "UTMASTG.3D", "UTMAREDG.3D.ADD",
+                     "UTCBAR", "UTCBAR.2CTA.MULTICAST", "ACQBULK", "PREEXIT"):
         assert mnemonic in sass, mnemonic
     assert "HGMMA" not in sass
 
