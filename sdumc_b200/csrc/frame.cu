@@ -571,8 +571,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   for (int k = 0; k < my_units; ++k) {
     const int u = u_begin + k;
     const int ub = u / n_iter, it = u - ub * n_iter;
-    if (ub != b) {                                    // uniform over the compute warps; flush_dqp's barriers separate the samples
-      if (b >= 0) flush_dqp(b);
+    if (ub != b) {                                    // uniform over the compute warps; the barriers separate the samples
+      if (b >= 0) {
+        // per-sample queries: the finished sample's dQp leaves now; a query shared by all samples (FRA2UTT context
+        // vector) keeps accumulating in the fragments and leaves once, at the end
+        if (a.qp_stride_b != 0) flush_dqp(b);
+        else compute_sync();                          // every warp is done with the old sample's shared-memory operands
+      }
       b = ub;
       load_sample(b);
     }
