@@ -120,8 +120,8 @@ def test_rnc_phases_equal_the_single_call():
         assert float(l0) != 0.0 and torch.isfinite(d0).all()
         for l, d in ((l1, d1), (l2, d2)):
             # loss and gradient are accumulated with fp32 atomics (the order varies between launches): equal to rounding
-            assert abs(float(l) - float(l0)) <= 2e-6 * abs(float(l0)), (float(l), float(l0))
-            assert float((d - d0).abs().max()) <= 1e-6 * float(d0.abs().max())
+            assert abs(float(l) - float(l0)) <= 1e-5 * abs(float(l0)), (float(l), float(l0))
+            assert float((d - d0).abs().max()) <= 5e-6 * float(d0.abs().max())
 
 
 def test_rnc_kernels_at_data_parallel_size():
