@@ -59,6 +59,8 @@ typedef struct sdumc_gemm_desc {
   float drop_p; /* element dropout after the activation */
   uint32_t drop_site;
   uint32_t fmask_site; /* != 0: multiply by the p=0.5 frame mask of this site */
+  uint32_t fmask_site2; /* with fmask_split > 0: rows >= fmask_split take the mask of this site at row r - fmask_split */
+  int64_t fmask_split;  /* (two tensors with their own dropout sites stacked along M: the passes of a modality) */
   float* out_f32;
   int64_t ld_f32;
   int32_t f32_mode;
@@ -166,6 +168,11 @@ typedef struct sdumc_attn_bwd_args {
   int32_t G;            /* general_dim: 0 or 256 (reference), or 1024 */
   int32_t max_ctas;     /* 0 = one persistent CTA per SM; > 0: at most this many (a share of the GPU, so that the
                            blocks of several modalities run side by side) */
+  int32_t split_b;      /* > 0: two problems with their own dropout sites stacked along B (the passes of a modality):
+                           samples >= split_b use out_site2 / fmask_site2 with the sample index b - split_b */
+  uint32_t out_site2;
+  uint32_t fmask_site2;
+  uint32_t reserved2;
 } sdumc_attn_bwd_args;
 int sdumc_attn_bwd(const sdumc_attn_bwd_args* a, void* stream);
 

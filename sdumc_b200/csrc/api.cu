@@ -49,7 +49,10 @@ int sdumc_gemm(const sdumc_gemm_desc* d, void* stream) {
   ep.act = d->act;
   ep.gate = d->gate; ep.ld_gate = d->ld_gate; ep.gate_scale = d->gate_scale;
   ep.drop_p = d->drop_p; ep.drop_site = d->drop_site;
-  ep.fmask_site = d->fmask_site;
+  ep.fmask_site = d->fmask_site; ep.fmask_site2 = d->fmask_site2; ep.fmask_split = d->fmask_split;
+  SDUMC_CHECK_ARG(d->fmask_split == 0 || (d->fmask_site && d->fmask_site2 && d->fmask_split > 0 && d->out_bf16 &&
+                                          d->bf16_mode == 1 && d->epi_kind == 0),
+                  "sdumc_gemm: fmask_split is defined for the bf16 '+=' output with a frame mask (dH accumulation)");
   ep.out_f32 = d->out_f32; ep.ld_f32 = d->ld_f32; ep.f32_mode = d->f32_mode;
   ep.out_bf16 = static_cast<__nv_bfloat16*>(d->out_bf16); ep.ld_bf16 = d->ld_bf16; ep.bf16_mode = d->bf16_mode;
   ep.n_tgt = d->n_tgt;

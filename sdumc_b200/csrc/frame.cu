@@ -500,9 +500,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const int q = (i * 4) / G, g = (i * 4) & (G - 1);
         float d[4] = {dv[j].x, dv[j].y, dv[j].z, dv[j].w};
         if (a.out_drop_p > 0.f) {
-          // four consecutive elements share one Philox counter (elem_rand: counter e >> 2, word e & 3)
-          const uint32_t e = (uint32_t)b * (uint32_t)(NQ * G) + (uint32_t)(i * 4);
-          const U4 r = philox4x32_10(e >> 2, 0x5D0Cu, a.out_site, key.step, key.seed_lo, key.seed_hi);
+          // four consecutive elements share one Philox counter (elem_rand: counter e >> 2, word e & 3); stacked passes
+          // (split_b): the second problem draws from its own site with its own sample index
+          const bool second = a.split_b > 0 && b >= a.split_b;
+          const uint32_t e = (uint32_t)(second ? b - a.split_b : b) * (uint32_t)(NQ * G) + (uint32_t)(i * 4);
+          const U4 r = philox4x32_10(e >> 2, 0x5D0Cu, second ? a.out_site2 : a.out_site, key.step, key.seed_lo, key.seed_hi);
           d[0] = r.x >= thr ? d[0] * oscale : 0.f; d[1] = r.y >= thr ? d[1] * oscale : 0.f;
           d[2] = r.z >= thr ? d[2] * oscale : 0.f; d[3] = r.w >= thr ? d[3] * oscale : 0.f;
         }
@@ -649,8 +651,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       // them by shuffle - the four lanes of a row group used to draw the same two rows each)
       U4 ma, mb;
       if (a.fmask_site) {
-        const uint32_t r0 = (uint32_t)((long)b * L + l0);
-        const U4 mine = frame_mask_words(key, a.fmask_site, r0 + (uint32_t)(lane & 15), (uint32_t)(hc >> 7));
+        const bool second = a.split_b > 0 && b >= a.split_b;
+        const uint32_t r0 = (uint32_t)((long)(second ? b - a.split_b : b) * L + l0);
+        const U4 mine = frame_mask_words(key, second ? a.fmask_site2 : a.fmask_site, r0 + (uint32_t)(lane & 15),
+                                         (uint32_t)(hc >> 7));
         ma.x = __shfl_sync(0xffffffffu, mine.x, gid);     mb.x = __shfl_sync(0xffffffffu, mine.x, gid + 8);
         ma.y = __shfl_sync(0xffffffffu, mine.y, gid);     mb.y = __shfl_sync(0xffffffffu, mine.y, gid + 8);
         ma.z = __shfl_sync(0xffffffffu, mine.z, gid);     mb.z = __shfl_sync(0xffffffffu, mine.z, gid + 8);

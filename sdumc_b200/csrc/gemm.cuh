@@ -44,6 +44,8 @@ struct GemmEpi {
   float drop_p;  // element dropout after activation, index e = r * N + n
   uint32_t drop_site;
   uint32_t fmask_site;  // != 0: v *= 2 * framebit(site, r, n)
+  uint32_t fmask_site2; // rows >= fmask_split (> 0): framebit(site2, r - fmask_split, n)
+  long fmask_split;
   float* out_f32;
   long ld_f32;
   int f32_mode;
@@ -507,7 +509,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
         if constexpr (kKind == KIND_RMW) {   // dH += acc * frame mask
           if (ep.fmask_site) {
-            const U4 w4 = frame_mask_words(key, ep.fmask_site, (uint32_t)r, (uint32_t)(n0 >> 7));
+            const bool second = ep.fmask_split > 0 && r >= ep.fmask_split;   // stacked passes: own site, own row count
+            const U4 w4 = frame_mask_words(key, second ? ep.fmask_site2 : ep.fmask_site,
+                                           (uint32_t)(second ? r - ep.fmask_split : r), (uint32_t)(n0 >> 7));
             const int wsel = (n0 >> 5) & 3;
             const uint32_t bits = wsel == 0 ? w4.x : (wsel == 1 ? w4.y : (wsel == 2 ? w4.z : w4.w));
 #pragma unroll
@@ -552,7 +556,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           }
         }
         if (ep.fmask_site) {
-          const U4 w4 = frame_mask_words(key, ep.fmask_site, (uint32_t)r, (uint32_t)(n0 >> 7));
+          const bool second = ep.fmask_split > 0 && r >= ep.fmask_split;
+          const U4 w4 = frame_mask_words(key, second ? ep.fmask_site2 : ep.fmask_site,
+                                         (uint32_t)(second ? r - ep.fmask_split : r), (uint32_t)(n0 >> 7));
           const int wsel = (n0 >> 5) & 3;
           const uint32_t bits = wsel == 0 ? w4.x : (wsel == 1 ? w4.y : (wsel == 2 ? w4.z : w4.w));
 #pragma unroll

@@ -400,7 +400,12 @@ class Engine:
                     self._new(st, f"Sf.{p}.{m}", (nr_p, 1))
                     if keep:
                         self._new(st, f"Kf.{p}.{m}", (nr_p, G), torch.bfloat16)
-                self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
+                if merged:
+                    if p == 0:
+                        self._new(st, f"Of_pre.all.{m}", (NP, B, 1, G))
+                    st.t[f"Of_pre.{p}.{m}"] = st.t[f"Of_pre.all.{m}"][p]
+                else:
+                    self._new(st, f"Of_pre.{p}.{m}", (B, 1, G))
 
         unit_share = _shares({i: cfg.frames[_unit_stream(p, m)] for i, (p, m) in enumerate(units)}) if self.sm_shares else {}
 
@@ -545,8 +550,15 @@ class Engine:
         for (p, m) in units:
             L = cfg.frames[_unit_stream(p, m)]
             nr = nrows[_unit_stream(p, m)]
-            self._new(st, f"Sc.{p}.{m}", (nr, NQ))
-            self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
+            if mrg[m]:                                   # pass-contiguous (the stacked backward of a modality, see backward)
+                if p == 0:
+                    self._new(st, f"Sc.all.{m}", (NP, nr, NQ))
+                    self._new(st, f"Oc_pre.all.{m}", (NP, B, NQ, G))
+                st.t[f"Sc.{p}.{m}"] = st.t[f"Sc.all.{m}"][p]
+                st.t[f"Oc_pre.{p}.{m}"] = st.t[f"Oc_pre.all.{m}"][p]
+            else:
+                self._new(st, f"Sc.{p}.{m}", (nr, NQ))
+                self._new(st, f"Oc_pre.{p}.{m}", (B, NQ, G))
         if early_k:
             self._join_side()
         else:
@@ -670,10 +682,21 @@ class Engine:
         self._parallel(3, cross_mlp_bwd)
         # B6. Cross_Attention blocks
         dH: Dict[str, torch.Tensor] = {}
+        # a modality whose passes read DIFFERENT streams (text / text substitute) has one dH per pass: with pass-contiguous
+        # tensors (forward) both passes of a block run as ONE attn_bwd + ONE dH GEMM over 2B samples, each half with its
+        # own dropout sites (split_b / fmask_split) - the short text launches are dominated by their fixed cost
+        stacked = {m: NP == 2 and f"Xc.all.{m}" in t and f"Kf.all.{m}" in t and
+                   len({_unit_stream(p, m) for p in range(NP)}) == NP for m in range(3)}
+        dH_all: Dict[int, torch.Tensor] = {}
         for (p, m) in units:                       # one dH per input stream, written first by the cross block
             s_ = _unit_stream(p, m)
             if s_ not in dH:
-                dH[s_] = torch.empty(B * cfg.frames[s_], G, dtype=torch.bfloat16, device=dev)
+                if stacked[m]:
+                    if m not in dH_all:
+                        dH_all[m] = torch.empty(NP, B * cfg.frames[s_], G, dtype=torch.bfloat16, device=dev)
+                    dH[s_] = dH_all[m][p]
+                else:
+                    dH[s_] = torch.empty(B * cfg.frames[s_], G, dtype=torch.bfloat16, device=dev)
         started: Dict[str, bool] = {}
         zq = z(4, R * NQ, G)                       # one fill for the four accumulators below
         dQp = [zq[m] for m in range(3)]            # attn_bwd accumulates (a sample may be split over CTAs)
@@ -696,7 +719,10 @@ class Engine:
         dZc = [new_dz(m) for m in range(3)]
 
         def cross_attn_bwd(m):                     # passes of one modality accumulate into the same dH: in order
-            for p in range(NP):
+            if stacked[m]:
+                self._attn_block_bwd_stacked(W, st, m, "cross_att_fra2utt", NQ, dOut=dC[m], Qp=t[f"Qp.{m}"],
+                                             qp_stride=NQ * G, dQp=dQp[m], dH_all=dH_all[m], started=started, dZ=dZc[m])
+            for p in range(NP if not stacked[m] else 0):
                 self._attn_block_bwd(W, st, p, m, "cross_att_fra2utt", NQ, dOut=dC[m][p * B * NQ:(p + 1) * B * NQ],
                                      Qp=t[f"Qp.{m}"][p * B * NQ:(p + 1) * B * NQ], qp_stride=NQ * G,
                                      dQp=dQp[m][p * B * NQ:(p + 1) * B * NQ], dH=dH, started=started,
@@ -750,7 +776,12 @@ class Engine:
 
         def fra2utt_bwd(m):
             pre = f"fra2utt_{m}"
-            for p in range(NP):
+            if stacked[m]:
+                self._attn_block_bwd_stacked(W, st, m, "fra2utt", 1, dOut=du[m],
+                                             Qp=W.f32(pre + ".attention_context_vector"), qp_stride=0,
+                                             dQp=W.grad(pre + ".attention_context_vector"), dH_all=dH_all[m],
+                                             started=started, dZ=dZf[m])
+            for p in range(NP if not stacked[m] else 0):
                 self._attn_block_bwd(W, st, p, m, "fra2utt", 1, dOut=du[m][p * B:(p + 1) * B],
                                      Qp=W.f32(pre + ".attention_context_vector"), qp_stride=0,
                                      dQp=W.grad(pre + ".attention_context_vector"), dH=dH, started=started,
@@ -773,6 +804,32 @@ class Engine:
             ops.colsum_bf16(dHs, W.grad(wname + ".bias"))
         self._parallel(len(items), inproj_bwd)
         self._join_side()
+
+    def _attn_block_bwd_stacked(self, W: Weights, st: State, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
+                                dH_all: torch.Tensor, started: Dict[str, bool], dZ: torch.Tensor):
+        """Both passes of one attention block of a modality whose passes have their own streams (and their own dH):
+        ONE attn_bwd over 2B samples and ONE dH GEMM over 2*B*L rows; samples / rows of pass 1 use their own dropout
+        sites with their own sample / row index (split_b, fmask_split).  The weight gradient is the caller's."""
+        cfg = st.cfg
+        G, t, B, NP = self.G, st.t, cfg.B, cfg.n_pass
+        L = cfg.frames[_unit_stream(0, m)]
+        tag, pre = blk[0], f"{blk}_{m}"
+        rows = NP * B * L
+        first = not started.get(_unit_stream(0, m), False)
+        for p in range(NP):
+            started[_unit_stream(p, m)] = True
+        fm = [site_id(pre + ".in", p) for p in range(NP)]
+        om = [site_id(pre + ".out", p) for p in range(NP)]
+        ops.attn_bwd(t[f"X{tag}.all.{m}"].view(rows, G), t[f"K{tag}.all.{m}"].view(rows, G),
+                     t[f"S{tag}.all.{m}"].view(rows, nq), dOut, dout_stride_b=nq * G,
+                     O_pre=t[f"O{tag}_pre.all.{m}"].view(NP * B, nq, G), Qp=Qp, qp_stride_b=qp_stride, B=NP * B, L=L, nq=nq,
+                     out_drop_p=FRAME_P, out_site=om[0], dZ=dZ.view(rows, G), dH=dH_all.view(rows, G),
+                     dh_mode=0 if first else 1, fmask_site=fm[0], dQp=dQp, dqp_stride_b=nq * G,
+                     db=W.grad(pre + ".input_proj.bias"), seed=cfg.seed, step=cfg.step, step_dev=cfg.step_dev,
+                     split_b=B, out_site2=om[1], fmask_site2=fm[1])
+        ops.gemm(dZ.view(rows, G), W.bf16(pre + ".input_proj.weight"), M=rows, N=G, K=G, b_mn=True, fmask_site=fm[0],
+                 fmask_site2=fm[1], fmask_split=B * L, out_bf16=dH_all.view(rows, G), bf16_mode=ops.OUT_ADD, seed=cfg.seed,
+                 step=cfg.step, step_dev=cfg.step_dev)
 
     def _attn_block_bwd(self, W: Weights, st: State, p: int, m: int, blk: str, nq: int, *, dOut, Qp, qp_stride, dQp,
                         dH: Dict[str, torch.Tensor], started: Dict[str, bool], max_ctas: int = 0, defer_dw=None,

@@ -23,7 +23,8 @@ def _ld(t: torch.Tensor) -> int:
 def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_mn=False, b_mn=False, k_splits=1,
          block_n=0, max_ctas=0, bias=None, act=ACT_NONE, gate=None, gate_scale=1.0, drop_p=0.0, drop_site=0,
          fmask_site=0, out_f32=None, f32_mode=OUT_STORE, out_bf16=None, bf16_mode=OUT_STORE, epi_kind=EPI_GENERIC,
-         targets=(), target_sites=(), qv=None, q_stride=0, nq=0, L=1, scores=None, seed=0, step=0, step_dev=None) -> None:
+         targets=(), target_sites=(), qv=None, q_stride=0, nq=0, L=1, scores=None, seed=0, step=0, step_dev=None,
+         fmask_site2=0, fmask_split=0) -> None:
     """C[M,N] = epilogue(op(A) op(B)) — tcgen05/TMA GEMM.
 
     A is stored [M,K] (a_mn=False) or [K,M]; B is stored [N,K] (b_mn=False, the nn.Linear weight
@@ -40,6 +41,7 @@ def gemm(A: torch.Tensor, B: torch.Tensor, *, M: int, N: int, K: int, a_mn=False
     d.bias = ptr(bias)
     d.gate, d.ld_gate, d.gate_scale = ptr(gate), (_ld(gate) if gate is not None else 0), gate_scale
     d.drop_p, d.drop_site, d.fmask_site = drop_p, drop_site, fmask_site
+    d.fmask_site2, d.fmask_split = fmask_site2, fmask_split
     d.out_f32, d.ld_f32, d.f32_mode = ptr(out_f32), (_ld(out_f32) if out_f32 is not None else 0), f32_mode
     d.out_bf16, d.ld_bf16, d.bf16_mode = ptr(out_bf16), (_ld(out_bf16) if out_bf16 is not None else 0), bf16_mode
     d.n_tgt = len(targets)
@@ -107,7 +109,8 @@ def pool_fwd(X, S, *, B, L, nq, O_pre, out, out_stride_b, out_bf16=None, drop_p=
 
 
 def attn_bwd(X, Kt, P, dOut, *, dout_stride_b, O_pre, Qp, qp_stride_b, B, L, nq, out_drop_p, out_site, dZ, dH,
-             dh_mode, fmask_site, dQp, dqp_stride_b, db, seed=0, step=0, step_dev=None, alpha=0.3, max_ctas=0) -> None:
+             dh_mode, fmask_site, dQp, dqp_stride_b, db, seed=0, step=0, step_dev=None, alpha=0.3, max_ctas=0,
+             split_b=0, out_site2=0, fmask_site2=0) -> None:
     a = STRUCTS["sdumc_attn_bwd_args"]()
     a.X, a.ldx, a.Kt, a.ldk, a.P = ptr(X), _ld(X), ptr(Kt), _ld(Kt), ptr(P)
     a.dOut, a.dout_stride_b, a.O_pre = ptr(dOut), dout_stride_b, ptr(O_pre)
@@ -115,6 +118,7 @@ def attn_bwd(X, Kt, P, dOut, *, dout_stride_b, O_pre, Qp, qp_stride_b, B, L, nq,
     a.B, a.L, a.nq, a.alpha = B, L, nq, alpha
     a.out_drop_p, a.out_site = out_drop_p, out_site
     a.dZ, a.lddz, a.dH, a.lddh, a.dh_mode, a.fmask_site = ptr(dZ), _ld(dZ), ptr(dH), _ld(dH), dh_mode, fmask_site
+    a.split_b, a.out_site2, a.fmask_site2 = split_b, out_site2, fmask_site2
     a.dQp, a.dqp_stride_b, a.db = ptr(dQp), dqp_stride_b, ptr(db)
     a.key = dropkey(seed, step, step_dev)
     a.G = X.shape[1]

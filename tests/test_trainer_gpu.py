@@ -60,6 +60,77 @@ def test_train_steps_follow_the_oracle():
             assert total > 1000 and agree / total > 0.995, (agree, total)
 
 
+def _fused_step_masks(tr, b, frames, p):
+    """The dropout masks pass p of the fused step that just ran was computed with, keyed by the oracle's site names and
+    shaped like the tensors the oracle drops.  Frame-level and pooled-output sites are per pass (rows / samples of the
+    pass); the utterance-level MLP sites are shared by the passes, which are rows p*b.. of ONE batch of 2b rows."""
+    from sdumc_b200 import ops
+    from sdumc_b200.engine import FRAME_P, MLP_P, dropout_site_names, site_id
+    seed, step = tr.drop_seed, int(tr.step_dev.item())
+    G = tr.layout.G
+    La, Lt, Lv, L4 = frames
+    Ls = (La, Lt if p == 0 else L4, Lv)
+    R = 2 * b
+    masks = {}
+    for name in dropout_site_names():
+        if name.endswith(".in"):
+            m = int(name.split(".")[0][-1])
+            masks[name] = ops.frame_mask(seed, step, site_id(name, p), b * Ls[m], G).view(b, Ls[m], G)
+        elif name.endswith(".out"):
+            nq = 1 if name.startswith("fra2utt") else 7
+            mk = ops.elem_mask(seed, step, site_id(name, p), b * nq * G, FRAME_P).view(b, nq, G)
+            masks[name] = mk[:, 0] if nq == 1 else mk
+        else:
+            base, idx = name.rsplit(".", 1)
+            seven = base.startswith("cross_") and base.endswith("_mlp") and base != "cross_attention_mlp" and "query" not in base
+            width = {"cross_audio_mlp": (256, 128), "cross_text_mlp": (256, 128), "cross_video_mlp": (256, 128),
+                     "cross_attention_mlp": (256, 128)}.get(base, (G, G))[int(idx)]
+            rows = R * 7 if seven else R
+            mk = ops.elem_mask(seed, step, site_id(name, 0), rows * width, MLP_P).view(rows, width)
+            masks[name] = mk[p * b * 7:(p + 1) * b * 7].view(b, 7, width) if seven else mk[p * b:(p + 1) * b]
+    return {k: v.double().cpu() for k, v in masks.items()}
+
+
+@pytest.mark.parametrize("frames", [(48, 16, 32, 16), (48, 16, 32, 12)], ids=["equal_text_lengths", "ragged_text_lengths"])
+def test_fused_dropout_step_matches_the_oracle_with_replayed_masks(frames):
+    """The fused two-pass step WITH dropout against the fp64 oracle fed the very masks the kernels drew (materialised
+    through the C ABI's mask hooks): the six loss terms and every live gradient.  With equal text / text-substitute
+    lengths the step takes the pass-merged GEMMs and the stacked two-pass backward (two dropout sites per launch);
+    with different lengths the per-pass launches.  A mask applied with the wrong site, row or sample index anywhere
+    between the forward and the backward pass moves the in-projection / block gradients by O(1)."""
+    from sdumc_b200.trainer import Trainer
+    dev = torch.device("cuda", 0)
+    P = O.init_params(DIMS, seed=100, gain=1.0, dtype=torch.float64)
+    batch = O.synth_batch(B, DIMS, frames, seed=9)
+    b64 = {k: (v.bfloat16().double() if k != "vals" else v.double()) for k, v in batch.items()}
+    tr = Trainer(DIMS, B, frames, dev, state_dict={k: v.float() for k, v in P.items()}, use_graph=False)
+    assert tr.train_dropout
+    _load(tr, batch)
+    tr.train_step()
+    torch.cuda.synchronize()
+    drops = [O.make_drop_from_masks(_fused_step_masks(tr, B, frames, p)) for p in range(2)]
+    _, terms, grads, _ = O.loss_and_grads(P, b64["audio"], b64["text"], b64["feat4"], b64["video"], b64["vals"], None,
+                                          drops[0], drops[1])
+    got = tr.terms.tolist()
+    for i, name in enumerate(TERMS):
+        ref = float(terms[name])
+        assert abs(got[i] - ref) <= 2e-2 * max(1.0, abs(ref)), (name, got[i], ref)
+    # gradients: free ReLU pattern (no emulation, nothing pinned): the same canary bound as
+    # tests/test_unemulated_gpu.py - a mask mismatch costs ~1.0, bf16 rounding + ReLU flips ~0.1
+    worst = {}
+    gmax = max(float(g.norm()) for g in grads.values() if g is not None)
+    for name, g in grads.items():
+        if g is None:
+            continue
+        mine = tr.layout.view(tr.grads, name).double().cpu()
+        # (the bias of the RnC head has an exactly zero gradient - distances do not see a shift: absolute floor)
+        worst[name] = float((mine - g).norm() / g.norm().clamp_min(1e-6 * gmax))
+    bad = {k: v for k, v in worst.items() if not v <= 0.5}
+    assert len(worst) == 83 and not bad, "gradient L2 error: " + ", ".join(f"{k}={v:.3g}" for k, v in sorted(bad.items()))
+    frame_level = [v for k, v in worst.items() if k.startswith(("frame_dim_reshape_", "fra2utt_", "cross_att_fra2utt_"))]
+    assert max(frame_level) <= 0.25, sorted(worst.items(), key=lambda kv: -kv[1])[:5]
+
+
 def test_graph_replay_equals_eager():
     """The captured CUDA graph (steps 3+) reproduces the eager step: same loss terms and parameters up to the
     non-deterministic order of the split-K / bias atomics."""
